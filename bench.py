@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- Poisson CG iterations/s (and HBM GB/s) of the B200 backend, 3-D 256^3 fp64.
+
+    python bench.py --gpus N --steps K --warmup W            # own arm (N>1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: KSP restatement on the host cores
+
+A "step" is one KSPSolve through the LinSolver interface: zero initial guess, fixed iteration count
+(rtol = atol = 0, max_it = --iters), on the synthetic problem of SURVEY.md section 8(d): uniform 256^3 on
+[0,1]^3, all-Dirichlet velocity BCs (homogeneous-Neumann, singular pressure system, constant null
+space attached), dt = 0.01, b = A x*, x* ~ N(0,1) seeded, mean removed.
+
+`value` is CG iterations/s of the whole job with b and x resident in HBM (device events, max over
+ranks); `e2e` is the same metric through LinSolverB200.solve with pinned HOST buffers (H2D of b and D2H of
+x inside the timed region).  `roofline` is for the dominant kernel (k_spmv: deferred x update + search
+direction + 7-point stencil + dot, 48 algorithmic B/row) from per-launch CUDA events recorded inside the
+timed region on the solver's stream.  `cpu_baseline` is the oracle (KSP restatement, PETSc-style unfused
+passes over an assembled CSR) on the host cores, on a bounded number of iterations of the same problem."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "poisson_cg_iterations_per_second"
+UNIT = "iterations/s"
+SEED = 20240521
+K1_BYTES_PER_ROW = 48.0   # read r,p',x ; write p,w,x
+K2_BYTES_PER_ROW = 24.0   # read r,w ; write r
+ITER_BYTES_PER_ROW = K1_BYTES_PER_ROW + K2_BYTES_PER_ROW
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, nargs="+", default=[256, 256, 256])
+    ap.add_argument("--iters", type=int, default=500, help="CG iterations per solve (step)")
+    ap.add_argument("--pc", default="none", choices=["none", "jacobi"])
+    ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--halo", default="store", choices=["store", "memcpy"])
+    ap.add_argument("--no-profile", action="store_true", help="no per-kernel events (CUDA-graph batches instead)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-iters", type=int, default=0, help="iterations of the CPU sample (0 = auto)")
+    ap.add_argument("--tune", nargs="*", default=[], help="key=value launch knobs (kz_chunk, tile, upd_blocks)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def workload_name(n, iters, pc):
+    return (f"3D {n[0]}x{n[1]}x{n[2]} uniform staggered-grid pressure Poisson D(dt I)G, fp64, KSP CG, pc {pc}, "
+            f"constant null space, {iters} iterations per solve")
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_record():
+    """DRAM bytes per launch of k_spmv from the committed ncu capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(n, iters, steps, warmup, pc):
+    """The oracle's KSP CG (PETSc-style unfused passes over the assembled CSR) on all host threads.
+    Returns (iterations/s, threads, seconds per step, description)."""
+    from oracle import oracle as orc
+
+    threads = orc.max_threads()
+    orc.set_fast(True, threads)
+    widths = [np.full(m, 1.0 / m) for m in n]
+    t0 = time.perf_counter()
+    A = orc.assemble_dbng(widths, (0, 0, 0), 0.01, literal=False)
+    t_asm = time.perf_counter() - t0
+    rng = np.random.default_rng(SEED)
+    xs = rng.standard_normal(A.shape[0])
+    xs -= xs.mean()
+    b = A.spmv(xs)
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        res = orc.ksp_solve(A, b, pc_type=pc, rtol=0.0, atol=0.0, max_it=iters, const_nullspace=True)
+        dt = time.perf_counter() - t0
+        assert res.its == iters
+        if s >= warmup:
+            times.append(dt)
+    orc.set_fast(False, 0)
+    per_step = float(np.mean(times))
+    return iters / per_step, threads, per_step, f"{iters} CG iterations of the same {n[0]}x{n[1]}x{n[2]} system (CSR assembly {t_asm:.1f} s not timed)"
+
+
+def auto_cpu_iters(n):
+    # ~4 GB of PETSc-style traffic per iteration at 256^3; aim for 10-20 s on a few tens of GB/s
+    rows = n[0] * n[1] * n[2]
+    return int(max(5, min(200, 40 * (16777216 / rows))))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = tuple(args.size)
+    iters = args.cpu_iters or auto_cpu_iters(n)
+    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
+    value, threads, per_step, sample = cpu_reference_run(n, iters, steps, warmup, args.pc)
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(n, args.iters, args.pc), "host": "CPU, KSP restatement (oracle port; PETSc is not installable here)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+
+    import petibm_b200 as pb
+    from petibm_b200.dist import Comm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched under torchrun (one process per GPU)")
+    comm = Comm.from_env(reduce=args.reduce, halo=args.halo)
+    torch.cuda.set_device(comm.device)
+    n = tuple(args.size)
+    N = n[0] * n[1] * n[2]
+    grid = pb.Grid.uniform(n, periodic=(False, False, False), dt=0.01)
+    solver = pb.LinSolverB200("poisson", "None", comm=comm if comm.nranks > 1 else None, device=comm.device)
+    solver.setOptions(ksp_type="cg", pc_type=args.pc, rtol=0.0, atol=0.0, max_it=args.iters)
+    for kv in args.tune:
+        k, v = kv.split("=")
+        solver.setTuning(k, int(v))
+    solver.setStencil(grid)
+    solver.setNullSpace(True)
+    nloc = solver.nlocal
+
+    # synthetic right-hand side b = A x*, built with the device operator
+    rng = np.random.default_rng(SEED)
+    xs = rng.standard_normal(N)
+    xs -= xs.mean()
+    xs_loc = comm.local_block(xs, n) if comm.nranks > 1 else xs
+    b_host = solver.apply(xs_loc)
+    del xs
+
+    b_dev = torch.from_numpy(b_host).to(f"cuda:{comm.device}")
+    x_dev = torch.empty_like(b_dev)
+    b_pin = torch.from_numpy(b_host).pin_memory()
+    x_pin = torch.empty(nloc, dtype=torch.float64).pin_memory()
+
+    def one_solve(x, b):
+        try:
+            solver.solve(x, b)
+        except pb.B200Error as e:
+            if e.code != -5:   # DIVERGED_ITS is how a fixed-iteration solve ends
+                raise
+        assert solver.getIters() == args.iters, (solver.getIters(), solver.getReason())
+
+    profile = not args.no_profile
+    for _ in range(max(args.warmup, 3)):
+        one_solve(x_dev, b_dev)
+    # ---- timed region 1: device-resident ---------------------------------------------------
+    sampler = ClockSampler(comm.device)
+    solver.setProfile(profile)
+    comm.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    dev_ms, launches = 0.0, 0
+    for _ in range(args.steps):
+        one_solve(x_dev, b_dev)
+        t = solver.timing()
+        dev_ms += t["solve_ms"]
+        launches += t["launches"]
+    torch.cuda.synchronize()
+    comm.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    k1_ms, k1_n = solver.profile(0)
+    k2_ms, k2_n = solver.profile(1)
+    solver.setProfile(False)
+    dev_ms_max = comm.allreduce_max(dev_ms)
+    wall_max = comm.allreduce_max(t_wall)
+    ms_per_step = dev_ms_max / args.steps
+    value = args.iters / (ms_per_step * 1e-3)
+
+    # ---- timed region 2: end to end through the plugin call with host buffers ---------------
+    one_solve(x_pin, b_pin)
+    comm.barrier()
+    torch.cuda.synchronize()
+    e2e_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_solve(x_pin, b_pin)
+        e2e_ms += solver.timing()["e2e_ms"]
+    torch.cuda.synchronize()
+    comm.barrier()
+    e2e_wall = comm.allreduce_max(time.perf_counter() - t0)
+    e2e_ms_max = comm.allreduce_max(e2e_ms)
+    e2e_value = args.iters * args.steps / max(e2e_ms_max * 1e-3, e2e_wall)
+    resid = solver.getResidual()
+
+    peak, peak_src = peaks()
+    roof = None
+    if profile and k1_n > 0:
+        k1_avg_s = k1_ms / k1_n * 1e-3
+        achieved = K1_BYTES_PER_ROW * nloc / k1_avg_s / 1e9
+        tr = traffic_record()
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": (tr or {}).get("k_spmv_dram_bytes_per_launch") if comm.nranks == 1 and n == (256, 256, 256) else None,
+                "kernel": "k_spmv (x+=a'p'; p=z+bp'; w=Ap; p.w)", "algorithmic_bytes_per_launch": K1_BYTES_PER_ROW * nloc,
+                "avg_launch_us": k1_avg_s * 1e6, "launches_timed": k1_n, "peak_source": peak_src,
+                "k_update": {"algorithmic_bytes_per_launch": K2_BYTES_PER_ROW * nloc,
+                             "avg_launch_us": (k2_ms / max(k2_n, 1)) * 1e3,
+                             "achieved": K2_BYTES_PER_ROW * nloc / max(k2_ms / max(k2_n, 1) * 1e-3, 1e-12) / 1e9},
+                "iteration_achieved": ITER_BYTES_PER_ROW * nloc * args.iters / (ms_per_step * 1e-3) / 1e9}
+
+    cpu = None
+    if comm.rank == 0 and comm.nranks == 1 and not args.no_cpu_baseline:
+        it = args.cpu_iters or auto_cpu_iters(n)
+        v, threads, per_step, sample = cpu_reference_run(n, it, 1, 0, args.pc)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+
+    if comm.rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": comm.nranks, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": workload_name(n, args.iters, args.pc),
+                "partition": f"z-slabs over {comm.nranks} GPU(s); halo {args.halo}, scalar all-reduce {args.reduce}" if comm.nranks > 1 else "single GPU",
+                "l2": ("inputs larger than L2: 5 vectors x %.0f MB per GPU" % (nloc * 8 / 1e6)) if nloc * 8 * 5 > 126e6
+                      else ("per-GPU working set %.0f MB fits the 126 MB L2 (strong scaling of a fixed problem)" % (nloc * 8 * 5 / 1e6)),
+                "timing": "CUDA events on the solver stream inside libb200ls (scatter of b .. gather of x), max over ranks",
+                "wall_s_timed_region": wall_max, "final_residual_norm": resid,
+            },
+            "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 8 * N,
+                    "ms_per_step": e2e_ms_max / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "hbm_gbs_iteration": ITER_BYTES_PER_ROW * N * args.iters / (ms_per_step * 1e-3) / 1e9,
+        }
+        print(json.dumps(line), flush=True)
+    solver.destroy()
+    if comm.nranks > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,203 @@
+/*
+ * b200ls.h -- C ABI of libb200ls.so, the B200-native (sm_100a) linear-solver core
+ * that sits behind petibm::linsolver::LinSolverBase as a third backend next to
+ * LinSolverKSP / LinSolverAmgX.
+ *
+ * Plain C: opaque handle, plain pointers and sizes, caller-owned buffers, no
+ * exceptions, no globals.  Every function returns B200LS_OK (0) or a negative
+ * B200LS_ERR_* code; b200ls_last_error(h) gives the text.  There is no CPU
+ * fallback anywhere: without a CUDA device every compute entry point fails with
+ * B200LS_ERR_CUDA.
+ *
+ * Reference interface each entry point replaces (paths into barbagroup/PetIBM):
+ *
+ *   b200ls_create / b200ls_set_options*   LinSolverKSP::LinSolverKSP + ::init
+ *                                         src/linsolver/linsolverksp.cpp:16-20,48-69
+ *                                         (KSPCreate, KSPSetOptionsPrefix, KSPSetType(KSPCG),
+ *                                          PetscOptionsInsertFile, KSPSetFromOptions)
+ *   b200ls_set_poisson_stencil            LinSolverKSP::setMatrix            linsolverksp.cpp:72-82
+ *   b200ls_set_csr                        (KSPSetOperators on the MPIAIJ Mat assembled by
+ *                                          createDivergence/createGradient/createBnHead +
+ *                                          MatMatMult, navierstokes.cpp:347-356)
+ *   b200ls_set_nullspace                  MatSetNullSpace on DBNG            navierstokes.cpp:404-413
+ *   b200ls_solve                          LinSolverKSP::solve -> KSPSolve    linsolverksp.cpp:85-105
+ *   b200ls_get_iters / _get_residual      LinSolverKSP::getIters/getResidual linsolverksp.cpp:110-132
+ *   b200ls_get_reason                     KSPGetConvergedReason              linsolverksp.cpp:94
+ *   b200ls_get_history                    KSPGetResidualHistory (parity tests)
+ *   b200ls_destroy                        LinSolverKSP::destroy / dtor       linsolverksp.cpp:23-45
+ *   b200ls_axis_from_subdomains           parser::parseSubDomains/parseOneSubDomain
+ *                                         src/parser/parser.cpp:297-356, misc::stretchGrid
+ *                                         include/petibm/misc.h:148-163
+ *   b200ls_comm_*                         PETSC_COMM_WORLD (MPI) inside KSP: VecScatter halos
+ *                                         of MatMult_MPIAIJ and MPI_Allreduce of VecDot/VecNorm
+ */
+#ifndef B200LS_H
+#define B200LS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200LS_VERSION 100 /* 0.1.0 */
+
+/* ---- error codes ---- */
+#define B200LS_OK 0
+#define B200LS_ERR_ARG (-1)         /* bad argument / call order */
+#define B200LS_ERR_CUDA (-2)        /* CUDA runtime error or no device */
+#define B200LS_ERR_UNSUPPORTED (-3) /* option / operator outside the supported set */
+#define B200LS_ERR_NCCL (-4)
+#define B200LS_ERR_DIVERGED (-5)    /* KSP reason < 0 (what LinSolverKSP::solve turns into SETERRQ) */
+#define B200LS_ERR_MISMATCH (-6)    /* operator verification against a CSR matrix failed */
+#define B200LS_ERR_PARSE (-7)       /* options text could not be parsed */
+
+/* ---- enums (values follow PETSc's option strings) ---- */
+#define B200LS_KSP_CG 0
+#define B200LS_KSP_BCGS 1
+#define B200LS_PC_NONE 0
+#define B200LS_PC_JACOBI 1
+#define B200LS_NORM_NONE 0
+#define B200LS_NORM_PRECONDITIONED 1
+#define B200LS_NORM_UNPRECONDITIONED 2
+#define B200LS_NORM_NATURAL 3
+
+/* KSPConvergedReason values reported by b200ls_get_reason (same numbers as PETSc) */
+#define B200LS_CONVERGED_RTOL 2
+#define B200LS_CONVERGED_ATOL 3
+#define B200LS_DIVERGED_ITS (-3)
+#define B200LS_DIVERGED_DTOL (-4)
+#define B200LS_DIVERGED_BREAKDOWN (-5)
+#define B200LS_DIVERGED_INDEFINITE_PC (-8)
+#define B200LS_DIVERGED_NANORINF (-9)
+#define B200LS_DIVERGED_INDEFINITE_MAT (-10)
+
+/* halo / reduction transports for the multi-GPU path */
+#define B200LS_REDUCE_P2P 0  /* in-kernel all-reduce through peer-mapped mailboxes (NVLink) */
+#define B200LS_REDUCE_NCCL 1 /* ncclAllReduce of the scalar partial sums */
+#define B200LS_HALO_STORE 0  /* boundary planes stored to the peer's ghost plane by the update kernel */
+#define B200LS_HALO_MEMCPY 1 /* cudaMemcpyPeerAsync of the boundary planes */
+
+typedef struct b200ls_solver b200ls_solver;
+
+typedef struct b200ls_options
+{
+    int ksp_type;   /* default B200LS_KSP_CG (linsolverksp.cpp:64) */
+    int pc_type;    /* default B200LS_PC_NONE */
+    int norm_type;  /* default B200LS_NORM_PRECONDITIONED */
+    int max_it;     /* default 10000 */
+    double rtol;    /* default 1e-5 */
+    double atol;    /* default 1e-50 */
+    double divtol;  /* default 1e4 */
+    int check_every; /* host polls the device convergence flag every this many iterations (default 32) */
+    int variant;     /* kernel variant selector for experiments; 0 = default */
+} b200ls_options;
+
+/* ---- library-level ---- */
+int b200ls_version(void);
+const char *b200ls_error_string(int code);
+int b200ls_device_count(int *n);
+
+/* Grid helper: cell widths of one axis from PetIBM's YAML sub-domain list. dL_out holds
+ * sum(cells) doubles on return; *n_out receives that count. cap is the capacity of dL_out. */
+int b200ls_axis_from_subdomains(double start, int nsub, const double *ends, const int *cells,
+                                const double *ratios, double *dL_out, int cap, int *n_out);
+
+/* Parse PETSc options-file text ("-poisson_ksp_type cg\n-poisson_ksp_atol 1e-6 ...") for the
+ * given prefix ("poisson_") into opts (which must hold defaults on entry, see
+ * b200ls_default_options). Any option under the prefix that this backend does not implement
+ * (gamg, hypre, lu, ...) is an error: B200LS_ERR_UNSUPPORTED, message in errbuf. */
+void b200ls_default_options(b200ls_options *opts);
+int b200ls_parse_options(const char *text, const char *prefix, b200ls_options *opts, char *errbuf,
+                         size_t errlen);
+
+/* ---- solver object ---- */
+int b200ls_create(b200ls_solver **out, int device);
+int b200ls_destroy(b200ls_solver *h);
+const char *b200ls_last_error(const b200ls_solver *h);
+int b200ls_set_options(b200ls_solver *h, const b200ls_options *opts);
+int b200ls_get_options(const b200ls_solver *h, b200ls_options *opts);
+/* Launch-configuration knobs for experiments: "kz_chunk" (z planes per CTA of the SpMV kernel,
+ * 0 = auto), "upd_blocks" (grid of the update kernel, 0 = auto), "tile" (SpMV tile variant),
+ * "use_graph" (CUDA-graph the iteration batches, default 1). */
+int b200ls_set_tuning(b200ls_solver *h, const char *key, int value);
+
+/* ---- multi-GPU communicator (one process per GPU; z-slab partition of the DMDA grid) ----
+ * Call order on every rank:  b200ls_comm_init -> b200ls_set_poisson_stencil (allocates the
+ * exchange arena) -> b200ls_comm_export (64-byte CUDA IPC handle of the arena) -> all-gather the
+ * handles with the host transport (MPI_Allgather in PetIBM, torch.distributed in the harness)
+ * -> b200ls_comm_connect(all handles, rank-major).  For B200LS_REDUCE_NCCL additionally:
+ * rank 0 b200ls_nccl_unique_id -> broadcast 128 bytes -> every rank b200ls_nccl_init. */
+int b200ls_comm_init(b200ls_solver *h, int rank, int nranks, int reduce_mode, int halo_mode);
+int b200ls_comm_export(b200ls_solver *h, void *handle64);
+int b200ls_comm_connect(b200ls_solver *h, const void *handles, int nranks);
+int b200ls_nccl_unique_id(void *id128);
+int b200ls_nccl_init(b200ls_solver *h, const void *id128);
+
+/* ---- operator ----
+ * Matrix-free separable pressure-Poisson operator DBNG = D (dt I) G of a stretched Cartesian
+ * staggered grid:  dx,dy,dz are the GLOBAL pressure-cell widths
+ * (dz ignored when dim == 2), periodic[d] the periodicity flags, [zlo, zhi) the z-planes this
+ * rank owns (0..nz for a single GPU; y-range for dim == 2 is always full, the slab axis is the
+ * slowest axis: z in 3-D, y in 2-D).  Vectors passed to b200ls_solve are the rank-local part in
+ * PETSc DMDA ordering (i fastest), length nx*ny*(zhi-zlo) (3-D) or nx*(yhi-ylo) (2-D). */
+int b200ls_set_poisson_stencil(b200ls_solver *h, int dim, const int64_t n[3], const int periodic[3],
+                               const double *dx, const double *dy, const double *dz, double dt,
+                               int64_t slab_lo, int64_t slab_hi);
+
+/* Verify the matrix-free operator bit-for-bit against rows of an assembled CSR matrix (what the
+ * PetIBM shim extracts with MatGetRow from the Mat given to setMatrix).  Rows are the rank-local
+ * rows, columns are global natural indices.  Returns B200LS_ERR_MISMATCH on any difference. */
+int b200ls_verify_csr(b200ls_solver *h, int64_t nrows, const int64_t *rowptr, const int32_t *col,
+                      const double *val, double *max_abs_diff);
+
+/* General assembled operator (any square CSR, single GPU): used for operators the separable
+ * stencil cannot express (IBPM modified Poisson, BN order > 1, the velocity system A). */
+int b200ls_set_csr(b200ls_solver *h, int64_t nrows, const int64_t *rowptr, const int32_t *col,
+                   const double *val);
+
+/* Null space attached to the operator: has_const != 0 -> the constant vector
+ * (MatNullSpaceCreate(comm, PETSC_TRUE, 0, ...), navierstokes.cpp:404-413); nvecs explicit
+ * orthonormal vectors of local length nrows (ibpm.cpp:251-267). */
+int b200ls_set_nullspace(b200ls_solver *h, int has_const, int nvecs, const double *vecs);
+
+/* y = A x on the device operator, host buffers (tests / verification). */
+int b200ls_apply(b200ls_solver *h, const double *x_host, double *y_host);
+
+/* ---- solve ----
+ * KSPSolve semantics with zero initial guess: x is overwritten. Host buffers; the H2D copy of b
+ * and D2H copy of x happen inside. Returns B200LS_OK if reason > 0, B200LS_ERR_DIVERGED if
+ * reason < 0 (x is still written), other codes on failure. */
+int b200ls_solve(b200ls_solver *h, const double *b_host, double *x_host);
+/* Same with device-resident buffers (length as above, compact i-fastest). */
+int b200ls_solve_device(b200ls_solver *h, const double *b_dev, double *x_dev);
+
+int b200ls_get_iters(const b200ls_solver *h, int *its);
+int b200ls_get_residual(const b200ls_solver *h, double *rnorm);
+int b200ls_get_reason(const b200ls_solver *h, int *reason);
+/* Copies min(cap, n) entries of the residual-norm history (entry 0 = initial) and sets *n. */
+int b200ls_get_history(const b200ls_solver *h, double *buf, int cap, int *n);
+
+/* ---- measurement hooks (bench.py) ----
+ * Device time of the last solve (solve_ms: scatter of b .. gather of x; loop_ms: the iteration loop
+ * only) measured with CUDA events on the solver's own stream, number of kernels launched in it,
+ * and per-kernel-class accumulated event time when
+ * profiling was enabled with b200ls_set_profile(h, 1) (serialises kernels; never used for the
+ * headline number). class 0 = fused SpMV kernel, 1 = fused update/reduction kernel. */
+int b200ls_get_timing(const b200ls_solver *h, double *solve_ms, double *loop_ms, int64_t *launches);
+/* Device time of the last b200ls_solve (host buffers) from before the H2D copy of b to after the D2H
+ * copy of x, CUDA events on the solver stream (ms). */
+int b200ls_get_e2e_ms(const b200ls_solver *h, double *e2e_ms);
+int b200ls_set_profile(b200ls_solver *h, int enable);
+int b200ls_get_profile(const b200ls_solver *h, int kclass, double *total_ms, int64_t *count);
+/* Run `reps` launches of one kernel class on the current solver state and return the average
+ * launch duration in ms (CUDA events on the solver stream); flush_l2 != 0 writes a >L2 buffer
+ * between launches. kclass as above; 2 = plain SpMV (b200ls_apply path). */
+int b200ls_time_kernel(b200ls_solver *h, int kclass, int reps, int flush_l2, double *avg_ms);
+void *b200ls_stream(b200ls_solver *h); /* cudaStream_t of the solver, for external event timing */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200LS_H */

@@ -1,0 +1,1505 @@
+// b200ls.cu -- host side of libb200ls.so: the C ABI declared in include/b200ls.h.
+//
+// Mirrors what petibm::linsolver::LinSolverKSP does with a KSP object
+// (src/linsolver/linsolverksp.cpp:16-132 of barbagroup/PetIBM): create -> options -> operator ->
+// solve (zero initial guess) -> iterations / residual / reason; all arithmetic runs in the sm_100a
+// kernels of kernels.cuh, all scalars of the Krylov recurrence stay on the device, the host only
+// enqueues work and polls a "done" flag.  There is no CPU solve path in this file.
+#include "../../include/b200ls.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "csr_kernels.cuh"
+
+using namespace b200;
+
+// ------------------------------------------------------------------------------------------
+// NCCL through dlopen: the library is already in the process when the host is PyTorch or an MPI
+// application linked with NCCL; we never link against a second copy.
+// ------------------------------------------------------------------------------------------
+namespace {
+typedef struct ncclComm *ncclComm_t;
+struct NcclUniqueId { char internal[128]; };
+struct NcclApi
+{
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, NcclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi &nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    // prefer a copy that is already loaded (torch's bundled one)
+    for (const char *n : names)
+    {
+        api.lib = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib)
+        for (const char *n : names)
+        {
+            api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+    if (!api.lib) return api;
+    api.GetUniqueId = (int (*)(NcclUniqueId *))dlsym(api.lib, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(ncclComm_t *, int, NcclUniqueId, int))dlsym(api.lib, "ncclCommInitRank");
+    api.CommDestroy = (int (*)(ncclComm_t))dlsym(api.lib, "ncclCommDestroy");
+    api.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(api.lib, "ncclAllReduce");
+    api.GetErrorString = (const char *(*)(int))dlsym(api.lib, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce;
+    return api;
+}
+constexpr int kNcclDouble = 8;  // ncclFloat64
+constexpr int kNcclSum = 0;     // ncclSum
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// solver object
+// ------------------------------------------------------------------------------------------
+enum OperatorKind { OP_NONE = 0, OP_STENCIL = 1, OP_CSR = 2 };
+
+struct b200ls_solver
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    b200ls_options opt;
+    std::string err;
+
+    // ---- operator: separable stencil
+    int op = OP_NONE;
+    int dim = 3;
+    int64_t n[3] = {0, 0, 0};
+    int per[3] = {0, 0, 0};
+    int64_t slab_lo = 0, slab_hi = 0;
+    double dt = 0.0;
+    std::vector<double> hdx, hdy, hdz, hgx, hgy, hgz;  // host copies (verification)
+    double *d_axes = nullptr;                          // one allocation for the six 1-D arrays
+    GridDev g{};
+    int64_t nlocal = 0;      // unknowns owned by this rank
+    int64_t nglobal = 0;
+    size_t vec_elems = 0;    // doubles per solver-layout vector (ghost planes included)
+
+    // ---- operator: general CSR (single GPU)
+    CsrDev csr{};
+    int64_t *d_rowptr = nullptr;
+    int32_t *d_col = nullptr;
+    double *d_val = nullptr;
+
+    // ---- vectors (solver layout)
+    double *arena = nullptr;  // [mailboxes | flags | r]; exported over CUDA IPC
+    size_t arena_bytes = 0;
+    double *r = nullptr, *p[2] = {nullptr, nullptr}, *w = nullptr, *x = nullptr, *dinv = nullptr;
+    double *bcg[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // BiCGStab work vectors
+    double *stage = nullptr;  // compact staging buffer for the host-pointer API
+    int has_const = 0;
+    int nnullvecs = 0;
+    double *d_nullvecs = nullptr;
+
+    // ---- device state
+    DevState *d_state = nullptr;
+    DevState *h_state = nullptr;  // pinned, 4 slots
+    cudaEvent_t ev_slot[4] = {nullptr, nullptr, nullptr, nullptr};
+    ReduceWs ws{};
+    int max_blocks = 0;
+    double *d_hist = nullptr;
+    int hist_cap = 0;
+    double *d_sendrecv = nullptr;  // NCCL mode: [0..7] send, [8..15] recv
+
+    // ---- comm
+    int rank = 0, nranks = 1;
+    int reduce_mode = B200LS_REDUCE_P2P, halo_mode = B200LS_HALO_STORE;
+    bool connected = false;
+    std::vector<void *> peer_base;  // arena base of every rank as mapped here
+    CommDev cm{};
+    ncclComm_t nccl = nullptr;
+    double *ghost_dn = nullptr, *ghost_up = nullptr;  // neighbours' ghost planes of r (mapped)
+
+    // ---- results
+    int its = 0, reason = 0;
+    double rnorm = 0.0;
+    std::vector<double> history;
+
+    // ---- launch configuration / tuning
+    int num_sms = 148;
+    int kz_chunk = 0;        // 0 = auto
+    int upd_blocks = 0;      // 0 = auto
+    int tile = 0;            // K1 tile variant
+    int use_graph = 1;
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_iters = 0;
+    unsigned long long graph_key = 0;
+
+    // ---- measurement
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+    double solve_ms = 0.0, loop_ms = 0.0, e2e_ms = 0.0;
+    cudaEvent_t ev_e0 = nullptr, ev_e1 = nullptr;
+    int64_t launches = 0;
+    int profile = 0;
+    std::vector<cudaEvent_t> prof_ev;  // pairs
+    std::vector<int> prof_cls;
+    double prof_ms[4] = {0, 0, 0, 0};
+    int64_t prof_cnt[4] = {0, 0, 0, 0};
+    double *flush_buf = nullptr;
+    size_t flush_elems = 0;
+};
+
+namespace {
+
+int fail(b200ls_solver *h, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    return code;
+}
+
+#define CU(h, call)                                                                                  \
+    do                                                                                               \
+    {                                                                                                \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return fail(h, B200LS_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,             \
+                        cudaGetErrorString(e__));                                                    \
+    } while (0)
+
+#define TRY(expr)                 \
+    do                            \
+    {                             \
+        int rc__ = (expr);        \
+        if (rc__ != B200LS_OK) return rc__; \
+    } while (0)
+
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+void free_vectors(b200ls_solver *h)
+{
+    auto fr = [](auto *&p) {
+        if (p) cudaFree(p);
+        p = nullptr;
+    };
+    if (h->connected)
+    {
+        for (int q = 0; q < (int)h->peer_base.size(); ++q)
+            if (q != h->rank && h->peer_base[q]) cudaIpcCloseMemHandle(h->peer_base[q]);
+        h->peer_base.clear();
+        h->connected = false;
+    }
+    fr(h->arena);
+    h->r = nullptr;
+    fr(h->p[0]);
+    fr(h->p[1]);
+    fr(h->w);
+    fr(h->x);
+    fr(h->dinv);
+    for (auto &b : h->bcg) fr(b);
+    fr(h->stage);
+    fr(h->d_axes);
+    fr(h->d_rowptr);
+    fr(h->d_col);
+    fr(h->d_val);
+    fr(h->d_nullvecs);
+    if (h->graph_exec)
+    {
+        cudaGraphExecDestroy(h->graph_exec);
+        h->graph_exec = nullptr;
+    }
+    h->op = OP_NONE;
+}
+
+SolveConsts make_consts(const b200ls_solver *h)
+{
+    SolveConsts k;
+    k.rtol = h->opt.rtol;
+    k.atol = h->opt.atol;
+    k.divtol = h->opt.divtol;
+    k.nglobal = (double)h->nglobal;
+    k.max_it = h->opt.max_it;
+    k.norm_type = h->opt.norm_type;
+    k.has_const = h->has_const;
+    k.hist_cap = h->hist_cap;
+    return k;
+}
+
+void invalidate_graph(b200ls_solver *h);
+
+int ensure_hist(b200ls_solver *h)
+{
+    const int want = std::min(std::max(h->opt.max_it, 0) + 2, 1 << 22);
+    if (want > h->hist_cap)
+    {
+        if (h->d_hist) cudaFree(h->d_hist);
+        h->d_hist = nullptr;
+        CU(h, cudaMalloc(&h->d_hist, sizeof(double) * (size_t)want));
+        h->hist_cap = want;
+        invalidate_graph(h);
+    }
+    return B200LS_OK;
+}
+
+// ---- profiling helpers: one event pair per launch, resolved after the solve
+struct ProfScope
+{
+    b200ls_solver *h;
+    int cls;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ProfScope(b200ls_solver *h_, int cls_) : h(h_), cls(cls_)
+    {
+        if (h->profile)
+        {
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, h->stream);
+        }
+    }
+    ~ProfScope()
+    {
+        if (h->profile)
+        {
+            cudaEventRecord(e1, h->stream);
+            h->prof_ev.push_back(e0);
+            h->prof_ev.push_back(e1);
+            h->prof_cls.push_back(cls);
+        }
+    }
+};
+
+void resolve_profile(b200ls_solver *h)
+{
+    for (size_t q = 0; q < h->prof_cls.size(); ++q)
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->prof_ev[2 * q], h->prof_ev[2 * q + 1]) == cudaSuccess)
+        {
+            h->prof_ms[h->prof_cls[q]] += ms;
+            h->prof_cnt[h->prof_cls[q]] += 1;
+        }
+        cudaEventDestroy(h->prof_ev[2 * q]);
+        cudaEventDestroy(h->prof_ev[2 * q + 1]);
+    }
+    h->prof_ev.clear();
+    h->prof_cls.clear();
+}
+
+// ------------------------------------------------------------------------------------------
+// launch wrappers
+// ------------------------------------------------------------------------------------------
+struct TileCfg { int txt, tyt; };
+inline TileCfg tile_cfg(const b200ls_solver *h)
+{
+    switch (h->tile)
+    {
+        case 1: return {32, 6};
+        case 2: return {32, 10};
+        case 3: return {16, 10};
+        case 4: return {32, 16};
+        default: return {32, 8};
+    }
+}
+
+inline int auto_kz_chunk(const b200ls_solver *h)
+{
+    if (h->kz_chunk > 0) return std::min<int>(h->kz_chunk, h->g.nzl);
+    const TileCfg t = tile_cfg(h);
+    const int64_t bx = (h->g.nx + 2 * t.txt - 1) / (2 * t.txt), by = (h->g.ny + (t.tyt - 2) - 1) / (t.tyt - 2);
+    const int64_t xy = bx * by;
+    const int per_sm = std::max(1, 2048 / (t.txt * t.tyt));
+    const int64_t target = (int64_t)h->num_sms * per_sm;  // one full wave of resident blocks
+    int64_t nch = std::max<int64_t>(1, (target + xy - 1) / xy);
+    nch = std::min<int64_t>(nch, std::max<int64_t>(1, h->g.nzl / 8));
+    nch = std::max<int64_t>(nch, 1);
+    return (int)((h->g.nzl + nch - 1) / nch);
+}
+
+template <bool JAC, bool APPLY>
+void launch_spmv_t(b200ls_solver *h, const VecSet &v, int ghost_store)
+{
+    const TileCfg t = tile_cfg(h);
+    const int kz = auto_kz_chunk(h);
+    dim3 grid((unsigned)((h->g.nx + 2 * t.txt - 1) / (2 * t.txt)), (unsigned)((h->g.ny + t.tyt - 3) / (t.tyt - 2)),
+              (unsigned)((h->g.nzl + kz - 1) / kz));
+    dim3 block(t.txt, t.tyt);
+    const SolveConsts kc = make_consts(h);
+#define B200_SPMV_CASE(TXT, TYT)                                                                               \
+    k_spmv<TXT, TYT, JAC, APPLY><<<grid, block, 0, h->stream>>>(h->g, v, kz, h->ws, h->cm, h->d_state, kc, \
+                                                                 h->d_hist, ghost_store)
+    switch (h->tile)
+    {
+        case 1: B200_SPMV_CASE(32, 6); break;
+        case 2: B200_SPMV_CASE(32, 10); break;
+        case 3: B200_SPMV_CASE(16, 10); break;
+        case 4: B200_SPMV_CASE(32, 16); break;
+        default: B200_SPMV_CASE(32, 8); break;
+    }
+#undef B200_SPMV_CASE
+    h->launches++;
+}
+
+int spmv_grid_blocks(const b200ls_solver *h)
+{
+    const TileCfg t = tile_cfg(h);
+    const int kz = auto_kz_chunk(h);
+    return (int)(((h->g.nx + 2 * t.txt - 1) / (2 * t.txt)) * ((h->g.ny + t.tyt - 3) / (t.tyt - 2)) *
+                 ((h->g.nzl + kz - 1) / kz));
+}
+
+int upd_grid_blocks(const b200ls_solver *h)
+{
+    if (h->upd_blocks > 0) return h->upd_blocks;
+    const int64_t items = (int64_t)((h->g.nx + 1) / 2) * h->g.ny * h->g.nzl;
+    const int64_t need = (items + 256 * 4 - 1) / (256 * 4);
+    return (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)h->num_sms * 8));
+}
+
+template <bool JAC, bool INIT>
+void launch_update_t(b200ls_solver *h, int fin_kind, bool push)
+{
+    UpdVecs v{h->r, h->w, h->dinv};
+    CommDev cm = h->cm;
+    if (!push)
+    {
+        cm.r_ghost_dn = nullptr;
+        cm.r_ghost_up = nullptr;
+    }
+    const SolveConsts kc = make_consts(h);
+    k_update<JAC, INIT, 4><<<upd_grid_blocks(h), 256, 0, h->stream>>>(h->g, v, fin_kind, h->ws, cm, h->d_state, kc,
+                                                                      h->d_hist);
+    h->launches++;
+}
+
+// reduction epilogue on the host side: NCCL transport
+int post_reduce(b200ls_solver *h, int kind)
+{
+    if (h->nranks > 1 && h->reduce_mode == B200LS_REDUCE_NCCL)
+    {
+        NcclApi &api = nccl_api();
+        if (!h->nccl) return fail(h, B200LS_ERR_NCCL, "NCCL reduce mode selected but b200ls_nccl_init was not called");
+        const int rc = api.AllReduce(h->d_sendrecv, h->d_sendrecv + B200_NSUM, B200_NSUM, kNcclDouble, kNcclSum,
+                                     h->nccl, h->stream);
+        if (rc != 0) return fail(h, B200LS_ERR_NCCL, "ncclAllReduce failed: %s", api.GetErrorString ? api.GetErrorString(rc) : "?");
+        k_scalars<<<1, 32, 0, h->stream>>>(kind, h->d_sendrecv + B200_NSUM, h->d_state, make_consts(h), h->d_hist);
+        h->launches += 2;
+    }
+    return B200LS_OK;
+}
+
+// halo of r by explicit peer copies (B200LS_HALO_MEMCPY)
+int memcpy_halo(b200ls_solver *h, const double *vec)
+{
+    if (h->nranks <= 1 || h->halo_mode != B200LS_HALO_MEMCPY) return B200LS_OK;
+    const size_t bytes = sizeof(double) * (size_t)h->g.plane;
+    if (h->ghost_dn) CU(h, cudaMemcpyAsync(h->ghost_dn, vec + h->g.plane, bytes, cudaMemcpyDefault, h->stream));
+    if (h->ghost_up)
+        CU(h, cudaMemcpyAsync(h->ghost_up, vec + (size_t)h->g.nzl * h->g.plane, bytes, cudaMemcpyDefault, h->stream));
+    return B200LS_OK;
+}
+
+inline bool kernel_push(const b200ls_solver *h) { return h->nranks > 1 && h->halo_mode == B200LS_HALO_STORE; }
+
+int enqueue_update(b200ls_solver *h, bool init, int kind)
+{
+    const bool jac = h->opt.pc_type == B200LS_PC_JACOBI;
+    {
+        ProfScope ps(h, 1);
+        const bool push = kernel_push(h);
+        if (init)
+        {
+            if (jac) launch_update_t<true, true>(h, kind, push);
+            else launch_update_t<false, true>(h, kind, push);
+        }
+        else
+        {
+            if (jac) launch_update_t<true, false>(h, kind, push);
+            else launch_update_t<false, false>(h, kind, push);
+        }
+    }
+    TRY(memcpy_halo(h, h->r));
+    return post_reduce(h, kind);
+}
+
+int enqueue_spmv(b200ls_solver *h, int parity)
+{
+    const bool jac = h->opt.pc_type == B200LS_PC_JACOBI;
+    VecSet v{h->r, h->p[parity], h->p[parity ^ 1], h->w, h->x, h->dinv};
+    {
+        ProfScope ps(h, 0);
+        const int ghost_store = h->nranks > 1 ? 1 : 0;
+        if (jac) launch_spmv_t<true, false>(h, v, ghost_store);
+        else launch_spmv_t<false, false>(h, v, ghost_store);
+    }
+    return post_reduce(h, FIN_SPMV);
+}
+
+int enqueue_cg_iterations(b200ls_solver *h, int first_iter, int count)
+{
+    for (int q = 0; q < count; ++q)
+    {
+        TRY(enqueue_spmv(h, (first_iter + q) & 1));
+        TRY(enqueue_update(h, false, FIN_UPDATE));
+    }
+    return B200LS_OK;
+}
+
+// a graph of `count` CG iterations starting at an even iteration (buffer parity repeats every 2)
+int launch_cg_batch(b200ls_solver *h, int first_iter, int count)
+{
+    const bool graphable = h->use_graph && !h->profile && (count % 2 == 0) && (first_iter % 2 == 0);
+    if (!graphable) return enqueue_cg_iterations(h, first_iter, count);
+    const unsigned long long key = (unsigned long long)count;
+    if (!h->graph_exec || h->graph_key != key || h->graph_iters != count)
+    {
+        if (h->graph_exec)
+        {
+            cudaGraphExecDestroy(h->graph_exec);
+            h->graph_exec = nullptr;
+        }
+        cudaGraph_t graph = nullptr;
+        const int64_t launches_before = h->launches;
+        CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_cg_iterations(h, 0, count);
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        h->launches = launches_before;
+        if (rc != B200LS_OK)
+        {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (ce != cudaSuccess) return fail(h, B200LS_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return fail(h, B200LS_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+        h->graph_key = key;
+        h->graph_iters = count;
+    }
+    CU(h, cudaGraphLaunch(h->graph_exec, h->stream));
+    int per_iter = 2;
+    if (h->nranks > 1 && h->reduce_mode == B200LS_REDUCE_NCCL) per_iter += 4;
+    h->launches += (int64_t)per_iter * count;
+    return B200LS_OK;
+}
+
+void invalidate_graph(b200ls_solver *h)
+{
+    if (h->graph_exec)
+    {
+        cudaGraphExecDestroy(h->graph_exec);
+        h->graph_exec = nullptr;
+    }
+}
+
+int alloc_state(b200ls_solver *h)
+{
+    if (h->d_state) return B200LS_OK;
+    CU(h, cudaMalloc(&h->d_state, sizeof(DevState)));
+    CU(h, cudaMemset(h->d_state, 0, sizeof(DevState)));
+    CU(h, cudaMallocHost(&h->h_state, 4 * sizeof(DevState)));
+    for (auto &e : h->ev_slot) CU(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->max_blocks = 1 << 16;
+    CU(h, cudaMalloc(&h->ws.partials, sizeof(double) * B200_NSUM * (size_t)h->max_blocks));
+    CU(h, cudaMalloc(&h->ws.counter, sizeof(unsigned int) * 4));
+    CU(h, cudaMemset(h->ws.counter, 0, sizeof(unsigned int) * 4));
+    CU(h, cudaMalloc(&h->d_sendrecv, sizeof(double) * 2 * B200_NSUM));
+    CU(h, cudaMemset(h->d_sendrecv, 0, sizeof(double) * 2 * B200_NSUM));
+    CU(h, cudaEventCreate(&h->ev_a));
+    CU(h, cudaEventCreate(&h->ev_b));
+    CU(h, cudaEventCreate(&h->ev_c));
+    CU(h, cudaEventCreate(&h->ev_d));
+    CU(h, cudaEventCreate(&h->ev_e0));
+    CU(h, cudaEventCreate(&h->ev_e1));
+    return B200LS_OK;
+}
+
+void build_commdev(b200ls_solver *h)
+{
+    CommDev &cm = h->cm;
+    memset(&cm, 0, sizeof cm);
+    cm.rank = h->rank;
+    cm.nranks = h->nranks;
+    cm.mode = 0;
+    cm.sendbuf = h->d_sendrecv;
+    if (h->nranks > 1) cm.mode = (h->reduce_mode == B200LS_REDUCE_NCCL) ? 2 : 1;
+}
+
+// arena layout: [mailboxes 2*nranks*NSUM doubles | flags 2*nranks u64 | pad to 256 B | r]
+inline size_t arena_head_bytes(int nranks)
+{
+    const size_t b = sizeof(double) * 2 * (size_t)nranks * B200_NSUM + sizeof(unsigned long long) * 2 * (size_t)nranks;
+    return (size_t)round_up((int64_t)b, 256);
+}
+
+int setup_stencil_vectors(b200ls_solver *h)
+{
+    const size_t ve = h->vec_elems;
+    const size_t head = arena_head_bytes(h->nranks);
+    h->arena_bytes = head + sizeof(double) * ve;
+    CU(h, cudaMalloc(&h->arena, h->arena_bytes));
+    CU(h, cudaMemset(h->arena, 0, h->arena_bytes));
+    h->r = reinterpret_cast<double *>(reinterpret_cast<char *>(h->arena) + head);
+    for (int q = 0; q < 2; ++q)
+    {
+        CU(h, cudaMalloc(&h->p[q], sizeof(double) * ve));
+        CU(h, cudaMemset(h->p[q], 0, sizeof(double) * ve));
+    }
+    CU(h, cudaMalloc(&h->w, sizeof(double) * ve));
+    CU(h, cudaMemset(h->w, 0, sizeof(double) * ve));
+    CU(h, cudaMalloc(&h->x, sizeof(double) * ve));
+    CU(h, cudaMemset(h->x, 0, sizeof(double) * ve));
+    CU(h, cudaMalloc(&h->stage, sizeof(double) * (size_t)std::max<int64_t>(h->nlocal, 1)));
+    return B200LS_OK;
+}
+
+int ensure_jacobi(b200ls_solver *h)
+{
+    if (h->opt.pc_type != B200LS_PC_JACOBI || h->dinv || h->op != OP_STENCIL) return B200LS_OK;
+    CU(h, cudaMalloc(&h->dinv, sizeof(double) * h->vec_elems));
+    CU(h, cudaMemsetAsync(h->dinv, 0, sizeof(double) * h->vec_elems, h->stream));
+    k_jacobi_setup<<<h->num_sms * 8, 256, 0, h->stream>>>(h->g, h->dinv);
+    CU(h, cudaGetLastError());
+    return B200LS_OK;
+}
+
+int check_state_err(b200ls_solver *h, const DevState &s)
+{
+    if (s.err) return fail(h, B200LS_ERR_CUDA, "cross-GPU reduction timed out (a peer rank never arrived)");
+    return B200LS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// CG on the separable stencil
+// ------------------------------------------------------------------------------------------
+int solve_stencil_cg(b200ls_solver *h, const double *b_dev, double *x_dev)
+{
+    TRY(ensure_hist(h));
+    TRY(ensure_jacobi(h));
+    const bool multi = h->nranks > 1;
+    if (multi && !h->connected) return fail(h, B200LS_ERR_ARG, "multi-GPU solver used before b200ls_comm_connect");
+    h->launches = 0;
+    CU(h, cudaEventRecord(h->ev_a, h->stream));
+    k_state_reset<<<1, 32, 0, h->stream>>>(h->d_state);
+    CU(h, cudaMemsetAsync(h->p[0], 0, sizeof(double) * h->vec_elems, h->stream));
+    k_scatter<<<h->num_sms * 8, 256, 0, h->stream>>>(h->g, b_dev, h->r, h->x);
+    h->launches += 2;
+    if (h->has_const) TRY(enqueue_update(h, true, FIN_INIT_CENTRE));
+    TRY(enqueue_update(h, true, FIN_INIT));
+    CU(h, cudaEventRecord(h->ev_b, h->stream));
+
+    // iterate in batches; the host only looks at the pinned snapshot of batch n-1 while batch n is
+    // already queued (kernels of a finished solve return immediately)
+    int check = std::max(2, h->opt.check_every);
+    check += check & 1;
+    int issued = 0, next_slot = 0;
+    std::deque<int> outstanding;
+    auto snapshot = [&]() -> int {
+        const int s = next_slot;
+        next_slot = (next_slot + 1) % 3;
+        CU(h, cudaMemcpyAsync(&h->h_state[s], h->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaEventRecord(h->ev_slot[s], h->stream));
+        outstanding.push_back(s);
+        return B200LS_OK;
+    };
+    TRY(snapshot());
+    for (;;)
+    {
+        while (outstanding.size() < 2 && issued < h->opt.max_it)
+        {
+            TRY(launch_cg_batch(h, issued, check));
+            issued += check;
+            TRY(snapshot());
+        }
+        const int s = outstanding.front();
+        outstanding.pop_front();
+        CU(h, cudaEventSynchronize(h->ev_slot[s]));
+        if (h->h_state[s].done) break;
+        if (outstanding.empty() && issued >= h->opt.max_it)
+            return fail(h, B200LS_ERR_CUDA, "internal: iteration budget exhausted without a reason");
+    }
+    CU(h, cudaEventRecord(h->ev_c, h->stream));
+    k_xtail<<<h->num_sms * 8, 256, 0, h->stream>>>(h->g, h->x, h->p[0], h->p[1], h->d_state);
+    k_gather<<<h->num_sms * 8, 256, 0, h->stream>>>(h->g, h->x, x_dev);
+    h->launches += 2;
+    CU(h, cudaMemcpyAsync(&h->h_state[3], h->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaEventRecord(h->ev_d, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaGetLastError());
+    const DevState s = h->h_state[3];
+    TRY(check_state_err(h, s));
+    h->its = s.its;
+    h->reason = s.reason;
+    h->rnorm = s.dp;
+    const int nh = std::min(s.nhist, h->hist_cap);
+    h->history.resize((size_t)std::max(nh, 0));
+    if (nh > 0) CU(h, cudaMemcpy(h->history.data(), h->d_hist, sizeof(double) * (size_t)nh, cudaMemcpyDeviceToHost));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_a, h->ev_d);
+    h->solve_ms = ms;
+    cudaEventElapsedTime(&ms, h->ev_b, h->ev_c);
+    h->loop_ms = ms;
+    if (h->profile) resolve_profile(h);
+    return B200LS_OK;
+}
+
+}  // namespace
+
+#include "csr_solver.inc"
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int b200ls_version(void) { return B200LS_VERSION; }
+
+const char *b200ls_error_string(int code)
+{
+    switch (code)
+    {
+        case B200LS_OK: return "ok";
+        case B200LS_ERR_ARG: return "bad argument or call order";
+        case B200LS_ERR_CUDA: return "CUDA error or no device";
+        case B200LS_ERR_UNSUPPORTED: return "unsupported option or operator";
+        case B200LS_ERR_NCCL: return "NCCL error";
+        case B200LS_ERR_DIVERGED: return "solver diverged (KSP reason < 0)";
+        case B200LS_ERR_MISMATCH: return "matrix-free operator does not match the assembled matrix";
+        case B200LS_ERR_PARSE: return "options text could not be parsed";
+        default: return "unknown error";
+    }
+}
+
+int b200ls_device_count(int *n)
+{
+    if (!n) return B200LS_ERR_ARG;
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess)
+    {
+        cudaGetLastError();
+        *n = 0;
+        return B200LS_ERR_CUDA;
+    }
+    *n = c;
+    return B200LS_OK;
+}
+
+// parser::parseSubDomains / parseOneSubDomain (src/parser/parser.cpp:297-356) and
+// misc::stretchGrid (include/petibm/misc.h:148-163)
+int b200ls_axis_from_subdomains(double start, int nsub, const double *ends, const int *cells, const double *ratios,
+                                double *dL_out, int cap, int *n_out)
+{
+    if (nsub < 0 || (nsub > 0 && (!ends || !cells || !ratios)) || !dL_out || !n_out) return B200LS_ERR_ARG;
+    int ntot = 0;
+    double bg = start;
+    for (int s = 0; s < nsub; ++s)
+    {
+        const int n = cells[s];
+        if (n <= 0 || ntot + n > cap) return B200LS_ERR_ARG;
+        const double ed = ends[s], r = ratios[s];
+        double *dL = dL_out + ntot;
+        if (std::abs(r - 1.0) <= 1e-12)
+        {
+            const double hcell = (ed - bg) / n;
+            for (int i = 0; i < n; ++i) dL[i] = hcell;
+        }
+        else
+        {
+            dL[0] = (ed - bg) * (r - 1.0) / (std::pow(r, n) - 1.0);
+            for (int i = 1; i < n; ++i) dL[i] = dL[i - 1] * r;
+        }
+        ntot += n;
+        bg = ed;
+    }
+    *n_out = ntot;
+    return B200LS_OK;
+}
+
+void b200ls_default_options(b200ls_options *o)
+{
+    if (!o) return;
+    o->ksp_type = B200LS_KSP_CG;  // linsolverksp.cpp:64
+    o->pc_type = B200LS_PC_NONE;
+    o->norm_type = B200LS_NORM_PRECONDITIONED;
+    o->max_it = 10000;
+    o->rtol = 1e-5;
+    o->atol = 1e-50;
+    o->divtol = 1e4;
+    o->check_every = 32;
+    o->variant = 0;
+}
+
+static void set_err(char *errbuf, size_t errlen, const char *fmt, ...)
+{
+    if (!errbuf || !errlen) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(errbuf, errlen, fmt, ap);
+    va_end(ap);
+}
+
+// PETSc options-file syntax: one or more "-name [value]" per line, '#' starts a comment
+// (what PetscOptionsInsertFile accepts, linsolverksp.cpp:58).
+int b200ls_parse_options(const char *text, const char *prefix, b200ls_options *opts, char *errbuf, size_t errlen)
+{
+    if (!text || !prefix || !opts) return B200LS_ERR_ARG;
+    std::vector<std::string> tok;
+    {
+        std::string cur;
+        bool comment = false;
+        for (const char *c = text;; ++c)
+        {
+            const char ch = *c;
+            if (ch == '\0' || ch == '\n')
+            {
+                if (!cur.empty()) tok.push_back(cur);
+                cur.clear();
+                comment = false;
+                if (ch == '\0') break;
+                continue;
+            }
+            if (comment) continue;
+            if (ch == '#' || ch == '!' || ch == '%')
+            {
+                if (cur.empty() || ch == '#')
+                {
+                    if (!cur.empty()) tok.push_back(cur);
+                    cur.clear();
+                    comment = true;
+                    continue;
+                }
+            }
+            if (ch == ' ' || ch == '\t' || ch == '\r')
+            {
+                if (!cur.empty()) tok.push_back(cur);
+                cur.clear();
+                continue;
+            }
+            cur.push_back(ch);
+        }
+    }
+    auto is_name = [](const std::string &s) {
+        return s.size() >= 2 && s[0] == '-' && !(s[1] >= '0' && s[1] <= '9') && s[1] != '.';
+    };
+    const std::string pre = std::string("-") + prefix;
+    for (size_t q = 0; q < tok.size(); ++q)
+    {
+        if (!is_name(tok[q])) { set_err(errbuf, errlen, "stray value '%s'", tok[q].c_str()); return B200LS_ERR_PARSE; }
+        const std::string name = tok[q];
+        std::string val;
+        bool has_val = false;
+        if (q + 1 < tok.size() && !is_name(tok[q + 1]))
+        {
+            val = tok[++q];
+            has_val = true;
+        }
+        if (name.compare(0, pre.size(), pre) != 0) continue;  // another solver's / global option
+        const std::string key = name.substr(pre.size());
+        auto need = [&]() -> bool {
+            if (!has_val) set_err(errbuf, errlen, "option %s needs a value", name.c_str());
+            return has_val;
+        };
+        auto num = [&](double &out) -> bool {
+            if (!need()) return false;
+            char *end = nullptr;
+            out = strtod(val.c_str(), &end);
+            if (end == val.c_str() || *end != '\0')
+            {
+                set_err(errbuf, errlen, "option %s: '%s' is not a number", name.c_str(), val.c_str());
+                return false;
+            }
+            return true;
+        };
+        double d = 0.0;
+        if (key == "ksp_type")
+        {
+            if (!need()) return B200LS_ERR_PARSE;
+            if (val == "cg") opts->ksp_type = B200LS_KSP_CG;
+            else if (val == "bcgs") opts->ksp_type = B200LS_KSP_BCGS;
+            else { set_err(errbuf, errlen, "-%sksp_type %s is not implemented by the B200 backend (cg, bcgs)", prefix, val.c_str()); return B200LS_ERR_UNSUPPORTED; }
+        }
+        else if (key == "pc_type")
+        {
+            if (!need()) return B200LS_ERR_PARSE;
+            if (val == "none") opts->pc_type = B200LS_PC_NONE;
+            else if (val == "jacobi") opts->pc_type = B200LS_PC_JACOBI;
+            else { set_err(errbuf, errlen, "-%spc_type %s is not implemented by the B200 backend (none, jacobi)", prefix, val.c_str()); return B200LS_ERR_UNSUPPORTED; }
+        }
+        else if (key == "pc_jacobi_type")
+        {
+            if (!need()) return B200LS_ERR_PARSE;
+            if (val != "diagonal") { set_err(errbuf, errlen, "-%spc_jacobi_type %s unsupported (diagonal)", prefix, val.c_str()); return B200LS_ERR_UNSUPPORTED; }
+        }
+        else if (key == "ksp_norm_type")
+        {
+            if (!need()) return B200LS_ERR_PARSE;
+            if (val == "preconditioned") opts->norm_type = B200LS_NORM_PRECONDITIONED;
+            else if (val == "unpreconditioned") opts->norm_type = B200LS_NORM_UNPRECONDITIONED;
+            else if (val == "natural") opts->norm_type = B200LS_NORM_NATURAL;
+            else { set_err(errbuf, errlen, "-%sksp_norm_type %s unsupported", prefix, val.c_str()); return B200LS_ERR_UNSUPPORTED; }
+        }
+        else if (key == "ksp_rtol") { if (!num(d)) return B200LS_ERR_PARSE; opts->rtol = d; }
+        else if (key == "ksp_atol") { if (!num(d)) return B200LS_ERR_PARSE; opts->atol = d; }
+        else if (key == "ksp_divtol") { if (!num(d)) return B200LS_ERR_PARSE; opts->divtol = d; }
+        else if (key == "ksp_max_it") { if (!num(d)) return B200LS_ERR_PARSE; opts->max_it = (int)d; }
+        else if (key == "ksp_initial_guess_nonzero")
+        {
+            if (has_val && val != "0" && val != "false" && val != "no")
+            {
+                set_err(errbuf, errlen, "-%sksp_initial_guess_nonzero is unsupported: PetIBM always starts from zero", prefix);
+                return B200LS_ERR_UNSUPPORTED;
+            }
+            if (!has_val) { set_err(errbuf, errlen, "-%sksp_initial_guess_nonzero is unsupported", prefix); return B200LS_ERR_UNSUPPORTED; }
+        }
+        else if (key == "ksp_monitor" || key == "ksp_view" || key == "ksp_converged_reason" || key == "ksp_reuse_preconditioner")
+        {
+            // diagnostics / no-ops for this backend
+        }
+        else if (key == "b200_check_every") { if (!num(d)) return B200LS_ERR_PARSE; opts->check_every = (int)d; }
+        else if (key == "b200_variant") { if (!num(d)) return B200LS_ERR_PARSE; opts->variant = (int)d; }
+        else
+        {
+            set_err(errbuf, errlen, "option %s is not implemented by the B200 backend; no silent fallback", name.c_str());
+            return B200LS_ERR_UNSUPPORTED;
+        }
+    }
+    return B200LS_OK;
+}
+
+int b200ls_create(b200ls_solver **out, int device)
+{
+    if (!out) return B200LS_ERR_ARG;
+    *out = nullptr;
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt <= 0)
+    {
+        cudaGetLastError();
+        return B200LS_ERR_CUDA;  // no CPU fallback
+    }
+    if (device < 0 || device >= cnt) return B200LS_ERR_ARG;
+    b200ls_solver *h = new (std::nothrow) b200ls_solver();
+    if (!h) return B200LS_ERR_ARG;
+    b200ls_default_options(&h->opt);
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+    {
+        cudaGetLastError();
+        delete h;
+        return B200LS_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+    const int rc = alloc_state(h);
+    if (rc != B200LS_OK)
+    {
+        delete h;
+        return rc;
+    }
+    build_commdev(h);
+    *out = h;
+    return B200LS_OK;
+}
+
+int b200ls_destroy(b200ls_solver *h)
+{
+    if (!h) return B200LS_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->nccl && nccl_api().ok) nccl_api().CommDestroy(h->nccl);
+    free_vectors(h);
+    if (h->d_state) cudaFree(h->d_state);
+    if (h->h_state) cudaFreeHost(h->h_state);
+    for (auto &e : h->ev_slot)
+        if (e) cudaEventDestroy(e);
+    if (h->ws.partials) cudaFree(h->ws.partials);
+    if (h->ws.counter) cudaFree(h->ws.counter);
+    if (h->d_hist) cudaFree(h->d_hist);
+    if (h->d_sendrecv) cudaFree(h->d_sendrecv);
+    if (h->flush_buf) cudaFree(h->flush_buf);
+    for (cudaEvent_t e : {h->ev_a, h->ev_b, h->ev_c, h->ev_d, h->ev_e0, h->ev_e1})
+        if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return B200LS_OK;
+}
+
+const char *b200ls_last_error(const b200ls_solver *h) { return h ? h->err.c_str() : "null handle"; }
+
+int b200ls_set_options(b200ls_solver *h, const b200ls_options *o)
+{
+    if (!h || !o) return B200LS_ERR_ARG;
+    if (o->ksp_type != B200LS_KSP_CG && o->ksp_type != B200LS_KSP_BCGS) return fail(h, B200LS_ERR_UNSUPPORTED, "ksp_type %d", o->ksp_type);
+    if (o->pc_type != B200LS_PC_NONE && o->pc_type != B200LS_PC_JACOBI) return fail(h, B200LS_ERR_UNSUPPORTED, "pc_type %d", o->pc_type);
+    if (o->norm_type < B200LS_NORM_PRECONDITIONED || o->norm_type > B200LS_NORM_NATURAL)
+        return fail(h, B200LS_ERR_UNSUPPORTED, "norm_type %d (KSP_NORM_NONE is not supported)", o->norm_type);
+    if (o->max_it < 0) return fail(h, B200LS_ERR_ARG, "max_it < 0");
+    h->opt = *o;
+    if (h->opt.check_every <= 0) h->opt.check_every = 32;
+    invalidate_graph(h);
+    return B200LS_OK;
+}
+
+int b200ls_get_options(const b200ls_solver *h, b200ls_options *o)
+{
+    if (!h || !o) return B200LS_ERR_ARG;
+    *o = h->opt;
+    return B200LS_OK;
+}
+
+int b200ls_set_tuning(b200ls_solver *h, const char *key, int value)
+{
+    if (!h || !key) return B200LS_ERR_ARG;
+    const std::string k(key);
+    if (k == "kz_chunk") h->kz_chunk = value;
+    else if (k == "upd_blocks") h->upd_blocks = value;
+    else if (k == "tile") h->tile = value;
+    else if (k == "use_graph") h->use_graph = value;
+    else return fail(h, B200LS_ERR_ARG, "unknown tuning key %s", key);
+    invalidate_graph(h);
+    return B200LS_OK;
+}
+
+// ---- communicator -----------------------------------------------------------------------
+int b200ls_comm_init(b200ls_solver *h, int rank, int nranks, int reduce_mode, int halo_mode)
+{
+    if (!h) return B200LS_ERR_ARG;
+    if (nranks < 1 || nranks > B200_MAX_RANKS || rank < 0 || rank >= nranks) return fail(h, B200LS_ERR_ARG, "bad rank/nranks %d/%d", rank, nranks);
+    if (h->op != OP_NONE) return fail(h, B200LS_ERR_ARG, "b200ls_comm_init must precede the operator set-up");
+    if (reduce_mode != B200LS_REDUCE_P2P && reduce_mode != B200LS_REDUCE_NCCL) return fail(h, B200LS_ERR_ARG, "bad reduce_mode");
+    if (halo_mode != B200LS_HALO_STORE && halo_mode != B200LS_HALO_MEMCPY) return fail(h, B200LS_ERR_ARG, "bad halo_mode");
+    if (reduce_mode == B200LS_REDUCE_P2P && halo_mode == B200LS_HALO_MEMCPY && nranks > 1)
+        return fail(h, B200LS_ERR_UNSUPPORTED, "memcpy halos need the NCCL all-reduce as their cross-GPU ordering point");
+    h->rank = rank;
+    h->nranks = nranks;
+    h->reduce_mode = reduce_mode;
+    h->halo_mode = halo_mode;
+    build_commdev(h);
+    return B200LS_OK;
+}
+
+int b200ls_comm_export(b200ls_solver *h, void *handle64)
+{
+    if (!h || !handle64) return B200LS_ERR_ARG;
+    if (!h->arena) return fail(h, B200LS_ERR_ARG, "no arena: set the operator first");
+    cudaSetDevice(h->device);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t hd;
+    CU(h, cudaIpcGetMemHandle(&hd, h->arena));
+    memcpy(handle64, &hd, 64);
+    return B200LS_OK;
+}
+
+int b200ls_comm_connect(b200ls_solver *h, const void *handles, int nranks)
+{
+    if (!h || !handles) return B200LS_ERR_ARG;
+    if (nranks != h->nranks) return fail(h, B200LS_ERR_ARG, "nranks mismatch");
+    if (!h->arena) return fail(h, B200LS_ERR_ARG, "no arena: set the operator first");
+    cudaSetDevice(h->device);
+    h->peer_base.assign((size_t)nranks, nullptr);
+    for (int q = 0; q < nranks; ++q)
+    {
+        if (q == h->rank)
+        {
+            h->peer_base[q] = h->arena;
+            continue;
+        }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, (const char *)handles + 64 * (size_t)q, 64);
+        void *ptr = nullptr;
+        CU(h, cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_base[q] = ptr;
+    }
+    h->connected = true;
+    const size_t head = arena_head_bytes(nranks);
+    CommDev &cm = h->cm;
+    for (int q = 0; q < nranks; ++q)
+    {
+        cm.mbox_peer[q] = reinterpret_cast<double *>(h->peer_base[q]);
+        cm.flag_peer[q] = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(h->peer_base[q]) +
+                                                                 sizeof(double) * 2 * (size_t)nranks * B200_NSUM);
+    }
+    cm.mbox_local = cm.mbox_peer[h->rank];
+    cm.flag_local = cm.flag_peer[h->rank];
+    // neighbours along the slab axis; periodic wrap closes the ring
+    const bool perz = h->dim == 3 && h->per[2];
+    int dn = h->rank - 1, up = h->rank + 1;
+    if (dn < 0) dn = perz ? nranks - 1 : -1;
+    if (up >= nranks) up = perz ? 0 : -1;
+    auto rbase = [&](int q) { return reinterpret_cast<double *>(reinterpret_cast<char *>(h->peer_base[q]) + head); };
+    h->ghost_dn = h->ghost_up = nullptr;
+    // our top plane goes to the BOTTOM ghost plane (storage plane 0) of the neighbour above
+    if (up >= 0) h->ghost_up = rbase(up);
+    // our plane 0 goes to the TOP ghost plane (storage plane nzl_peer + 1) of the neighbour below; slab sizes
+    // follow the PETSc ownership rule (checked in b200ls_set_poisson_stencil), so nzl_peer is computable here
+    if (dn >= 0)
+    {
+        const int64_t M = h->n[2], m = nranks;
+        const int64_t nzl_peer = M / m + ((dn < (M % m)) ? 1 : 0);
+        h->ghost_dn = rbase(dn) + (size_t)(nzl_peer + 1) * (size_t)h->g.plane;
+    }
+    if (kernel_push(h))
+    {
+        cm.r_ghost_dn = h->ghost_dn;
+        cm.r_ghost_up = h->ghost_up;
+    }
+    invalidate_graph(h);
+    return B200LS_OK;
+}
+
+int b200ls_nccl_unique_id(void *id128)
+{
+    if (!id128) return B200LS_ERR_ARG;
+    NcclApi &api = nccl_api();
+    if (!api.ok) return B200LS_ERR_NCCL;
+    NcclUniqueId id;
+    if (api.GetUniqueId(&id) != 0) return B200LS_ERR_NCCL;
+    memcpy(id128, &id, 128);
+    return B200LS_OK;
+}
+
+int b200ls_nccl_init(b200ls_solver *h, const void *id128)
+{
+    if (!h || !id128) return B200LS_ERR_ARG;
+    NcclApi &api = nccl_api();
+    if (!api.ok) return fail(h, B200LS_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    cudaSetDevice(h->device);
+    NcclUniqueId id;
+    memcpy(&id, id128, 128);
+    const int rc = api.CommInitRank(&h->nccl, h->nranks, id, h->rank);
+    if (rc != 0) return fail(h, B200LS_ERR_NCCL, "ncclCommInitRank failed: %s", api.GetErrorString ? api.GetErrorString(rc) : "?");
+    return B200LS_OK;
+}
+
+// ---- operator ---------------------------------------------------------------------------
+int b200ls_set_poisson_stencil(b200ls_solver *h, int dim, const int64_t n[3], const int periodic[3], const double *dx,
+                               const double *dy, const double *dz, double dt, int64_t slab_lo, int64_t slab_hi)
+{
+    if (!h || !n || !periodic || !dx || !dy) return B200LS_ERR_ARG;
+    if (dim != 2 && dim != 3) return fail(h, B200LS_ERR_ARG, "dim must be 2 or 3");
+    if (dim == 3 && !dz) return fail(h, B200LS_ERR_ARG, "dz missing");
+    cudaSetDevice(h->device);
+    const int64_t nx = n[0], ny = n[1], nz = (dim == 3) ? n[2] : 1;
+    if (nx < 1 || ny < 1 || nz < 1) return fail(h, B200LS_ERR_ARG, "empty grid");
+    if (nx > (1 << 24) || ny > (1 << 24) || nz > (1 << 24) || nx * ny * nz > (int64_t)3 << 31)
+        return fail(h, B200LS_ERR_UNSUPPORTED, "grid too large for 32-bit item indexing");
+    for (int d = 0; d < dim; ++d)
+        if (periodic[d] && n[d] < 3) return fail(h, B200LS_ERR_UNSUPPORTED, "periodic axis %d needs at least 3 cells", d);
+    if (dim == 2)
+    {
+        if (h->nranks > 1) return fail(h, B200LS_ERR_UNSUPPORTED, "2-D grids run on one GPU");
+        slab_lo = 0;
+        slab_hi = 1;
+    }
+    if (slab_lo < 0 || slab_hi > nz || slab_lo >= slab_hi) return fail(h, B200LS_ERR_ARG, "bad slab [%lld,%lld)", (long long)slab_lo, (long long)slab_hi);
+    if (h->nranks == 1 && (slab_lo != 0 || slab_hi != nz)) return fail(h, B200LS_ERR_ARG, "single-GPU solver must own the whole grid");
+    if (h->nranks > 1)
+    {
+        // PETSc DMDA ownership rule along the slab axis: first M mod m ranks get one more
+        const int64_t M = nz, m = h->nranks;
+        if (M < m) return fail(h, B200LS_ERR_ARG, "fewer planes than ranks");
+        const int64_t base = M / m, rem = M % m;
+        const int64_t lo = h->rank * base + std::min<int64_t>(h->rank, rem);
+        const int64_t hi = lo + base + (h->rank < rem ? 1 : 0);
+        if (lo != slab_lo || hi != slab_hi)
+            return fail(h, B200LS_ERR_ARG, "slab [%lld,%lld) is not the DMDA range [%lld,%lld) of rank %d", (long long)slab_lo,
+                        (long long)slab_hi, (long long)lo, (long long)hi, h->rank);
+    }
+    free_vectors(h);
+    h->dim = dim;
+    h->n[0] = nx;
+    h->n[1] = ny;
+    h->n[2] = nz;
+    for (int d = 0; d < 3; ++d) h->per[d] = (d < dim) ? (periodic[d] != 0) : 0;
+    h->slab_lo = slab_lo;
+    h->slab_hi = slab_hi;
+    h->dt = dt;
+    h->hdx.assign(dx, dx + nx);
+    h->hdy.assign(dy, dy + ny);
+    if (dim == 3) h->hdz.assign(dz, dz + nz);
+    else h->hdz.assign(1, 1.0);  // cartesianmesh.cpp:91-99,166-171
+    // face coefficients dt*(1/h), h = 0.5*(dL[s-1]+dL[s]) (cartesianmesh.cpp:237-247, creategradient.cpp:72,
+    // createbn.cpp:49); g[s] = minus face of cell s
+    auto faces = [&](const std::vector<double> &d, bool per, bool active) {
+        const size_t m = d.size();
+        std::vector<double> g(m + 1, 0.0);
+        if (!active) return g;
+        for (size_t s = 1; s < m; ++s)
+        {
+            const double hh = 0.5 * (d[s] + d[s - 1]);
+            const double inv = 1.0 / hh;
+            g[s] = dt * inv;
+        }
+        if (per)
+        {
+            const double hh = 0.5 * (d[0] + d[m - 1]);
+            const double inv = 1.0 / hh;
+            g[0] = g[m] = dt * inv;
+        }
+        return g;
+    };
+    h->hgx = faces(h->hdx, h->per[0], true);
+    h->hgy = faces(h->hdy, h->per[1], true);
+    h->hgz = faces(h->hdz, h->per[2], dim == 3);
+    // device copies
+    const size_t tot = (size_t)(2 * (nx + ny + nz) + 3);
+    std::vector<double> pack;
+    pack.reserve(tot);
+    size_t o_dx = 0, o_dy, o_dz, o_gx, o_gy, o_gz;
+    pack.insert(pack.end(), h->hdx.begin(), h->hdx.end());
+    o_dy = pack.size();
+    pack.insert(pack.end(), h->hdy.begin(), h->hdy.end());
+    o_dz = pack.size();
+    pack.insert(pack.end(), h->hdz.begin(), h->hdz.end());
+    o_gx = pack.size();
+    pack.insert(pack.end(), h->hgx.begin(), h->hgx.end());
+    o_gy = pack.size();
+    pack.insert(pack.end(), h->hgy.begin(), h->hgy.end());
+    o_gz = pack.size();
+    pack.insert(pack.end(), h->hgz.begin(), h->hgz.end());
+    CU(h, cudaMalloc(&h->d_axes, sizeof(double) * pack.size()));
+    CU(h, cudaMemcpy(h->d_axes, pack.data(), sizeof(double) * pack.size(), cudaMemcpyHostToDevice));
+    GridDev &g = h->g;
+    g.nx = (int)nx;
+    g.ny = (int)ny;
+    g.nzl = (int)(slab_hi - slab_lo);
+    g.px = (int)round_up(nx, 16);
+    g.plane = (long long)g.px * g.ny;
+    g.perx = h->per[0];
+    g.pery = h->per[1];
+    g.perz_wrap = (h->per[2] && h->nranks == 1) ? 1 : 0;
+    g.kz0 = (int)slab_lo;
+    g.nzg = (int)nz;
+    g.wrapz_lo = (h->per[2] && slab_lo == 0) ? 1 : 0;
+    g.wrapz_hi = (h->per[2] && slab_hi == nz) ? 1 : 0;
+    g.dx = h->d_axes + o_dx;
+    g.dy = h->d_axes + o_dy;
+    g.dz = h->d_axes + o_dz;
+    g.gx = h->d_axes + o_gx;
+    g.gy = h->d_axes + o_gy;
+    g.gz = h->d_axes + o_gz;
+    h->nlocal = nx * ny * (slab_hi - slab_lo);
+    h->nglobal = nx * ny * nz;
+    h->vec_elems = (size_t)g.plane * (size_t)(g.nzl + 2);
+    h->op = OP_STENCIL;
+    TRY(setup_stencil_vectors(h));
+    build_commdev(h);
+    invalidate_graph(h);
+    if (spmv_grid_blocks(h) > h->max_blocks) return fail(h, B200LS_ERR_UNSUPPORTED, "grid needs more reduction slots than allocated");
+    return B200LS_OK;
+}
+
+int b200ls_verify_csr(b200ls_solver *h, int64_t nrows, const int64_t *rowptr, const int32_t *col, const double *val,
+                      double *max_abs_diff)
+{
+    if (!h || !rowptr || !col || !val) return B200LS_ERR_ARG;
+    if (h->op != OP_STENCIL) return fail(h, B200LS_ERR_ARG, "no stencil operator to verify");
+    if (nrows != h->nlocal) return fail(h, B200LS_ERR_MISMATCH, "row count %lld != %lld", (long long)nrows, (long long)h->nlocal);
+    const int64_t nx = h->n[0], ny = h->n[1], nz = h->n[2];
+    const int dim = h->dim;
+    double worst = 0.0;
+    int64_t bad_row = -1;
+    const volatile double *dx = h->hdx.data(), *dy = h->hdy.data(), *dz = h->hdz.data();
+    const volatile double *gx = h->hgx.data(), *gy = h->hgy.data(), *gz = h->hgz.data();
+    for (int64_t row = 0; row < nrows; ++row)
+    {
+        const int64_t i = row % nx, j = (row / nx) % ny, k = h->slab_lo + row / (nx * ny);
+        // expected entries: (global column, value); same products as k_spmv
+        int64_t ecol[7];
+        double eval[7];
+        int ne = 0;
+        const volatile double ayz = dy[j] * dz[k], axz = dx[i] * dz[k], axy = dx[i] * dy[j];
+        const volatile double cxm = ayz * gx[i], cxp = ayz * gx[i + 1];
+        const volatile double cym = axz * gy[j], cyp = axz * gy[j + 1];
+        const volatile double czm = axy * gz[k], czp = axy * gz[k + 1];
+        const bool wy = h->per[1] && j == 0, wz = h->per[2] && k == 0;
+        volatile double dg = cxm + cxp;
+        dg = dg + (wy ? cyp : cym);
+        dg = dg + (wy ? cym : cyp);
+        if (dim == 3)
+        {
+            dg = dg + (wz ? czp : czm);
+            dg = dg + (wz ? czm : czp);
+        }
+        const int64_t self = i + nx * (j + ny * k);
+        ecol[ne] = self;
+        eval[ne++] = -dg;
+        auto add = [&](double c, int64_t ii, int64_t jj, int64_t kk) {
+            if (c == 0.0) return;
+            ecol[ne] = ii + nx * (jj + ny * kk);
+            eval[ne++] = c;
+        };
+        add(cxm, (i - 1 + nx) % nx, j, k);
+        add(cxp, (i + 1) % nx, j, k);
+        add(cym, i, (j - 1 + ny) % ny, k);
+        add(cyp, i, (j + 1) % ny, k);
+        if (dim == 3)
+        {
+            add(czm, i, j, (k - 1 + nz) % nz);
+            add(czp, i, j, (k + 1) % nz);
+        }
+        // compare as sets (assembled rows may carry explicit zeros)
+        int matched = 0;
+        for (int64_t q = rowptr[row]; q < rowptr[row + 1]; ++q)
+        {
+            int e = -1;
+            for (int t = 0; t < ne; ++t)
+                if (ecol[t] == (int64_t)col[q]) e = t;
+            const double diff = (e >= 0) ? std::fabs(val[q] - eval[e]) : std::fabs(val[q]);
+            if (e >= 0) matched++;
+            if (diff > worst || (diff != diff))
+            {
+                worst = (diff != diff) ? INFINITY : diff;
+                bad_row = row;
+            }
+        }
+        if (matched != ne)
+        {
+            // an expected non-zero entry is missing from the assembled row
+            worst = INFINITY;
+            bad_row = row;
+        }
+    }
+    if (max_abs_diff) *max_abs_diff = worst;
+    if (worst != 0.0) return fail(h, B200LS_ERR_MISMATCH, "assembled matrix differs from the separable stencil (max |diff| %.3e, e.g. local row %lld)", worst, (long long)bad_row);
+    return B200LS_OK;
+}
+
+int b200ls_set_nullspace(b200ls_solver *h, int has_const, int nvecs, const double *vecs)
+{
+    if (!h) return B200LS_ERR_ARG;
+    if (h->op == OP_NONE) return fail(h, B200LS_ERR_ARG, "set the operator before its null space");
+    if (nvecs < 0 || (nvecs > 0 && !vecs)) return B200LS_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (h->op == OP_STENCIL && nvecs > 0) return fail(h, B200LS_ERR_UNSUPPORTED, "explicit null-space vectors need the CSR operator");
+    h->has_const = has_const ? 1 : 0;
+    if (h->op == OP_CSR) TRY(csr_set_nullvecs(h, nvecs, vecs));
+    invalidate_graph(h);
+    return B200LS_OK;
+}
+
+int b200ls_apply(b200ls_solver *h, const double *x_host, double *y_host)
+{
+    if (!h || !x_host || !y_host) return B200LS_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (h->op == OP_CSR) return csr_apply_host(h, x_host, y_host);
+    if (h->op != OP_STENCIL) return fail(h, B200LS_ERR_ARG, "no operator");
+    if (h->nranks > 1 && !h->connected) return fail(h, B200LS_ERR_ARG, "not connected");
+    const size_t nb = sizeof(double) * (size_t)h->nlocal;
+    CU(h, cudaMemcpyAsync(h->stage, x_host, nb, cudaMemcpyHostToDevice, h->stream));
+    k_state_reset<<<1, 32, 0, h->stream>>>(h->d_state);
+    k_scatter<<<h->num_sms * 8, 256, 0, h->stream>>>(h->g, h->stage, h->r, nullptr);
+    if (h->nranks > 1)
+    {
+        if (h->reduce_mode == B200LS_REDUCE_P2P)
+        {
+            k_barrier<<<1, 32, 0, h->stream>>>(h->cm, h->d_state);
+            k_push_halo<<<h->num_sms, 256, 0, h->stream>>>(h->g, h->r, h->ghost_dn, h->ghost_up);
+            k_barrier<<<1, 32, 0, h->stream>>>(h->cm, h->d_state);
+        }
+        else
+        {
+            TRY(post_reduce(h, FIN_INIT_CENTRE));
+            k_push_halo<<<h->num_sms, 256, 0, h->stream>>>(h->g, h->r, h->ghost_dn, h->ghost_up);
+            TRY(post_reduce(h, FIN_INIT_CENTRE));
+        }
+    }
+    VecSet v{h->r, nullptr, nullptr, h->w, nullptr, nullptr};
+    launch_spmv_t<false, true>(h, v, 0);
+    if (h->nranks > 1)
+    {
+        if (h->reduce_mode == B200LS_REDUCE_P2P) k_barrier<<<1, 32, 0, h->stream>>>(h->cm, h->d_state);
+        else TRY(post_reduce(h, FIN_INIT_CENTRE));
+    }
+    k_gather<<<h->num_sms * 8, 256, 0, h->stream>>>(h->g, h->w, h->stage);
+    CU(h, cudaMemcpyAsync(y_host, h->stage, nb, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(&h->h_state[0], h->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaGetLastError());
+    return check_state_err(h, h->h_state[0]);
+}
+
+// ---- solve ------------------------------------------------------------------------------
+int b200ls_solve_device(b200ls_solver *h, const double *b_dev, double *x_dev)
+{
+    if (!h || !b_dev || !x_dev) return B200LS_ERR_ARG;
+    cudaSetDevice(h->device);
+    int rc;
+    if (h->op == OP_STENCIL)
+    {
+        if (h->opt.ksp_type != B200LS_KSP_CG)
+            return fail(h, B200LS_ERR_UNSUPPORTED, "the separable stencil operator is solved with cg; bcgs needs the CSR operator");
+        rc = solve_stencil_cg(h, b_dev, x_dev);
+    }
+    else if (h->op == OP_CSR)
+        rc = csr_solve(h, b_dev, x_dev);
+    else
+        return fail(h, B200LS_ERR_ARG, "no operator set");
+    if (rc != B200LS_OK) return rc;
+    if (h->reason < 0) return fail(h, B200LS_ERR_DIVERGED, "diverged: KSPConvergedReason %d after %d iterations, residual %.6e", h->reason, h->its, h->rnorm);
+    return B200LS_OK;
+}
+
+int b200ls_solve(b200ls_solver *h, const double *b_host, double *x_host)
+{
+    if (!h || !b_host || !x_host) return B200LS_ERR_ARG;
+    if (h->op == OP_NONE) return fail(h, B200LS_ERR_ARG, "no operator set");
+    cudaSetDevice(h->device);
+    const size_t nb = sizeof(double) * (size_t)h->nlocal;
+    CU(h, cudaEventRecord(h->ev_e0, h->stream));
+    CU(h, cudaMemcpyAsync(h->stage, b_host, nb, cudaMemcpyHostToDevice, h->stream));
+    const int rc = b200ls_solve_device(h, h->stage, h->stage);
+    if (rc != B200LS_OK && rc != B200LS_ERR_DIVERGED) return rc;
+    CU(h, cudaMemcpyAsync(x_host, h->stage, nb, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaEventRecord(h->ev_e1, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_e0, h->ev_e1);
+    h->e2e_ms = ms;
+    return rc;
+}
+
+int b200ls_get_iters(const b200ls_solver *h, int *its)
+{
+    if (!h || !its) return B200LS_ERR_ARG;
+    *its = h->its;
+    return B200LS_OK;
+}
+int b200ls_get_residual(const b200ls_solver *h, double *rnorm)
+{
+    if (!h || !rnorm) return B200LS_ERR_ARG;
+    *rnorm = h->rnorm;
+    return B200LS_OK;
+}
+int b200ls_get_reason(const b200ls_solver *h, int *reason)
+{
+    if (!h || !reason) return B200LS_ERR_ARG;
+    *reason = h->reason;
+    return B200LS_OK;
+}
+int b200ls_get_history(const b200ls_solver *h, double *buf, int cap, int *n)
+{
+    if (!h || !n) return B200LS_ERR_ARG;
+    *n = (int)h->history.size();
+    if (buf && cap > 0) memcpy(buf, h->history.data(), sizeof(double) * (size_t)std::min<int>(cap, *n));
+    return B200LS_OK;
+}
+
+// ---- measurement ------------------------------------------------------------------------
+int b200ls_get_timing(const b200ls_solver *h, double *solve_ms, double *loop_ms, int64_t *launches)
+{
+    if (!h) return B200LS_ERR_ARG;
+    if (solve_ms) *solve_ms = h->solve_ms;
+    if (loop_ms) *loop_ms = h->loop_ms;
+    if (launches) *launches = h->launches;
+    return B200LS_OK;
+}
+int b200ls_get_e2e_ms(const b200ls_solver *h, double *e2e_ms)
+{
+    if (!h || !e2e_ms) return B200LS_ERR_ARG;
+    *e2e_ms = h->e2e_ms;
+    return B200LS_OK;
+}
+int b200ls_set_profile(b200ls_solver *h, int enable)
+{
+    if (!h) return B200LS_ERR_ARG;
+    h->profile = enable ? 1 : 0;
+    for (int q = 0; q < 4; ++q)
+    {
+        h->prof_ms[q] = 0.0;
+        h->prof_cnt[q] = 0;
+    }
+    return B200LS_OK;
+}
+int b200ls_get_profile(const b200ls_solver *h, int kclass, double *total_ms, int64_t *count)
+{
+    if (!h || kclass < 0 || kclass > 3) return B200LS_ERR_ARG;
+    if (total_ms) *total_ms = h->prof_ms[kclass];
+    if (count) *count = h->prof_cnt[kclass];
+    return B200LS_OK;
+}
+
+int b200ls_time_kernel(b200ls_solver *h, int kclass, int reps, int flush_l2, double *avg_ms)
+{
+    if (!h || !avg_ms || reps <= 0) return B200LS_ERR_ARG;
+    if (h->op != OP_STENCIL) return fail(h, B200LS_ERR_ARG, "kernel timing needs the stencil operator");
+    if (h->nranks > 1) return fail(h, B200LS_ERR_UNSUPPORTED, "kernel timing is single-GPU");
+    cudaSetDevice(h->device);
+    TRY(ensure_hist(h));
+    TRY(ensure_jacobi(h));
+    if (flush_l2 && !h->flush_buf)
+    {
+        h->flush_elems = (size_t)40 << 20;  // 320 MB > 126 MB L2
+        CU(h, cudaMalloc(&h->flush_buf, sizeof(double) * h->flush_elems));
+    }
+    // a benign state: never "done", a = 0 so the vectors keep their values, b = 0
+    DevState s{};
+    s.betaold = 1.0;
+    s.a = 0.0;
+    s.b = 0.0;
+    s.pending = 1;
+    double total = 0.0;
+    const b200ls_options keep = h->opt;
+    h->opt.max_it = 1 << 30;
+    h->opt.rtol = 0.0;
+    h->opt.atol = 0.0;
+    h->opt.divtol = 1e300;
+    cudaEvent_t e0, e1;
+    CU(h, cudaEventCreate(&e0));
+    CU(h, cudaEventCreate(&e1));
+    const bool jac = h->opt.pc_type == B200LS_PC_JACOBI;
+    for (int q = -2; q < reps; ++q)
+    {
+        CU(h, cudaMemcpyAsync(h->d_state, &s, sizeof s, cudaMemcpyHostToDevice, h->stream));
+        if (flush_l2) k_fill<<<h->num_sms * 8, 256, 0, h->stream>>>(h->flush_buf, (long long)h->flush_elems, 0.0);
+        CU(h, cudaEventRecord(e0, h->stream));
+        if (kclass == 0)
+        {
+            VecSet v{h->r, h->p[0], h->p[1], h->w, h->x, h->dinv};
+            if (jac) launch_spmv_t<true, false>(h, v, 0);
+            else launch_spmv_t<false, false>(h, v, 0);
+        }
+        else if (kclass == 1)
+        {
+            if (jac) launch_update_t<true, false>(h, FIN_UPDATE, false);
+            else launch_update_t<false, false>(h, FIN_UPDATE, false);
+        }
+        else
+        {
+            VecSet v{h->r, nullptr, nullptr, h->w, nullptr, nullptr};
+            launch_spmv_t<false, true>(h, v, 0);
+        }
+        CU(h, cudaEventRecord(e1, h->stream));
+        CU(h, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(h, cudaEventElapsedTime(&ms, e0, e1));
+        if (q >= 0) total += ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    h->opt = keep;
+    CU(h, cudaGetLastError());
+    *avg_ms = total / reps;
+    return B200LS_OK;
+}
+
+void *b200ls_stream(b200ls_solver *h) { return h ? (void *)h->stream : nullptr; }
+
+}  // extern "C"

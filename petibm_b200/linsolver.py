@@ -1,0 +1,326 @@
+"""Host-side mirror of PetIBM's linear-solver plugin interface for the B200 backend.
+
+Mirrors, name for name, ``petibm::linsolver::LinSolverBase`` (include/petibm/linsolver.h:59-147) and the
+factory ``createLinSolver`` (src/linsolver/linsolver.cpp:57-91); ``LinSolverB200`` is the third
+backend next to ``LinSolverKSP`` (src/linsolver/linsolverksp.cpp) and ``LinSolverAmgX``
+(src/linsolver/linsolveramgx.cpp).  All arithmetic happens in libb200ls.so (hand-written sm_100a CUDA
+behind the C ABI of include/b200ls.h); this module only moves pointers.  The C++ shim that does the
+same with real PETSc ``Mat``/``Vec`` objects is petibm_b200/csrc/petibm_shim/ (see INTEGRATION.md).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import B200Error
+from .mesh import Grid, slab_range
+
+
+class Mat:
+    """What ``setMatrix`` receives: the rank-local rows of an assembled AIJ matrix (CSR, global column
+    indices in natural/DMDA ordering) plus the null space the application attached with
+    ``MatSetNullSpace`` (navierstokes.cpp:404-413, ibpm.cpp:251-267)."""
+
+    def __init__(self, indptr, indices, data, ncols=None):
+        self.indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        self.indices = np.ascontiguousarray(indices, dtype=np.int32)
+        self.data = np.ascontiguousarray(data, dtype=np.float64)
+        self.nrows = int(self.indptr.size - 1)
+        self.ncols = int(ncols) if ncols is not None else self.nrows
+        self.null_has_const = False
+        self.null_vecs = None
+
+    @staticmethod
+    def from_scipy(A) -> "Mat":
+        A = A.tocsr()
+        A.sort_indices()
+        return Mat(A.indptr, A.indices, A.data, A.shape[1])
+
+    def setNullSpace(self, has_const: bool, vecs=None) -> "Mat":
+        """MatNullSpaceCreate(comm, has_cnst, n, vecs) + MatSetNullSpace."""
+        self.null_has_const = bool(has_const)
+        self.null_vecs = None if vecs is None else np.ascontiguousarray(np.atleast_2d(vecs), dtype=np.float64)
+        return self
+
+
+class LinSolverBase:
+    """include/petibm/linsolver.h:59-147."""
+
+    def __init__(self, solverName: str, file: str):
+        self.name = solverName
+        self.config = file
+        self.type = "undefined"
+
+    def getType(self) -> str:
+        return self.type
+
+    def printInfo(self) -> str:  # linsolver.cpp:27-46
+        info = "=" * 80 + "\n"
+        info += f"Linear Solver {self.name}:\n"
+        info += "=" * 80 + "\n"
+        info += f"\tType: {self.type}\n\n"
+        info += f"\tConfig file: {self.config}\n\n"
+        info += "=" * 80 + "\n"
+        return info
+
+    def destroy(self):
+        self.name = self.config = self.type = ""
+
+    # pure virtuals
+    def setMatrix(self, A):
+        raise NotImplementedError
+
+    def solve(self, x, b):
+        raise NotImplementedError
+
+    def getIters(self) -> int:
+        raise NotImplementedError
+
+    def getResidual(self) -> float:
+        raise NotImplementedError
+
+
+def _is_torch_cuda(t) -> bool:
+    return hasattr(t, "is_cuda") and bool(t.is_cuda)
+
+
+class LinSolverB200(LinSolverBase):
+    """The B200-native backend.
+
+    ``type`` reads "PETSc KSP" on purpose: the applications dispatch their null-space handling on that
+    string and abort on anything else (navierstokes.cpp:401-426, ibpm.cpp:248-280); reporting the KSP
+    type makes them attach the constant null space to DBNG exactly as they do for LinSolverKSP, which is
+    the behaviour this backend reproduces.  ``backend`` carries the real name for printInfo()."""
+
+    backend = "B200 sm_100a (libb200ls)"
+
+    def __init__(self, solverName: str, file: str, node=None, device: int | None = None, comm=None):
+        super().__init__(solverName, file)
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        self._node = node
+        self._comm = comm
+        self._grid = None
+        self.operator = None   # "stencil" | "csr" after setMatrix
+        if device is None:
+            device = comm.device if comm is not None else 0
+        _lib.check(self._L.b200ls_create(C.byref(self._h), int(device)))
+        self.init()
+
+    # ---- LinSolverKSP::init (linsolverksp.cpp:48-69)
+    def init(self):
+        self.type = "PETSc KSP"
+        opts = _lib.Options()
+        self._L.b200ls_default_options(C.byref(opts))
+        if self.config and self.config != "None":
+            with open(self.config, "r") as fh:
+                text = fh.read()
+            err = C.create_string_buffer(512)
+            rc = self._L.b200ls_parse_options(text.encode(), (self.name + "_").encode(), C.byref(opts), err, 512)
+            if rc != _lib.OK:
+                raise B200Error(rc, err.value.decode())
+        _lib.check(self._L.b200ls_set_options(self._h, C.byref(opts)), self._h)
+        if self._comm is not None and self._comm.nranks > 1:
+            self._comm.init_solver(self)
+
+    def printInfo(self) -> str:
+        return super().printInfo().replace(f"\tType: {self.type}\n", f"\tType: {self.type} (interface) / {self.backend}\n")
+
+    def destroy(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.b200ls_destroy(self._h)
+            self._h = C.c_void_p()
+        super().destroy()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    # ---- options access for tests / bench
+    def options(self) -> _lib.Options:
+        o = _lib.Options()
+        _lib.check(self._L.b200ls_get_options(self._h, C.byref(o)), self._h)
+        return o
+
+    def setOptions(self, **kw):
+        o = self.options()
+        names = {"cg": _lib.KSP_CG, "bcgs": _lib.KSP_BCGS, "none": _lib.PC_NONE, "jacobi": _lib.PC_JACOBI,
+                 "preconditioned": _lib.NORM_PRECONDITIONED, "unpreconditioned": _lib.NORM_UNPRECONDITIONED,
+                 "natural": _lib.NORM_NATURAL}
+        for k, v in kw.items():
+            if isinstance(v, str):
+                v = names[v]
+            setattr(o, k, v)
+        _lib.check(self._L.b200ls_set_options(self._h, C.byref(o)), self._h)
+
+    def setTuning(self, key: str, value: int):
+        _lib.check(self._L.b200ls_set_tuning(self._h, key.encode(), int(value)), self._h)
+
+    # ---- operator
+    def setGrid(self, grid: Grid):
+        """Grid description used to recognise the separable operator inside setMatrix; the factory fills
+        it from the YAML node (mesh, boundary conditions, dt) exactly like the C++ shim does."""
+        self._grid = grid
+
+    def _slab(self, grid: Grid):
+        nslow = grid.n[2] if grid.dim == 3 else 1
+        if self._comm is not None and self._comm.nranks > 1:
+            return slab_range(nslow, self._comm.rank, self._comm.nranks)
+        return 0, nslow
+
+    def setStencil(self, grid: Grid):
+        """Matrix-free operator D (dt I) G straight from the grid (what setMatrix does after recognising
+        the assembled matrix); used by the benchmark where assembling a 256^3 CSR on the host is not
+        part of the measured path."""
+        self._grid = grid
+        n = (C.c_int64 * 3)(*(list(grid.n) + [1] * (3 - grid.dim)))
+        per = (C.c_int * 3)(*[int(bool(p)) for p in grid.periodic])
+        w = [np.ascontiguousarray(a, dtype=np.float64) for a in grid.widths]
+        dz = w[2].ctypes.data_as(_lib._dp) if grid.dim == 3 else None
+        lo, hi = self._slab(grid)
+        _lib.check(self._L.b200ls_set_poisson_stencil(
+            self._h, grid.dim, n, per, w[0].ctypes.data_as(_lib._dp), w[1].ctypes.data_as(_lib._dp), dz,
+            float(grid.dt), lo, hi), self._h)
+        self.operator = "stencil"
+        self.nlocal = int(grid.n[0] * grid.n[1] * (hi - lo))
+        if self._comm is not None and self._comm.nranks > 1:
+            self._comm.connect_solver(self)
+
+    def setMatrix(self, A: Mat):
+        """LinSolverKSP::setMatrix (linsolverksp.cpp:72-82).  The matrix is copied/recognised here, the
+        caller keeps ownership (as with AmgXSolver::setA, linsolveramgx.cpp:84)."""
+        if not isinstance(A, Mat):
+            A = Mat.from_scipy(A)
+        recognised = False
+        if self._grid is not None:
+            lo, hi = self._slab(self._grid)
+            if A.nrows == self._grid.n[0] * self._grid.n[1] * (hi - lo):
+                self.setStencil(self._grid)
+                diff = C.c_double(0.0)
+                rc = self._L.b200ls_verify_csr(self._h, A.nrows, A.indptr.ctypes.data_as(_lib._i64p),
+                                               A.indices.ctypes.data_as(_lib._i32p), A.data.ctypes.data_as(_lib._dp),
+                                               C.byref(diff))
+                if rc == _lib.OK:
+                    recognised = True
+                elif rc != _lib.ERR_MISMATCH:
+                    _lib.check(rc, self._h)
+        if not recognised:
+            # general assembled operator, still on the GPU (IBPM modified Poisson, velocity system, BN > 1)
+            _lib.check(self._L.b200ls_set_csr(self._h, A.nrows, A.indptr.ctypes.data_as(_lib._i64p),
+                                              A.indices.ctypes.data_as(_lib._i32p), A.data.ctypes.data_as(_lib._dp)),
+                       self._h)
+            self.operator = "csr"
+            self.nlocal = A.nrows
+        nv = 0 if A.null_vecs is None else int(A.null_vecs.shape[0])
+        pv = A.null_vecs.ctypes.data_as(_lib._dp) if nv else None
+        _lib.check(self._L.b200ls_set_nullspace(self._h, int(A.null_has_const), nv, pv), self._h)
+
+    def setNullSpace(self, has_const: bool, vecs=None):
+        nv = 0 if vecs is None else int(np.atleast_2d(vecs).shape[0])
+        arr = None if vecs is None else np.ascontiguousarray(np.atleast_2d(vecs), dtype=np.float64)
+        _lib.check(self._L.b200ls_set_nullspace(self._h, int(bool(has_const)), nv,
+                                                arr.ctypes.data_as(_lib._dp) if nv else None), self._h)
+
+    # ---- LinSolverKSP::solve (linsolverksp.cpp:85-105): zero initial guess, error if reason < 0
+    def solve(self, x, b):
+        if _is_torch_cuda(b) or _is_torch_cuda(x):
+            if not (_is_torch_cuda(b) and _is_torch_cuda(x)):
+                raise ValueError("x and b must live on the same side")
+            import torch
+
+            if b.dtype != torch.float64 or x.dtype != torch.float64 or not b.is_contiguous() or not x.is_contiguous():
+                raise ValueError("device vectors must be contiguous float64")
+            if b.numel() != self.nlocal or x.numel() != self.nlocal:
+                raise ValueError("vector length does not match the operator")
+            torch.cuda.current_stream(b.device).synchronize()
+            rc = self._L.b200ls_solve_device(self._h, C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()))
+        else:
+            if hasattr(b, "data_ptr"):   # CPU torch tensors (pinned or not)
+                bp, xp, nb, nx_ = b.data_ptr(), x.data_ptr(), b.numel(), x.numel()
+            else:
+                if not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous):
+                    raise ValueError("x must be a contiguous float64 numpy array (it is written in place)")
+                b = np.ascontiguousarray(b, dtype=np.float64)
+                bp, xp, nb, nx_ = b.ctypes.data, x.ctypes.data, b.size, x.size
+            if nb != self.nlocal or nx_ != self.nlocal:
+                raise ValueError("vector length does not match the operator")
+            rc = self._L.b200ls_solve(self._h, C.c_void_p(bp), C.c_void_p(xp))
+        _lib.check(rc, self._h)   # reason < 0 raises, like SETERRQ2(PETSC_ERR_CONV_FAILED)
+        return x
+
+    def apply(self, x):
+        """y = A x through the device operator (tests)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        _lib.check(self._L.b200ls_apply(self._h, C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data)), self._h)
+        return y
+
+    def getIters(self) -> int:
+        v = C.c_int(0)
+        _lib.check(self._L.b200ls_get_iters(self._h, C.byref(v)), self._h)
+        return v.value
+
+    def getResidual(self) -> float:
+        v = C.c_double(0.0)
+        _lib.check(self._L.b200ls_get_residual(self._h, C.byref(v)), self._h)
+        return v.value
+
+    def getReason(self) -> int:
+        v = C.c_int(0)
+        _lib.check(self._L.b200ls_get_reason(self._h, C.byref(v)), self._h)
+        return v.value
+
+    def getHistory(self) -> np.ndarray:
+        n = C.c_int(0)
+        _lib.check(self._L.b200ls_get_history(self._h, None, 0, C.byref(n)), self._h)
+        buf = np.empty(max(n.value, 1), dtype=np.float64)
+        _lib.check(self._L.b200ls_get_history(self._h, buf.ctypes.data_as(_lib._dp), n.value, C.byref(n)), self._h)
+        return buf[: n.value].copy()
+
+    # ---- measurement hooks
+    def timing(self):
+        s, l, k = C.c_double(0), C.c_double(0), C.c_int64(0)
+        _lib.check(self._L.b200ls_get_timing(self._h, C.byref(s), C.byref(l), C.byref(k)), self._h)
+        e = C.c_double(0)
+        _lib.check(self._L.b200ls_get_e2e_ms(self._h, C.byref(e)), self._h)
+        return {"solve_ms": s.value, "loop_ms": l.value, "launches": k.value, "e2e_ms": e.value}
+
+    def setProfile(self, enable: bool):
+        _lib.check(self._L.b200ls_set_profile(self._h, int(bool(enable))), self._h)
+
+    def profile(self, kclass: int):
+        t, c = C.c_double(0), C.c_int64(0)
+        _lib.check(self._L.b200ls_get_profile(self._h, int(kclass), C.byref(t), C.byref(c)), self._h)
+        return t.value, c.value
+
+    def timeKernel(self, kclass: int, reps: int = 20, flush_l2: bool = True) -> float:
+        v = C.c_double(0)
+        _lib.check(self._L.b200ls_time_kernel(self._h, int(kclass), int(reps), int(bool(flush_l2)), C.byref(v)), self._h)
+        return v.value
+
+
+def createLinSolver(solverName: str, node, device: int | None = None, comm=None) -> LinSolverBase:
+    """petibm::linsolver::createLinSolver (src/linsolver/linsolver.cpp:57-91) with the third branch.
+
+    ``parameters.<name>Solver.type``: "CPU" -> LinSolverKSP and "GPU" -> LinSolverAmgX exist only inside
+    PetIBM (PETSc / AmgX are not part of this package), "B200" -> LinSolverB200."""
+    key = solverName + "Solver"
+    params = node.get("parameters", {}).get(key, {})
+    stype = str(params.get("type", "CPU"))
+    config = str(params.get("config", "None"))
+    if config != "None" and not config.startswith("/"):
+        config = os.path.join(str(node["directory"]), config)
+    if stype == "B200":
+        solver = LinSolverB200(solverName, config, node=node, device=device, comm=comm)
+        if "mesh" in node:
+            solver.setGrid(Grid.from_config(node))
+        return solver
+    if stype in ("CPU", "GPU"):
+        raise ValueError(f'solver type "{stype}" of "{solverName}" is PetIBM\'s own PETSc KSP / AmgX backend; '
+                         'this package provides only type "B200"')
+    raise ValueError(f'Unrecognized value "{stype}" of the type of the linear solver "{solverName}"')
