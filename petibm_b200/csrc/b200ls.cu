@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "spmv2.cuh"
 #include "csr_kernels.cuh"
 
 using namespace b200;
@@ -308,21 +309,33 @@ void resolve_profile(b200ls_solver *h)
 // launch wrappers
 // ------------------------------------------------------------------------------------------
 struct TileCfg { int txt, tyt; };
+// tile < 10: first-generation register-prefetch kernel (k_spmv); tile >= 10: cp.async ring kernel (k_spmv2)
 inline TileCfg tile_cfg(const b200ls_solver *h)
 {
     switch (h->tile)
     {
+        case 0: return {32, 8};
         case 1: return {32, 6};
         case 2: return {32, 10};
         case 3: return {16, 10};
         case 4: return {32, 16};
-        default: return {32, 8};
+        case 11: return {32, 8};
+        case 12: return {32, 10};
+        case 13: return {32, 6};
+        case 14: return {32, 12};
+        case 15: return {32, 8};
+        case 16: return {32, 16};
+        case 17: return {32, 8};
+        case 18: return {32, 12};
+        case 19: return {32, 10};
+        case 20: return {32, 16};
+        default: return {32, 8};  // 10
     }
 }
 
 inline int auto_kz_chunk(const b200ls_solver *h)
 {
-    if (h->kz_chunk > 0) return std::min<int>(h->kz_chunk, h->g.nzl);
+    if (h->kz_chunk > 0) return std::min<int>(std::min<int>(h->kz_chunk, h->g.nzl), 512);
     const TileCfg t = tile_cfg(h);
     const int64_t bx = (h->g.nx + 2 * t.txt - 1) / (2 * t.txt), by = (h->g.ny + (t.tyt - 2) - 1) / (t.tyt - 2);
     const int64_t xy = bx * by;
@@ -330,12 +343,45 @@ inline int auto_kz_chunk(const b200ls_solver *h)
     const int64_t target = (int64_t)h->num_sms * per_sm;  // one full wave of resident blocks
     int64_t nch = std::max<int64_t>(1, (target + xy - 1) / xy);
     nch = std::min<int64_t>(nch, std::max<int64_t>(1, h->g.nzl / 8));
-    nch = std::max<int64_t>(nch, 1);
+    nch = std::max<int64_t>(nch, (h->g.nzl + 511) / 512);  // the coefficient table of a chunk holds 512 planes
     return (int)((h->g.nzl + nch - 1) / nch);
 }
 
+inline bool grid_periodic(const b200ls_solver *h) { return h->per[0] || h->per[1] || h->per[2]; }
+
+template <int TYT, int S, int MINB, bool JAC, bool APPLY>
+int launch_spmv2_cfg(b200ls_solver *h, const VecSet &v, int ghost_store, dim3 grid, int kz)
+{
+    using L = Spmv2Smem<32, TYT, S, JAC, APPLY>;
+    const SolveConsts kc = make_consts(h);
+    dim3 block(32, TYT);
+    if (grid_periodic(h))
+    {
+        auto kern = k_spmv2<32, TYT, S, MINB, JAC, APPLY, true>;
+        static bool attr_done = false;
+        if (!attr_done)
+        {
+            CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total(512)));
+            attr_done = true;
+        }
+        kern<<<grid, block, L::total(kz), h->stream>>>(h->g, v, kz, h->ws, h->cm, h->d_state, kc, h->d_hist, ghost_store);
+    }
+    else
+    {
+        auto kern = k_spmv2<32, TYT, S, MINB, JAC, APPLY, false>;
+        static bool attr_done = false;
+        if (!attr_done)
+        {
+            CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total(512)));
+            attr_done = true;
+        }
+        kern<<<grid, block, L::total(kz), h->stream>>>(h->g, v, kz, h->ws, h->cm, h->d_state, kc, h->d_hist, ghost_store);
+    }
+    return B200LS_OK;
+}
+
 template <bool JAC, bool APPLY>
-void launch_spmv_t(b200ls_solver *h, const VecSet &v, int ghost_store)
+int launch_spmv_t(b200ls_solver *h, const VecSet &v, int ghost_store)
 {
     const TileCfg t = tile_cfg(h);
     const int kz = auto_kz_chunk(h);
@@ -343,19 +389,32 @@ void launch_spmv_t(b200ls_solver *h, const VecSet &v, int ghost_store)
               (unsigned)((h->g.nzl + kz - 1) / kz));
     dim3 block(t.txt, t.tyt);
     const SolveConsts kc = make_consts(h);
+    h->launches++;
 #define B200_SPMV_CASE(TXT, TYT)                                                                               \
     k_spmv<TXT, TYT, JAC, APPLY><<<grid, block, 0, h->stream>>>(h->g, v, kz, h->ws, h->cm, h->d_state, kc, \
                                                                  h->d_hist, ghost_store)
+    if (APPLY && h->tile >= 10) return launch_spmv2_cfg<8, 4, 3, JAC, APPLY>(h, v, ghost_store, dim3(grid.x, (unsigned)((h->g.ny + 5) / 6), grid.z), kz);
     switch (h->tile)
     {
+        case 0: B200_SPMV_CASE(32, 8); break;
         case 1: B200_SPMV_CASE(32, 6); break;
         case 2: B200_SPMV_CASE(32, 10); break;
         case 3: B200_SPMV_CASE(16, 10); break;
         case 4: B200_SPMV_CASE(32, 16); break;
-        default: B200_SPMV_CASE(32, 8); break;
+        case 11: return launch_spmv2_cfg<8, 2, 4, JAC, false>(h, v, ghost_store, grid, kz);
+        case 12: return launch_spmv2_cfg<10, 4, 2, JAC, false>(h, v, ghost_store, grid, kz);
+        case 13: return launch_spmv2_cfg<6, 4, 4, JAC, false>(h, v, ghost_store, grid, kz);
+        case 14: return launch_spmv2_cfg<12, 2, 2, JAC, false>(h, v, ghost_store, grid, kz);
+        case 15: return launch_spmv2_cfg<8, 3, 3, JAC, false>(h, v, ghost_store, grid, kz);
+        case 16: return launch_spmv2_cfg<16, 2, 1, JAC, false>(h, v, ghost_store, grid, kz);
+        case 17: return launch_spmv2_cfg<8, 3, 4, JAC, false>(h, v, ghost_store, grid, kz);
+        case 18: return launch_spmv2_cfg<12, 3, 2, JAC, false>(h, v, ghost_store, grid, kz);
+        case 19: return launch_spmv2_cfg<10, 2, 3, JAC, false>(h, v, ghost_store, grid, kz);
+        case 20: return launch_spmv2_cfg<16, 2, 2, JAC, false>(h, v, ghost_store, grid, kz);
+        default: return launch_spmv2_cfg<8, 4, 3, JAC, false>(h, v, ghost_store, grid, kz);
     }
 #undef B200_SPMV_CASE
-    h->launches++;
+    return B200LS_OK;
 }
 
 int spmv_grid_blocks(const b200ls_solver *h)
@@ -447,8 +506,8 @@ int enqueue_spmv(b200ls_solver *h, int parity)
     {
         ProfScope ps(h, 0);
         const int ghost_store = h->nranks > 1 ? 1 : 0;
-        if (jac) launch_spmv_t<true, false>(h, v, ghost_store);
-        else launch_spmv_t<false, false>(h, v, ghost_store);
+        if (jac) TRY((launch_spmv_t<true, false>(h, v, ghost_store)));
+        else TRY((launch_spmv_t<false, false>(h, v, ghost_store)));
     }
     return post_reduce(h, FIN_SPMV);
 }
@@ -625,8 +684,9 @@ int solve_stencil_cg(b200ls_solver *h, const double *b_dev, double *x_dev)
     {
         while (outstanding.size() < 2 && issued < h->opt.max_it)
         {
-            TRY(launch_cg_batch(h, issued, check));
-            issued += check;
+            const int count = std::min(check, h->opt.max_it - issued);  // never queue past max_it
+            TRY(launch_cg_batch(h, issued, count));
+            issued += count;
             TRY(snapshot());
         }
         const int s = outstanding.front();
@@ -913,6 +973,8 @@ int b200ls_create(b200ls_solver **out, int device)
         delete h;
         return rc;
     }
+    if (const char *e = getenv("B200LS_TILE")) h->tile = atoi(e);
+    if (const char *e = getenv("B200LS_KZ_CHUNK")) h->kz_chunk = atoi(e);
     build_commdev(h);
     *out = h;
     return B200LS_OK;
@@ -1322,7 +1384,7 @@ int b200ls_apply(b200ls_solver *h, const double *x_host, double *y_host)
         }
     }
     VecSet v{h->r, nullptr, nullptr, h->w, nullptr, nullptr};
-    launch_spmv_t<false, true>(h, v, 0);
+    TRY((launch_spmv_t<false, true>(h, v, 0)));
     if (h->nranks > 1)
     {
         if (h->reduce_mode == B200LS_REDUCE_P2P) k_barrier<<<1, 32, 0, h->stream>>>(h->cm, h->d_state);
@@ -1473,8 +1535,8 @@ int b200ls_time_kernel(b200ls_solver *h, int kclass, int reps, int flush_l2, dou
         if (kclass == 0)
         {
             VecSet v{h->r, h->p[0], h->p[1], h->w, h->x, h->dinv};
-            if (jac) launch_spmv_t<true, false>(h, v, 0);
-            else launch_spmv_t<false, false>(h, v, 0);
+            if (jac) TRY((launch_spmv_t<true, false>(h, v, 0)));
+            else TRY((launch_spmv_t<false, false>(h, v, 0)));
         }
         else if (kclass == 1)
         {
@@ -1484,7 +1546,7 @@ int b200ls_time_kernel(b200ls_solver *h, int kclass, int reps, int flush_l2, dou
         else
         {
             VecSet v{h->r, nullptr, nullptr, h->w, nullptr, nullptr};
-            launch_spmv_t<false, true>(h, v, 0);
+            TRY((launch_spmv_t<false, true>(h, v, 0)));
         }
         CU(h, cudaEventRecord(e1, h->stream));
         CU(h, cudaEventSynchronize(e1));
