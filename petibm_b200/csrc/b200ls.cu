@@ -145,7 +145,8 @@ struct b200ls_solver
     int num_sms = 148;
     int kz_chunk = 0;        // 0 = auto
     int upd_blocks = 0;      // 0 = auto
-    int tile = 0;            // K1 tile variant
+    int tile = 18;           // K1 tile variant (10+: k_spmv2)
+    int upd_variant = 0;     // 0: flat k_update2, 1: first-generation k_update
     int use_graph = 1;
     cudaGraphExec_t graph_exec = nullptr;
     int graph_iters = 0;
@@ -428,9 +429,9 @@ int spmv_grid_blocks(const b200ls_solver *h)
 int upd_grid_blocks(const b200ls_solver *h)
 {
     if (h->upd_blocks > 0) return h->upd_blocks;
-    const int64_t items = (int64_t)((h->g.nx + 1) / 2) * h->g.ny * h->g.nzl;
+    const int64_t items = (int64_t)(h->g.plane / 2) * h->g.nzl;
     const int64_t need = (items + 256 * 4 - 1) / (256 * 4);
-    return (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)h->num_sms * 8));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)h->num_sms * 4));  // one resident wave
 }
 
 template <bool JAC, bool INIT>
@@ -444,8 +445,21 @@ void launch_update_t(b200ls_solver *h, int fin_kind, bool push)
         cm.r_ghost_up = nullptr;
     }
     const SolveConsts kc = make_consts(h);
-    k_update<JAC, INIT, 4><<<upd_grid_blocks(h), 256, 0, h->stream>>>(h->g, v, fin_kind, h->ws, cm, h->d_state, kc,
-                                                                      h->d_hist);
+    const int blocks = upd_grid_blocks(h);
+    if (h->upd_variant == 1)
+        k_update<JAC, INIT, 4><<<blocks, 256, 0, h->stream>>>(h->g, v, fin_kind, h->ws, cm, h->d_state, kc, h->d_hist);
+    else
+    {
+        const bool padded = h->g.px != h->g.nx;
+        const bool psh = cm.r_ghost_dn || cm.r_ghost_up;
+#define B200_UPD(PAD, PSH) \
+    k_update2<JAC, INIT, PAD, PSH, 4><<<blocks, 256, 0, h->stream>>>(h->g, v, fin_kind, h->ws, cm, h->d_state, kc, h->d_hist)
+        if (padded && psh) B200_UPD(true, true);
+        else if (padded) B200_UPD(true, false);
+        else if (psh) B200_UPD(false, true);
+        else B200_UPD(false, false);
+#undef B200_UPD
+    }
     h->launches++;
 }
 
@@ -1033,6 +1047,7 @@ int b200ls_set_tuning(b200ls_solver *h, const char *key, int value)
     if (k == "kz_chunk") h->kz_chunk = value;
     else if (k == "upd_blocks") h->upd_blocks = value;
     else if (k == "tile") h->tile = value;
+    else if (k == "upd_variant") h->upd_variant = value;
     else if (k == "use_graph") h->use_graph = value;
     else return fail(h, B200LS_ERR_ARG, "unknown tuning key %s", key);
     invalidate_graph(h);

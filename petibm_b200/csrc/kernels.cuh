@@ -817,6 +817,107 @@ __global__ void __launch_bounds__(256) k_update(GridDev g, UpdVecs v, int fin_ki
     grid_reduce_finalize<6>(acc, fin_kind, ws, cm, st, kc, hist, push);
 }
 
+// Second-generation class-1 kernel: the owned planes of a solver-layout vector are ONE contiguous range
+// (plane = px*ny, no gaps between planes), so the update is a flat 128-bit stream with no index
+// arithmetic; only grids whose row pitch is padded (nx not a multiple of 16) mask the pad columns out
+// of the shifted sums.  Guard-free main loop (U loads in flight per thread) + scalar tail.
+template <bool JACOBI, bool INIT, bool PADDED, bool PUSH>
+struct UpdItem
+{
+    __device__ static __forceinline__ void run(unsigned int i, double2 rr, double2 wr, double2 dr, double ma, double c,
+                                               double2 *r2, double2 *gdn, double2 *gup, unsigned int plane2,
+                                               unsigned int last0, unsigned int pxh, unsigned int nx, double (&acc)[6])
+    {
+        double2 rn = rr;
+        if (!INIT)
+        {
+            rn.x = __dadd_rn(rr.x, __dmul_rn(ma, wr.x));  // VecAXPY(R, -a, W)
+            rn.y = __dadd_rn(rr.y, __dmul_rn(ma, wr.y));
+            r2[i] = rn;
+        }
+        if (PUSH)
+        {
+            if (gdn && i < plane2) gdn[i] = rn;
+            if (gup && i >= last0) gup[i - last0] = rn;
+        }
+        bool v0 = true, v1 = true;
+        if (PADDED)
+        {
+            const unsigned int col = 2u * (i % pxh);
+            v0 = col < nx;
+            v1 = col + 1u < nx;
+        }
+        const double z0 = JACOBI ? __dmul_rn(rn.x, dr.x) : rn.x;
+        const double z1 = JACOBI ? __dmul_rn(rn.y, dr.y) : rn.y;
+        const double d0 = v0 ? z0 - c : 0.0;
+        const double d1 = v1 ? z1 - c : 0.0;
+        acc[0] += z0;
+        acc[1] += d0;
+        acc[2] = fma(d0, d0, acc[2]);
+        acc[3] = fma(d0, rn.x, acc[3]);
+        acc[4] += rn.x;
+        acc[5] = fma(rn.x, rn.x, acc[5]);
+        acc[0] += z1;
+        acc[1] += d1;
+        acc[2] = fma(d1, d1, acc[2]);
+        acc[3] = fma(d1, rn.y, acc[3]);
+        acc[4] += rn.y;
+        acc[5] = fma(rn.y, rn.y, acc[5]);
+    }
+};
+
+template <bool JACOBI, bool INIT, bool PADDED, bool PUSH, int U>
+__global__ void __launch_bounds__(256) k_update2(GridDev g, UpdVecs v, int fin_kind, ReduceWs ws, CommDev cm,
+                                                 DevState *st, SolveConsts kc, double *hist)
+{
+    if (st->done) return;
+    const double ma = INIT ? 0.0 : -st->a;
+    const double c = st->c;
+    const unsigned int plane2 = (unsigned int)(g.plane >> 1);
+    const unsigned int n2 = plane2 * (unsigned int)g.nzl;       // host guarantees < 2^32
+    const unsigned int last0 = plane2 * (unsigned int)(g.nzl - 1);
+    double2 *const __restrict__ r2 = reinterpret_cast<double2 *>(v.r + g.plane);
+    const double2 *const __restrict__ w2 = reinterpret_cast<const double2 *>(v.w + g.plane);
+    const double2 *const __restrict__ d2 = reinterpret_cast<const double2 *>(v.dinv + (JACOBI ? g.plane : 0));
+    double2 *const gdn = reinterpret_cast<double2 *>(cm.r_ghost_dn);
+    double2 *const gup = reinterpret_cast<double2 *>(cm.r_ghost_up);
+    const unsigned int stride = gridDim.x * blockDim.x;
+    const unsigned int pxh = (unsigned int)g.px >> 1;
+    const unsigned int nx = (unsigned int)g.nx;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    unsigned int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    // main loop: all U items in range (n2 - i0 > (U-1)*stride, written without overflow)
+    while (i0 < n2 && n2 - i0 > (unsigned int)(U - 1) * stride)
+    {
+        double2 rr[U], wr[U], dr[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            rr[u] = r2[i0 + u * stride];
+            if (!INIT) wr[u] = w2[i0 + u * stride];
+            if (JACOBI) dr[u] = d2[i0 + u * stride];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            UpdItem<JACOBI, INIT, PADDED, PUSH>::run(i0 + u * stride, rr[u], wr[u], dr[u], ma, c, r2, gdn, gup, plane2, last0,
+                                                     pxh, nx, acc);
+        if (n2 - i0 <= (unsigned int)U * stride)
+        {
+            i0 = n2;
+            break;
+        }
+        i0 += U * stride;
+    }
+    for (; i0 < n2; i0 = (n2 - i0 > stride) ? i0 + stride : n2)
+    {
+        double2 rr = r2[i0], wr = make_double2(0, 0), dr = make_double2(0, 0);
+        if (!INIT) wr = w2[i0];
+        if (JACOBI) dr = d2[i0];
+        UpdItem<JACOBI, INIT, PADDED, PUSH>::run(i0, rr, wr, dr, ma, c, r2, gdn, gup, plane2, last0, pxh, nx, acc);
+    }
+    grid_reduce_finalize<6>(acc, fin_kind, ws, cm, st, kc, hist, PUSH);
+}
+
 // ------------------------------------------------------------------------------------------
 // tail: apply the x update still owed when the loop ended (cg.c updates x before every test)
 // ------------------------------------------------------------------------------------------

@@ -94,6 +94,18 @@ def test_cg_history_matches_oracle(pb, pc, shape, per):
     s.destroy()
 
 
+def _order_sensitivity(A, b, **kw):
+    """Relative difference between two CPU summation orders of the SAME algorithm (strict serial vs
+    OpenMP/SIMD reductions): the floor below which no implementation can be compared."""
+    ref = orc.ksp_solve(A, b, **kw)
+    orc.set_fast(True, 4)
+    alt = orc.ksp_solve(A, b, **kw)
+    orc.set_fast(False, 0)
+    m = min(ref.history.size, alt.history.size)
+    sens = np.abs(ref.history[:m] - alt.history[:m]) / ref.history[:m]
+    return ref, alt, sens
+
+
 @pytest.mark.parametrize("check_every", [2, 7, 32])
 def test_converged_reasons_and_iteration_counts(pb, check_every):
     shape, per = (16, 12, 10), (0, 0, 0)
@@ -103,17 +115,23 @@ def test_converged_reasons_and_iteration_counts(pb, check_every):
     grid = H.grid_of(widths, per)
     for kw in (dict(rtol=0.0, atol=1e-6, max_it=2000), dict(rtol=1e-6, atol=1e-50, max_it=2000),
                dict(rtol=1e-12, atol=1e-50, max_it=5000)):
-        ref = orc.ksp_solve(A, b, const_nullspace=True, **kw)
+        ref, alt, sens = _order_sensitivity(A, b, const_nullspace=True, **kw)
         s = _solver(pb, grid, check_every=check_every, **kw)
         s.setNullSpace(True)
         x = np.empty_like(b)
         s.solve(x, b)
         assert s.getReason() == ref.reason
-        assert abs(s.getIters() - ref.its) <= 1          # a tolerance crossing can fall either side
-        if s.getIters() == ref.its:
-            np.testing.assert_allclose(s.getHistory(), ref.history, rtol=1e-7)
+        # a tolerance crossing can fall either side once round-off has been amplified; the two CPU
+        # summation orders bound how far apart two correct implementations may end
+        assert abs(s.getIters() - ref.its) <= max(1, abs(alt.its - ref.its) + 1)
+        hist = s.getHistory()
+        assert hist.size == s.getIters() + 1
+        m = min(hist.size, sens.size)
+        rel = np.abs(hist[:m] - ref.history[:m]) / ref.history[:m]
+        # 1e-10 wherever the algorithm itself is reproducible to 1e-12; elsewhere within 100x of the
+        # order sensitivity of the oracle
+        assert np.all(rel <= np.maximum(HIST_RTOL, 100.0 * sens[:m])), (rel.max(), sens.max())
         np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-6 * np.abs(ref.x).max())
-        assert s.getHistory().size == s.getIters() + 1
         s.destroy()
 
 
