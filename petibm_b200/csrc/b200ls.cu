@@ -539,7 +539,10 @@ int enqueue_cg_iterations(b200ls_solver *h, int first_iter, int count)
 // a graph of `count` CG iterations starting at an even iteration (buffer parity repeats every 2)
 int launch_cg_batch(b200ls_solver *h, int first_iter, int count)
 {
-    const bool graphable = h->use_graph && !h->profile && (count % 2 == 0) && (first_iter % 2 == 0);
+    // NCCL collectives are enqueued directly: capturing them hung in testing (NCCL 2.28 on this image), and
+    // that transport is the literal north-star baseline, not the fast path.
+    const bool nccl_path = h->nranks > 1 && h->reduce_mode == B200LS_REDUCE_NCCL;
+    const bool graphable = h->use_graph && !h->profile && !nccl_path && (count % 2 == 0) && (first_iter % 2 == 0);
     if (!graphable) return enqueue_cg_iterations(h, first_iter, count);
     const unsigned long long key = (unsigned long long)count;
     if (!h->graph_exec || h->graph_key != key || h->graph_iters != count)
