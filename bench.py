@@ -84,58 +84,105 @@ def traffic_record():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock / throttle reasons of one GPU during the timed region, polled in-process through NVML
+    (nvidia-ml-py) every 100 ms; falls back to an `nvidia-smi -lms` child process."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.device = device
-        self.rows = []
+        self.rows = []          # (sm_mhz, max_mhz, power_w, reasons bitmask or set)
         self.proc = None
+        self.nvml = None
+        self._stop = threading.Event()
+
+    def _uuid_index(self):
+        # CUDA_VISIBLE_DEVICES may renumber; torch reports the UUID of the CUDA device
+        try:
+            import torch
+
+            uuid = str(torch.cuda.get_device_properties(self.device).uuid)
+            return "GPU-" + uuid if not uuid.startswith("GPU-") else uuid
+        except Exception:
+            return None
 
     def start(self):
         try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            uuid = self._uuid_index()
+            self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid) if uuid \
+                else pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.device)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _poll_nvml(self):
+        n = self.nvml
+        R = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+             "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+             "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+             "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        while not self._stop.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append((float(sm), float(mx), pw, {k for k, b in R.items() if mask & b}))
+            except Exception:
+                pass
+            self._stop.wait(0.1)
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
+    def _pump(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [c.strip() for c in r.split(",")]
+        for line in self.proc.stdout:
+            f = [c.strip() for c in line.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-                power.append(float(f[2]))
+                self.rows.append((float(f[0]), float(f[1]), float(f[2]),
+                                  {nm for nm, v in zip(names, f[3:7]) if v.lower().startswith("active")}))
             except ValueError:
                 continue
-            for name, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+
+    def stop(self):
+        if self.nvml is None and not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+        else:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power) if power else None}
+        reasons = set()
+        for r in self.rows:
+            reasons |= r[3]
+        return {"sm_mhz": float(np.median([r[0] for r in self.rows])), "sm_max_mhz": float(max(r[1] for r in self.rows)),
+                "reasons": sorted(reasons), "samples": len(self.rows), "power_w_max": max(r[2] for r in self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -245,11 +292,12 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         one_solve(x_dev, b_dev)
     # ---- timed region 1: device-resident ---------------------------------------------------
-    sampler = ClockSampler(comm.device)
+    sampler = ClockSampler(comm.device) if comm.rank == 0 else None
     solver.setProfile(profile)
     comm.barrier()
     torch.cuda.synchronize()
-    sampler.start()
+    if sampler:
+        sampler.start()
     t_wall0 = time.perf_counter()
     dev_ms, launches = 0.0, 0
     for _ in range(args.steps):
@@ -260,7 +308,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     comm.barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     k1_ms, k1_n = solver.profile(0)
     k2_ms, k2_n = solver.profile(1)
     solver.setProfile(False)

@@ -195,6 +195,11 @@ int b200ls_get_profile(const b200ls_solver *h, int kclass, double *total_ms, int
  * launch duration in ms (CUDA events on the solver stream); flush_l2 != 0 writes a >L2 buffer
  * between launches. kclass as above; 2 = plain SpMV (b200ls_apply path). */
 int b200ls_time_kernel(b200ls_solver *h, int kclass, int reps, int flush_l2, double *avg_ms);
+/* Device-side timeline of the reduction-carrying kernels (diagnostics): capacity entries of 5 uint64
+ * {kernel start, local grid reduction done, cross-GPU all-reduce done, scalar logic done, kind} in
+ * %globaltimer nanoseconds; b200ls_get_trace copies and clears. capacity 0 disables. */
+int b200ls_set_trace(b200ls_solver *h, int capacity);
+int b200ls_get_trace(b200ls_solver *h, unsigned long long *buf, int capacity, int *n);
 void *b200ls_stream(b200ls_solver *h); /* cudaStream_t of the solver, for external event timing */
 
 #ifdef __cplusplus

@@ -75,6 +75,8 @@ SIGNATURES = {
     "b200ls_set_profile": (C.c_int, [_vp, C.c_int]),
     "b200ls_get_profile": (C.c_int, [_vp, C.c_int, _dp, _i64p]),
     "b200ls_time_kernel": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp]),
+    "b200ls_set_trace": (C.c_int, [_vp, C.c_int]),
+    "b200ls_get_trace": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.c_int, _ip]),
     "b200ls_stream": (_vp, [_vp]),
 }
 

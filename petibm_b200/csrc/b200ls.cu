@@ -429,9 +429,12 @@ int spmv_grid_blocks(const b200ls_solver *h)
 int upd_grid_blocks(const b200ls_solver *h)
 {
     if (h->upd_blocks > 0) return h->upd_blocks;
+    // one resident wave (4 CTAs/SM); the block count is chosen so that every thread runs the same number
+    // of guard-free 4-item trips (no serial scalar tail on small slabs)
     const int64_t items = (int64_t)(h->g.plane / 2) * h->g.nzl;
-    const int64_t need = (items + 256 * 4 - 1) / (256 * 4);
-    return (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)h->num_sms * 4));  // one resident wave
+    const int64_t units = (items + 1023) / 1024;  // 256 threads x 4 items
+    const int64_t trips = (units + (int64_t)h->num_sms * 4 - 1) / ((int64_t)h->num_sms * 4);
+    return (int)std::max<int64_t>(1, (units + trips - 1) / trips);
 }
 
 template <bool JAC, bool INIT>
@@ -597,6 +600,7 @@ int alloc_state(b200ls_solver *h)
     CU(h, cudaMalloc(&h->ws.partials, sizeof(double) * B200_NSUM * (size_t)h->max_blocks));
     CU(h, cudaMalloc(&h->ws.counter, sizeof(unsigned int) * 4));
     CU(h, cudaMemset(h->ws.counter, 0, sizeof(unsigned int) * 4));
+    h->ws.trace = nullptr;
     CU(h, cudaMalloc(&h->d_sendrecv, sizeof(double) * 2 * B200_NSUM));
     CU(h, cudaMemset(h->d_sendrecv, 0, sizeof(double) * 2 * B200_NSUM));
     CU(h, cudaEventCreate(&h->ev_a));
@@ -619,10 +623,10 @@ void build_commdev(b200ls_solver *h)
     if (h->nranks > 1) cm.mode = (h->reduce_mode == B200LS_REDUCE_NCCL) ? 2 : 1;
 }
 
-// arena layout: [mailboxes 2*nranks*NSUM doubles | flags 2*nranks u64 | pad to 256 B | r]
+// arena layout: [mailboxes 2 parities * nranks records * 16 LL words | pad to 256 B | r]
 inline size_t arena_head_bytes(int nranks)
 {
-    const size_t b = sizeof(double) * 2 * (size_t)nranks * B200_NSUM + sizeof(unsigned long long) * 2 * (size_t)nranks;
+    const size_t b = sizeof(unsigned long long) * 2 * (size_t)nranks * B200_LLW;
     return (size_t)round_up((int64_t)b, 256);
 }
 
@@ -1010,6 +1014,7 @@ int b200ls_destroy(b200ls_solver *h)
         if (e) cudaEventDestroy(e);
     if (h->ws.partials) cudaFree(h->ws.partials);
     if (h->ws.counter) cudaFree(h->ws.counter);
+    if (h->ws.trace) cudaFree(h->ws.trace);
     if (h->d_hist) cudaFree(h->d_hist);
     if (h->d_sendrecv) cudaFree(h->d_sendrecv);
     if (h->flush_buf) cudaFree(h->flush_buf);
@@ -1112,12 +1117,9 @@ int b200ls_comm_connect(b200ls_solver *h, const void *handles, int nranks)
     CommDev &cm = h->cm;
     for (int q = 0; q < nranks; ++q)
     {
-        cm.mbox_peer[q] = reinterpret_cast<double *>(h->peer_base[q]);
-        cm.flag_peer[q] = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(h->peer_base[q]) +
-                                                                 sizeof(double) * 2 * (size_t)nranks * B200_NSUM);
+        cm.mbox_peer[q] = reinterpret_cast<unsigned long long *>(h->peer_base[q]);
     }
     cm.mbox_local = cm.mbox_peer[h->rank];
-    cm.flag_local = cm.flag_peer[h->rank];
     // neighbours along the slab axis; periodic wrap closes the ring
     const bool perz = h->dim == 3 && h->per[2];
     int dn = h->rank - 1, up = h->rank + 1;
@@ -1577,6 +1579,42 @@ int b200ls_time_kernel(b200ls_solver *h, int kclass, int reps, int flush_l2, dou
     h->opt = keep;
     CU(h, cudaGetLastError());
     *avg_ms = total / reps;
+    return B200LS_OK;
+}
+
+int b200ls_set_trace(b200ls_solver *h, int capacity)
+{
+    if (!h || capacity < 0) return B200LS_ERR_ARG;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->ws.trace) cudaFree(h->ws.trace);
+    h->ws.trace = nullptr;
+    invalidate_graph(h);
+    if (capacity == 0) return B200LS_OK;
+    const size_t n = 8 + 5 * (size_t)capacity;
+    CU(h, cudaMalloc(&h->ws.trace, sizeof(unsigned long long) * n));
+    CU(h, cudaMemset(h->ws.trace, 0, sizeof(unsigned long long) * n));
+    const unsigned long long cap = (unsigned long long)capacity;
+    CU(h, cudaMemcpy(h->ws.trace + 2, &cap, sizeof cap, cudaMemcpyHostToDevice));
+    return B200LS_OK;
+}
+
+int b200ls_get_trace(b200ls_solver *h, unsigned long long *buf, int capacity, int *n)
+{
+    if (!h || !n) return B200LS_ERR_ARG;
+    *n = 0;
+    if (!h->ws.trace) return B200LS_OK;
+    cudaSetDevice(h->device);
+    CU(h, cudaStreamSynchronize(h->stream));
+    unsigned long long head[8];
+    CU(h, cudaMemcpy(head, h->ws.trace, sizeof head, cudaMemcpyDeviceToHost));
+    const int have = (int)std::min<unsigned long long>(head[0], head[2]);
+    *n = have;
+    const int take = std::min(have, capacity);
+    if (buf && take > 0)
+        CU(h, cudaMemcpy(buf, h->ws.trace + 8, sizeof(unsigned long long) * 5 * (size_t)take, cudaMemcpyDeviceToHost));
+    const unsigned long long zero = 0;
+    CU(h, cudaMemcpy(h->ws.trace, &zero, sizeof zero, cudaMemcpyHostToDevice));
     return B200LS_OK;
 }
 

@@ -67,20 +67,37 @@ struct CommDev
 {
     int rank, nranks;
     int mode;                    // 0 = single GPU, 1 = P2P mailboxes, 2 = NCCL (sums left in sendbuf)
-    double *mbox_peer[B200_MAX_RANKS];              // peer q's mailbox base (mapped); [parity][src rank][NSUM]
-    unsigned long long *flag_peer[B200_MAX_RANKS];  // peer q's flag base; [parity][src rank]
-    double *mbox_local;
-    unsigned long long *flag_local;
+    // peer q's mailbox base (mapped over CUDA IPC): [parity][src rank][2*NSUM] 8-byte words, each word
+    // = {flag: low 32 bits of the reduction sequence number, data: one 32-bit half of a double}
+    unsigned long long *mbox_peer[B200_MAX_RANKS];
+    unsigned long long *mbox_local;
     double *sendbuf;             // NCCL mode: local sums
     double *r_ghost_dn;          // neighbour below: address of ITS top ghost plane of r (or null)
     double *r_ghost_up;          // neighbour above: address of ITS bottom ghost plane of r (or null)
 };
 
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 struct ReduceWs
 {
     double *partials;        // [max_blocks][B200_NSUM]
     unsigned int *counter;   // ticket counter, self-resetting
+    // optional timeline (b200ls_set_trace): [0] = entries written, [1] = start stamp of the running kernel,
+    // [2] = capacity, entries of 5 u64 from [8]: {kernel start, local reduction done, all-reduce done,
+    // scalars done, kind} in globaltimer ns
+    unsigned long long *trace;
 };
+
+__device__ __forceinline__ void trace_kernel_start(const ReduceWs &ws)
+{
+    if (ws.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0 && threadIdx.y == 0)
+        ws.trace[1] = global_timer_ns();
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
 {
@@ -97,12 +114,6 @@ __device__ __forceinline__ double ld_volatile(const double *p)
     double v;
     asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
-}
-__device__ __forceinline__ unsigned long long global_timer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -214,51 +225,87 @@ __device__ inline void finalize_scalars(int kind, const double *S, DevState &s, 
 }
 
 // ------------------------------------------------------------------------------------------
-// cross-GPU all-reduce of one B200_NSUM record through peer-mapped mailboxes (one warp)
+// cross-GPU all-reduce of one B200_NSUM record through peer-mapped mailboxes (one warp).
+// Low-latency ("LL") protocol: every 8-byte word carries 32 bits of payload and the 32-bit sequence
+// number, so a word is valid the moment its flag matches -- one NVLink store hop, no fence and no
+// separate flag write on the critical path.  Every rank adds the nranks records in rank order, so the
+// result is bit-identical everywhere.  Slots are double-buffered by the parity of the sequence number.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool mailbox_allreduce(double (&S)[B200_NSUM], const CommDev &cm, DevState *st,
-                                                  int lane)
+#define B200_LLW (2 * B200_NSUM)  // words per record
+
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v)
 {
-    // lane q posts this rank's sums into peer q's mailbox, then every rank adds the nranks
-    // records in rank order (bit-identical result on every rank)
-    const unsigned long long seq = st->seq + 1;
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// S: this rank's sums on entry (valid in every lane), the global sums on exit (valid in lane 0).
+// seq: sequence number of THIS reduction (previous + 1), identical on every rank.
+__device__ __forceinline__ bool mailbox_allreduce(double (&S)[B200_NSUM], const CommDev &cm,
+                                                  unsigned long long seq, int lane, unsigned int *s_ll)
+{
     const int par = (int)(seq & 1ull);
-    bool ok = true;
-    if (lane < cm.nranks)
+    const unsigned int flag = (unsigned int)seq;
+    const int nr = cm.nranks;
+    // ---- send: lane l < 16 owns word l of the record (double l/2, half l%2)
     {
-        double *mb = cm.mbox_peer[lane] + ((size_t)par * cm.nranks + cm.rank) * B200_NSUM;
+        unsigned int half = 0u;
 #pragma unroll
-        for (int q = 0; q < B200_NSUM; ++q) mb[q] = S[q];
-        __threadfence_system();
-        st_release_sys(cm.flag_peer[lane] + (size_t)par * cm.nranks + cm.rank, seq);
-        const unsigned long long *fl = cm.flag_local + (size_t)par * cm.nranks + lane;
-        const unsigned long long t0 = global_timer_ns();
+        for (int q = 0; q < B200_NSUM; ++q)
+        {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(S[q]);
+            if ((lane >> 1) == q) half = (lane & 1) ? (unsigned int)(bits >> 32) : (unsigned int)bits;
+        }
+        const unsigned long long word = ((unsigned long long)flag << 32) | (unsigned long long)half;
+        if (lane < B200_LLW)
+            for (int p = 0; p < nr; ++p)
+                st_relaxed_sys_u64(cm.mbox_peer[p] + ((size_t)par * nr + cm.rank) * B200_LLW + lane, word);
+    }
+    // ---- receive: nr * 16 words, strided over the warp
+    bool ok = true;
+    const unsigned long long *base = cm.mbox_local + (size_t)par * nr * B200_LLW;
+    const unsigned long long t0 = global_timer_ns();
+    for (int idx = lane; idx < nr * B200_LLW; idx += 32)
+    {
+        unsigned long long w = ld_relaxed_sys_u64(base + idx);
         unsigned int spins = 0;
-        while (ld_acquire_sys(fl) < seq)
+        while ((unsigned int)(w >> 32) != flag)
         {
             if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > 4000000000ull)
             {
                 ok = false;  // a peer never arrived: give up instead of hanging the GPU
                 break;
             }
+            w = ld_relaxed_sys_u64(base + idx);
         }
+        s_ll[idx] = (unsigned int)w;
     }
     ok = __all_sync(0xffffffffu, ok);
+    __syncwarp();
+    // ---- fixed-order sum over the ranks: lane q < NSUM builds sum q, lane 0 collects
+    double mine = 0.0;
+    if (lane < B200_NSUM)
+        for (int src = 0; src < nr; ++src)
+        {
+            const unsigned int lo = s_ll[src * B200_LLW + 2 * lane], hi = s_ll[src * B200_LLW + 2 * lane + 1];
+            mine += __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+        }
 #pragma unroll
-    for (int q = 0; q < B200_NSUM; ++q) S[q] = 0.0;
-    for (int src = 0; src < cm.nranks; ++src)
-    {
-        const double *mb = cm.mbox_local + ((size_t)par * cm.nranks + src) * B200_NSUM;
-#pragma unroll
-        for (int q = 0; q < B200_NSUM; ++q) S[q] += ld_volatile(mb + q);
-    }
-    if (lane == 0) st->seq = seq;
+    for (int q = 0; q < B200_NSUM; ++q) S[q] = __shfl_sync(0xffffffffu, mine, q);
     return ok;
 }
 
 // ------------------------------------------------------------------------------------------
 // block reduction + deterministic grid reduction + (multi-GPU) all-reduce + scalar logic
 // ------------------------------------------------------------------------------------------
+constexpr int kStateWords = (int)((sizeof(DevState) + 7) / 8);
+static_assert(kStateWords <= 32, "DevState must fit one warp-wide staging pass");
+
 template <int NS>
 __device__ __forceinline__ void grid_reduce_finalize(double (&acc)[NS], int kind, const ReduceWs &ws,
                                                      const CommDev &cm, DevState *st,
@@ -266,11 +313,16 @@ __device__ __forceinline__ void grid_reduce_finalize(double (&acc)[NS], int kind
 {
     __shared__ double s_red[32][NS];
     __shared__ bool s_last;
+    __shared__ __align__(8) unsigned long long s_state[32];  // staged copy of *st (constant during the kernel)
+    __shared__ unsigned int s_ll[B200_MAX_RANKS * B200_LLW];
     const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
     const int nthr = blockDim.x * blockDim.y * blockDim.z;
     const int lane = tid & 31, wid = tid >> 5, nw = (nthr + 31) >> 5;
     const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
     const unsigned int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    // every block prefetches the solver state (168 B): whichever block turns out to be last finds it in
+    // shared memory instead of paying serial round trips to L2 after the reduction
+    if (tid < kStateWords) s_state[tid] = reinterpret_cast<const unsigned long long *>(st)[tid];
 #pragma unroll
     for (int q = 0; q < NS; ++q)
     {
@@ -299,7 +351,8 @@ __device__ __forceinline__ void grid_reduce_finalize(double (&acc)[NS], int kind
     }
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
+    if (cm.mode == 1) __threadfence_system();  // order every block's peer stores before our mailbox words
+    else __threadfence();
     // last block: fixed-order sum of all block partials
     double tot[NS];
 #pragma unroll
@@ -328,25 +381,53 @@ __device__ __forceinline__ void grid_reduce_finalize(double (&acc)[NS], int kind
         S[q] = warp_sum(v);
     }
     if (lane == 0) *ws.counter = 0u;
+    unsigned long long tr1 = 0, tr2 = 0;
+    if (ws.trace && lane == 0) tr1 = global_timer_ns();
     if (cm.mode == 2)
     {
         // NCCL transport: leave the local sums for ncclAllReduce; k_scalars finishes the job
         if (lane < B200_NSUM) cm.sendbuf[lane] = S[lane];
         return;
     }
+    DevState &sst = *reinterpret_cast<DevState *>(s_state);
     if (cm.mode == 1)
     {
-        if (!mailbox_allreduce(S, cm, st, lane))
+        const unsigned long long seq = sst.seq + 1;
+        const bool ok = mailbox_allreduce(S, cm, seq, lane, s_ll);
+        if (lane == 0)
         {
-            if (lane == 0)
+            sst.seq = seq;
+            if (!ok)
             {
-                st->err = 1;
-                st->done = 1;
+                sst.err = 1;
+                sst.done = 1;
             }
+        }
+        if (!ok)
+        {
+            __syncwarp();
+            if (lane < kStateWords) reinterpret_cast<unsigned long long *>(st)[lane] = s_state[lane];
             return;
         }
     }
-    if (lane == 0) finalize_scalars(kind, S, *st, k, hist);
+    if (ws.trace && lane == 0) tr2 = global_timer_ns();
+    if (lane == 0) finalize_scalars(kind, S, sst, k, hist);
+    __syncwarp();
+    if (lane < kStateWords) reinterpret_cast<unsigned long long *>(st)[lane] = s_state[lane];
+    if (ws.trace && lane == 0)
+    {
+        const unsigned long long idx = ws.trace[0];
+        if (idx < ws.trace[2])
+        {
+            unsigned long long *e = ws.trace + 8 + 5 * idx;
+            e[0] = ws.trace[1];
+            e[1] = tr1;
+            e[2] = tr2;
+            e[3] = global_timer_ns();
+            e[4] = (unsigned long long)kind;
+        }
+        ws.trace[0] = idx + 1;
+    }
 }
 
 // NCCL transport: scalar logic after ncclAllReduce
@@ -427,6 +508,7 @@ __global__ void __launch_bounds__(TXT *TYT) k_spmv(GridDev g, VecSet v, int kz_c
     constexpr int SROW = BX + 4;  // [1] left halo, [2..BX+1] tile, [BX+2] right halo
     __shared__ __align__(16) double sp[3][TYT][SROW];
 
+    trace_kernel_start(ws);
     double shift = 0.0, bcoef = 0.0, aprev = 0.0;
     bool xupd = false;
     if (!APPLY)
@@ -871,6 +953,7 @@ __global__ void __launch_bounds__(256) k_update2(GridDev g, UpdVecs v, int fin_k
                                                  DevState *st, SolveConsts kc, double *hist)
 {
     if (st->done) return;
+    trace_kernel_start(ws);
     const double ma = INIT ? 0.0 : -st->a;
     const double c = st->c;
     const unsigned int plane2 = (unsigned int)(g.plane >> 1);
@@ -1019,17 +1102,24 @@ __global__ void k_push_halo(GridDev g, const double *vsrc, double *ghost_dn, dou
 // cross-GPU barrier through the mailboxes (a reduction whose result is dropped)
 __global__ void k_barrier(CommDev cm, DevState *st)
 {
+    __shared__ unsigned int s_ll[B200_MAX_RANKS * B200_LLW];
     if (blockIdx.x == 0 && threadIdx.x < 32)
     {
         double S[B200_NSUM];
 #pragma unroll
         for (int q = 0; q < B200_NSUM; ++q) S[q] = 0.0;
-        if (!mailbox_allreduce(S, cm, st, threadIdx.x))
-            if (threadIdx.x == 0)
+        __threadfence_system();
+        const unsigned long long seq = st->seq + 1;
+        const bool ok = mailbox_allreduce(S, cm, seq, (int)threadIdx.x, s_ll);
+        if (threadIdx.x == 0)
+        {
+            st->seq = seq;
+            if (!ok)
             {
                 st->err = 1;
                 st->done = 1;
             }
+        }
     }
 }
 

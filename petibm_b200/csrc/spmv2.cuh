@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(TXT *TYT, MINB)
     if (!APPLY)
     {
         if (st->done) return;
+        trace_kernel_start(ws);
         shift = st->shift;
         bcoef = st->b;
         aprev = st->a;

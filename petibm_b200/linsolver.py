@@ -298,6 +298,15 @@ class LinSolverB200(LinSolverBase):
         _lib.check(self._L.b200ls_get_profile(self._h, int(kclass), C.byref(t), C.byref(c)), self._h)
         return t.value, c.value
 
+    def setTrace(self, capacity: int):
+        _lib.check(self._L.b200ls_set_trace(self._h, int(capacity)), self._h)
+
+    def getTrace(self, capacity: int = 4096) -> np.ndarray:
+        buf = np.zeros((capacity, 5), dtype=np.uint64)
+        n = C.c_int(0)
+        _lib.check(self._L.b200ls_get_trace(self._h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), capacity, C.byref(n)), self._h)
+        return buf[: min(n.value, capacity)].copy()
+
     def timeKernel(self, kclass: int, reps: int = 20, flush_l2: bool = True) -> float:
         v = C.c_double(0)
         _lib.check(self._L.b200ls_time_kernel(self._h, int(kclass), int(reps), int(bool(flush_l2)), C.byref(v)), self._h)

@@ -128,9 +128,10 @@ def test_converged_reasons_and_iteration_counts(pb, check_every):
         assert hist.size == s.getIters() + 1
         m = min(hist.size, sens.size)
         rel = np.abs(hist[:m] - ref.history[:m]) / ref.history[:m]
-        # 1e-10 wherever the algorithm itself is reproducible to 1e-12; elsewhere within 100x of the
-        # order sensitivity of the oracle
-        assert np.all(rel <= np.maximum(HIST_RTOL, 100.0 * sens[:m])), (rel.max(), sens.max())
+        # 1e-10 wherever the algorithm itself is reproducible to 1e-12; once round-off has been amplified
+        # (running maximum of the oracle's own order sensitivity) within 100x of that level
+        floor = np.maximum.accumulate(sens[:m])
+        assert np.all(rel <= np.maximum(HIST_RTOL, 100.0 * floor)), (rel.max(), sens.max())
         np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-6 * np.abs(ref.x).max())
         s.destroy()
 
