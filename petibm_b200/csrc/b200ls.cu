@@ -145,9 +145,11 @@ struct b200ls_solver
     int num_sms = 148;
     int kz_chunk = 0;        // 0 = auto
     int upd_blocks = 0;      // 0 = auto
-    int tile = 18;           // K1 tile variant (10+: k_spmv2)
+    int tile = -1;           // K1 tile variant (-1: cost model picks 10 or 18; 10+: k_spmv2; <10: k_spmv)
     int upd_variant = 0;     // 0: flat k_update2, 1: first-generation k_update
     int use_graph = 1;
+    int use_pdl = 1;
+    bool in_loop = false;    // launches issued from the CG loop may overlap their predecessor (PDL)
     cudaGraphExec_t graph_exec = nullptr;
     int graph_iters = 0;
     unsigned long long graph_key = 0;
@@ -309,11 +311,33 @@ void resolve_profile(b200ls_solver *h)
 // ------------------------------------------------------------------------------------------
 // launch wrappers
 // ------------------------------------------------------------------------------------------
+// Kernel launch with (optionally) the programmatic-dependent-launch attribute.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(b200ls_solver *h, bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+inline bool pdl_on(const b200ls_solver *h)
+{
+    return h->use_pdl && !h->profile && !(h->nranks > 1 && h->reduce_mode == B200LS_REDUCE_NCCL);
+}
+
 struct TileCfg { int txt, tyt; };
 // tile < 10: first-generation register-prefetch kernel (k_spmv); tile >= 10: cp.async ring kernel (k_spmv2)
-inline TileCfg tile_cfg(const b200ls_solver *h)
+inline TileCfg tile_dims(int tile)
 {
-    switch (h->tile)
+    switch (tile)
     {
         case 0: return {32, 8};
         case 1: return {32, 6};
@@ -333,20 +357,63 @@ inline TileCfg tile_cfg(const b200ls_solver *h)
         default: return {32, 8};  // 10
     }
 }
-
-inline int auto_kz_chunk(const b200ls_solver *h)
+inline int tile_ctas_per_sm(int tile)
 {
-    if (h->kz_chunk > 0) return std::min<int>(std::min<int>(h->kz_chunk, h->g.nzl), 512);
-    const TileCfg t = tile_cfg(h);
-    const int64_t bx = (h->g.nx + 2 * t.txt - 1) / (2 * t.txt), by = (h->g.ny + (t.tyt - 2) - 1) / (t.tyt - 2);
-    const int64_t xy = bx * by;
-    const int per_sm = std::max(1, 2048 / (t.txt * t.tyt));
-    const int64_t target = (int64_t)h->num_sms * per_sm;  // one full wave of resident blocks
-    int64_t nch = std::max<int64_t>(1, (target + xy - 1) / xy);
-    nch = std::min<int64_t>(nch, std::max<int64_t>(1, h->g.nzl / 8));
-    nch = std::max<int64_t>(nch, (h->g.nzl + 511) / 512);  // the coefficient table of a chunk holds 512 planes
-    return (int)((h->g.nzl + nch - 1) / nch);
+    switch (tile)
+    {
+        case 10: case 15: return 3;
+        case 11: case 13: case 17: return 4;
+        case 16: return 1;
+        case 12: case 14: case 18: case 20: return 2;
+        case 19: return 3;
+        default: return 2;
+    }
 }
+
+// Launch shape of the fused SpMV kernel: tile variant and planes per CTA.  Deterministic cost model fitted to
+// the sweeps in profiles/ (scripts/sweep_k1.py): a CTA marches kz planes plus a ~5-plane pipeline fill,
+// CTAs fill SMs in waves of (SMs x resident CTAs), and a tile with TY of TYT thread rows doing stencil work
+// has efficiency TY/TYT.
+struct K1Cfg { int tile, kz; };
+inline K1Cfg k1_config(const b200ls_solver *h)
+{
+    const int nzl = h->g.nzl;
+    int tiles[2] = {10, 18};
+    int ntiles = 2;
+    if (h->tile >= 0)
+    {
+        tiles[0] = h->tile;
+        ntiles = 1;
+    }
+    K1Cfg best{tiles[0], std::max(1, std::min(nzl, 512))};
+    double best_score = -1.0;
+    for (int q = 0; q < ntiles; ++q)
+    {
+        const TileCfg t = tile_dims(tiles[q]);
+        const int ty = t.tyt - 2;
+        const int64_t xy = (int64_t)((h->g.nx + 2 * t.txt - 1) / (2 * t.txt)) * ((h->g.ny + ty - 1) / ty);
+        const int64_t slots = (int64_t)h->num_sms * tile_ctas_per_sm(tiles[q]);
+        const int max_nch = (h->kz_chunk > 0) ? 1 : std::max(1, std::min(64, nzl / 4));
+        for (int nch = 1; nch <= max_nch; ++nch)
+        {
+            int kz = (h->kz_chunk > 0) ? std::min(h->kz_chunk, nzl) : (nzl + nch - 1) / nch;
+            if (kz > 512) kz = 512;
+            const int64_t chunks = (nzl + kz - 1) / kz;
+            const int64_t blocks = xy * chunks;
+            const int64_t waves = (blocks + slots - 1) / slots;
+            const double fill = (double)blocks / (double)(waves * slots);
+            const double score = fill * ((double)kz / (double)(kz + 5)) * ((double)ty / (double)t.tyt);
+            if (score > best_score * (1.0 + 1e-12))
+            {
+                best_score = score;
+                best = {tiles[q], kz};
+            }
+        }
+    }
+    return best;
+}
+inline TileCfg tile_cfg(const b200ls_solver *h) { return tile_dims(k1_config(h).tile); }
+inline int auto_kz_chunk(const b200ls_solver *h) { return k1_config(h).kz; }
 
 inline bool grid_periodic(const b200ls_solver *h) { return h->per[0] || h->per[1] || h->per[2]; }
 
@@ -365,7 +432,8 @@ int launch_spmv2_cfg(b200ls_solver *h, const VecSet &v, int ghost_store, dim3 gr
             CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total(512)));
             attr_done = true;
         }
-        kern<<<grid, block, L::total(kz), h->stream>>>(h->g, v, kz, h->ws, h->cm, h->d_state, kc, h->d_hist, ghost_store);
+        CU(h, launch_k(h, h->in_loop && pdl_on(h), kern, grid, block, L::total(kz), h->g, v, kz, h->ws, h->cm, h->d_state, kc,
+                       h->d_hist, ghost_store));
     }
     else
     {
@@ -376,7 +444,8 @@ int launch_spmv2_cfg(b200ls_solver *h, const VecSet &v, int ghost_store, dim3 gr
             CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total(512)));
             attr_done = true;
         }
-        kern<<<grid, block, L::total(kz), h->stream>>>(h->g, v, kz, h->ws, h->cm, h->d_state, kc, h->d_hist, ghost_store);
+        CU(h, launch_k(h, h->in_loop && pdl_on(h), kern, grid, block, L::total(kz), h->g, v, kz, h->ws, h->cm, h->d_state, kc,
+                       h->d_hist, ghost_store));
     }
     return B200LS_OK;
 }
@@ -394,8 +463,9 @@ int launch_spmv_t(b200ls_solver *h, const VecSet &v, int ghost_store)
 #define B200_SPMV_CASE(TXT, TYT)                                                                               \
     k_spmv<TXT, TYT, JAC, APPLY><<<grid, block, 0, h->stream>>>(h->g, v, kz, h->ws, h->cm, h->d_state, kc, \
                                                                  h->d_hist, ghost_store)
-    if (APPLY && h->tile >= 10) return launch_spmv2_cfg<8, 4, 3, JAC, APPLY>(h, v, ghost_store, dim3(grid.x, (unsigned)((h->g.ny + 5) / 6), grid.z), kz);
-    switch (h->tile)
+    const int tile = k1_config(h).tile;
+    if (APPLY && tile >= 10) return launch_spmv2_cfg<8, 4, 3, JAC, APPLY>(h, v, ghost_store, dim3(grid.x, (unsigned)((h->g.ny + 5) / 6), grid.z), kz);
+    switch (tile)
     {
         case 0: B200_SPMV_CASE(32, 8); break;
         case 1: B200_SPMV_CASE(32, 6); break;
@@ -455,8 +525,9 @@ void launch_update_t(b200ls_solver *h, int fin_kind, bool push)
     {
         const bool padded = h->g.px != h->g.nx;
         const bool psh = cm.r_ghost_dn || cm.r_ghost_up;
-#define B200_UPD(PAD, PSH) \
-    k_update2<JAC, INIT, PAD, PSH, 4><<<blocks, 256, 0, h->stream>>>(h->g, v, fin_kind, h->ws, cm, h->d_state, kc, h->d_hist)
+#define B200_UPD(PAD, PSH)                                                                                            \
+    launch_k(h, h->in_loop && pdl_on(h), k_update2<JAC, INIT, PAD, PSH, 4>, dim3(blocks), dim3(256), 0, h->g, v, fin_kind, \
+             h->ws, cm, h->d_state, kc, h->d_hist)
         if (padded && psh) B200_UPD(true, true);
         else if (padded) B200_UPD(true, false);
         else if (psh) B200_UPD(false, true);
@@ -531,12 +602,15 @@ int enqueue_spmv(b200ls_solver *h, int parity)
 
 int enqueue_cg_iterations(b200ls_solver *h, int first_iter, int count)
 {
-    for (int q = 0; q < count; ++q)
+    h->in_loop = true;
+    int rc = B200LS_OK;
+    for (int q = 0; q < count && rc == B200LS_OK; ++q)
     {
-        TRY(enqueue_spmv(h, (first_iter + q) & 1));
-        TRY(enqueue_update(h, false, FIN_UPDATE));
+        rc = enqueue_spmv(h, (first_iter + q) & 1);
+        if (rc == B200LS_OK) rc = enqueue_update(h, false, FIN_UPDATE);
     }
-    return B200LS_OK;
+    h->in_loop = false;
+    return rc;
 }
 
 // a graph of `count` CG iterations starting at an even iteration (buffer parity repeats every 2)
@@ -1057,6 +1131,7 @@ int b200ls_set_tuning(b200ls_solver *h, const char *key, int value)
     else if (k == "tile") h->tile = value;
     else if (k == "upd_variant") h->upd_variant = value;
     else if (k == "use_graph") h->use_graph = value;
+    else if (k == "use_pdl") h->use_pdl = value;
     else return fail(h, B200LS_ERR_ARG, "unknown tuning key %s", key);
     invalidate_graph(h);
     return B200LS_OK;

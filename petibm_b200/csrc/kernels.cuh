@@ -116,6 +116,15 @@ __device__ __forceinline__ double ld_volatile(const double *p)
     return v;
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute
+// may start while its predecessor is still draining; everything before pdl_sync() must not touch memory the
+// predecessor writes.  The trigger is issued AFTER the wait, so at most two grids are ever co-resident.
+__device__ __forceinline__ void pdl_sync()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -508,6 +517,7 @@ __global__ void __launch_bounds__(TXT *TYT) k_spmv(GridDev g, VecSet v, int kz_c
     constexpr int SROW = BX + 4;  // [1] left halo, [2..BX+1] tile, [BX+2] right halo
     __shared__ __align__(16) double sp[3][TYT][SROW];
 
+    pdl_sync();
     trace_kernel_start(ws);
     double shift = 0.0, bcoef = 0.0, aprev = 0.0;
     bool xupd = false;
@@ -803,6 +813,7 @@ template <bool JACOBI, bool INIT, int UNROLL>
 __global__ void __launch_bounds__(256) k_update(GridDev g, UpdVecs v, int fin_kind, ReduceWs ws, CommDev cm,
                                                 DevState *st, SolveConsts kc, double *hist)
 {
+    pdl_sync();
     if (st->done) return;
     const double ma = INIT ? 0.0 : -st->a;
     const double c = st->c;
@@ -952,6 +963,7 @@ template <bool JACOBI, bool INIT, bool PADDED, bool PUSH, int U>
 __global__ void __launch_bounds__(256) k_update2(GridDev g, UpdVecs v, int fin_kind, ReduceWs ws, CommDev cm,
                                                  DevState *st, SolveConsts kc, double *hist)
 {
+    pdl_sync();
     if (st->done) return;
     trace_kernel_start(ws);
     const double ma = INIT ? 0.0 : -st->a;

@@ -97,17 +97,6 @@ __global__ void __launch_bounds__(TXT *TYT, MINB)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned int smem_base = (unsigned int)__cvta_generic_to_shared(smem_raw);
 
-    double shift = 0.0, bcoef = 0.0, aprev = 0.0;
-    bool xupd = false;
-    if (!APPLY)
-    {
-        if (st->done) return;
-        trace_kernel_start(ws);
-        shift = st->shift;
-        bcoef = st->b;
-        aprev = st->a;
-        xupd = st->pending != 0;
-    }
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int i0 = blockIdx.x * BX, j0 = blockIdx.y * TY;
     const int k0 = blockIdx.z * kz_chunk;
@@ -185,6 +174,20 @@ __global__ void __launch_bounds__(TXT *TYT, MINB)
             cf[kz_chunk + 2 + t] = g.gz[g.kz0 + k0 + t];
         }
         if (tx == 0 && ty == 0) cf[kz_chunk + 2] = g.gz[g.kz0 + k0];  // minus face of plane k0
+    }
+
+    // ---- everything above reads only launch-invariant data: from here on the predecessor must be done
+    pdl_sync();
+    double shift = 0.0, bcoef = 0.0, aprev = 0.0;
+    bool xupd = false;
+    if (!APPLY)
+    {
+        if (st->done) return;
+        trace_kernel_start(ws);
+        shift = st->shift;
+        bcoef = st->b;
+        aprev = st->a;
+        xupd = st->pending != 0;
     }
 
     // storage offset (bytes) of plane kk = k0-1+t: (kk+1)*plane, except the single-GPU periodic wrap
