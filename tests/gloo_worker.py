@@ -1,0 +1,38 @@
+"""Worker of tests/test_dist_gloo.py: the host transport of the multi-GPU wiring on CPU (gloo, no GPU)."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from petibm_b200.dist import Comm  # noqa: E402
+from petibm_b200.mesh import slab_range  # noqa: E402
+
+
+def main():
+    comm = Comm.from_env(backend="gloo")
+    assert comm.nranks == int(os.environ["WORLD_SIZE"]) and comm.rank == int(os.environ["RANK"])
+    # 64-byte "IPC handles" travel rank-major
+    mine = bytes([comm.rank]) * 64
+    got = comm.allgather_bytes(mine)
+    assert got == [bytes([r]) * 64 for r in range(comm.nranks)]
+    uid = comm.broadcast_bytes(b"\x07" * 128 if comm.rank == 0 else None, 0)
+    assert uid == b"\x07" * 128
+    assert comm.allreduce_max(float(comm.rank)) == float(comm.nranks - 1)
+    # natural-ordering vector <-> DMDA z-slabs
+    n = (5, 4, 7)
+    full = np.arange(np.prod(n), dtype=np.float64)
+    loc = comm.local_block(full, n)
+    lo, hi = slab_range(n[2], comm.rank, comm.nranks)
+    assert loc.size == n[0] * n[1] * (hi - lo) and loc[0] == lo * n[0] * n[1]
+    back = comm.gather_blocks(loc)
+    assert np.array_equal(back, full)
+    comm.barrier()
+    import torch.distributed as dist
+
+    dist.destroy_process_group()
+    print(f"GLOO_WORKER_OK rank {comm.rank}")
+
+
+if __name__ == "__main__":
+    main()
