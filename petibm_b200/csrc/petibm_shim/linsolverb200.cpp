@@ -1,0 +1,267 @@
+/**
+ * \file linsolverb200.cpp
+ * \brief Implementation of LinSolverB200 (see linsolverb200.h).
+ *
+ * Call protocol is the one the applications use (navierstokes.cpp:151-164, 566-580, 780-788):
+ * createLinSolver -> setMatrix once (re-called every step by rigidkinematics.cpp:135) -> solve per time
+ * step with a zero initial guess -> getIters / getResidual.  Errors are PetscErrorCodes; a diverged solve
+ * raises PETSC_ERR_CONV_FAILED exactly like LinSolverKSP::solve (linsolverksp.cpp:96-104).
+ */
+#include "linsolverb200.h"
+
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+namespace petibm
+{
+namespace linsolver
+{
+namespace
+{
+// b200ls status -> PETSc error
+#define B200CHK(h, call)                                                                                       \
+    do                                                                                                         \
+    {                                                                                                          \
+        int rc__ = (call);                                                                                     \
+        if (rc__ != B200LS_OK)                                                                                 \
+            SETERRQ3(PETSC_COMM_WORLD, rc__ == B200LS_ERR_UNSUPPORTED ? PETSC_ERR_SUP : PETSC_ERR_LIB,         \
+                     "B200 linear solver: %s failed: %s (%s)", #call, b200ls_error_string(rc__),               \
+                     b200ls_last_error(h));                                                                    \
+    } while (0)
+}  // namespace
+
+LinSolverB200::LinSolverB200(const std::string &solverName, const std::string &file)
+    : LinSolverBase(solverName, file)
+{
+    initStatus = init();
+}
+
+LinSolverB200::~LinSolverB200()
+{
+    PetscBool finalized;
+    PetscErrorCode ierr = PetscFinalized(&finalized);
+    if (ierr || finalized) return;  // same guard as linsolverksp.cpp:30-31
+    if (handle) b200ls_destroy(handle);
+    handle = nullptr;
+}
+
+PetscErrorCode LinSolverB200::destroy()
+{
+    PetscErrorCode ierr;
+    PetscFunctionBeginUser;
+    if (handle) b200ls_destroy(handle);
+    handle = nullptr;
+    ierr = LinSolverBase::destroy(); CHKERRQ(ierr);
+    PetscFunctionReturn(0);
+}
+
+// LinSolverKSP::init (linsolverksp.cpp:48-69): the options file is read with the prefix "<name>_".
+PetscErrorCode LinSolverB200::init()
+{
+    PetscErrorCode ierr;
+    PetscFunctionBeginUser;
+
+    // The applications dispatch their null-space handling on this string and abort on anything else
+    // (navierstokes.cpp:401-426, ibpm.cpp:248-280).  Reporting the KSP type makes them attach the
+    // MatNullSpace to DBNG, which setMatrix reads back -- the behaviour this backend reproduces.
+    type = "PETSc KSP";
+
+    ierr = MPI_Comm_rank(PETSC_COMM_WORLD, &rank); CHKERRQ(ierr);
+    ierr = MPI_Comm_size(PETSC_COMM_WORLD, &nranks); CHKERRQ(ierr);
+
+    int ndev = 0;
+    if (b200ls_device_count(&ndev) != B200LS_OK || ndev <= 0)
+        SETERRQ(PETSC_COMM_WORLD, PETSC_ERR_SUP, "B200 linear solver: no CUDA device (there is no CPU fallback).");
+    int rc = b200ls_create(&handle, rank % ndev);
+    if (rc != B200LS_OK)
+        SETERRQ1(PETSC_COMM_WORLD, PETSC_ERR_LIB, "B200 linear solver: b200ls_create failed: %s", b200ls_error_string(rc));
+
+    b200ls_options opts;
+    b200ls_default_options(&opts);
+    if (config != "None")
+    {
+        std::ifstream f(config);
+        if (!f) SETERRQ1(PETSC_COMM_WORLD, PETSC_ERR_FILE_OPEN, "Could not open the solver configuration file %s", config.c_str());
+        std::stringstream ss;
+        ss << f.rdbuf();
+        char err[512] = {0};
+        rc = b200ls_parse_options(ss.str().c_str(), (name + "_").c_str(), &opts, err, sizeof err);
+        if (rc != B200LS_OK)
+            SETERRQ2(PETSC_COMM_WORLD, rc == B200LS_ERR_UNSUPPORTED ? PETSC_ERR_SUP : PETSC_ERR_ARG_WRONG,
+                     "B200 linear solver \"%s\": %s", name.c_str(), err);
+    }
+    B200CHK(handle, b200ls_set_options(handle, &opts));
+    if (nranks > 1) B200CHK(handle, b200ls_comm_init(handle, rank, nranks, B200LS_REDUCE_P2P, B200LS_HALO_STORE));
+    PetscFunctionReturn(0);
+}
+
+PetscErrorCode LinSolverB200::setGridInfo(const PetscInt &dim, const PetscInt n[3], const PetscBool periodic[3],
+                                          const std::vector<std::vector<PetscReal>> &dL, const PetscReal &dt)
+{
+    PetscFunctionBeginUser;
+    gdim = dim;
+    for (int d = 0; d < 3; ++d)
+    {
+        gn[d] = (d < dim) ? n[d] : 1;
+        gper[d] = (d < dim && periodic[d]) ? 1 : 0;
+        gdL[d].assign(d < dim ? dL[d].begin() : dL[0].begin(), d < dim ? dL[d].end() : dL[0].begin());
+    }
+    gdt = dt;
+    haveGrid = true;
+    PetscFunctionReturn(0);
+}
+
+// LinSolverKSP::setMatrix (linsolverksp.cpp:72-82).  The matrix is read once (like AmgXSolver::setA,
+// linsolveramgx.cpp:84); the caller keeps ownership.
+PetscErrorCode LinSolverB200::setMatrix(const Mat &A)
+{
+    PetscErrorCode ierr;
+    PetscFunctionBeginUser;
+    if (initStatus) SETERRQ1(PETSC_COMM_WORLD, initStatus, "B200 linear solver \"%s\" was not initialised.", name.c_str());
+
+    PetscInt rbeg, rend;
+    ierr = MatGetOwnershipRange(A, &rbeg, &rend); CHKERRQ(ierr);
+    const PetscInt nloc = rend - rbeg;
+
+    // local rows -> CSR with global column indices
+    std::vector<int64_t> rowptr((size_t)nloc + 1, 0);
+    std::vector<int32_t> col;
+    std::vector<double> val;
+    col.reserve((size_t)nloc * 7);
+    val.reserve((size_t)nloc * 7);
+    for (PetscInt r = rbeg; r < rend; ++r)
+    {
+        PetscInt nc;
+        const PetscInt *cols;
+        const PetscScalar *vals;
+        ierr = MatGetRow(A, r, &nc, &cols, &vals); CHKERRQ(ierr);
+        for (PetscInt q = 0; q < nc; ++q)
+        {
+            col.push_back((int32_t)cols[q]);
+            val.push_back((double)vals[q]);
+        }
+        rowptr[(size_t)(r - rbeg) + 1] = (int64_t)col.size();
+        ierr = MatRestoreRow(A, r, &nc, &cols, &vals); CHKERRQ(ierr);
+    }
+
+    // 1. try the matrix-free separable operator, verified entry by entry against A
+    bool recognised = false;
+    if (haveGrid)
+    {
+        const int64_t nslow = (gdim == 3) ? gn[2] : 1;
+        int64_t lo = 0, hi = nslow;
+        if (nranks > 1)
+        {
+            // z-slabs in natural ordering coincide with PETSc's DMDA ordering only for a 1 x 1 x P process
+            // grid (run with -da_processors_x 1 -da_processors_y 1); the range check below catches the rest
+            const int64_t base = nslow / nranks, rem = nslow % nranks;
+            lo = rank * base + (rank < rem ? rank : rem);
+            hi = lo + base + (rank < rem ? 1 : 0);
+        }
+        if ((int64_t)nloc == gn[0] * gn[1] * (hi - lo) && (int64_t)rbeg == gn[0] * gn[1] * lo)
+        {
+            B200CHK(handle, b200ls_set_poisson_stencil(handle, (int)gdim, gn, gper, gdL[0].data(), gdL[1].data(),
+                                                       gdim == 3 ? gdL[2].data() : nullptr, gdt, lo, hi));
+            double diff = 0.0;
+            const int rc = b200ls_verify_csr(handle, nloc, rowptr.data(), col.data(), val.data(), &diff);
+            if (rc == B200LS_OK) recognised = true;
+            else if (rc != B200LS_ERR_MISMATCH) B200CHK(handle, rc);
+        }
+        // every rank must agree, otherwise the transports would be mismatched
+        PetscMPIInt mine = recognised ? 1 : 0, all = 0;
+        ierr = MPI_Allreduce(&mine, &all, 1, MPI_INT, MPI_MIN, PETSC_COMM_WORLD); CHKERRQ(ierr);
+        recognised = (all == 1);
+    }
+    if (recognised)
+    {
+        opKind = "stencil";
+        if (nranks > 1)
+        {
+            // exchange the CUDA IPC handles of the exchange arenas: MPI is the host transport only
+            std::vector<char> mine(64), all((size_t)64 * nranks);
+            B200CHK(handle, b200ls_comm_export(handle, mine.data()));
+            ierr = MPI_Allgather(mine.data(), 64, MPI_BYTE, all.data(), 64, MPI_BYTE, PETSC_COMM_WORLD); CHKERRQ(ierr);
+            B200CHK(handle, b200ls_comm_connect(handle, all.data(), nranks));
+        }
+    }
+    else
+    {
+        // 2. verified fallback: the assembled operator itself, still on the GPU (IBPM's modified Poisson
+        //    system, the velocity system, BN order > 1)
+        if (nranks > 1)
+            SETERRQ1(PETSC_COMM_WORLD, PETSC_ERR_SUP,
+                     "B200 linear solver \"%s\": the matrix is not the separable pressure stencil of the mesh and the "
+                     "general CSR operator runs on one GPU only.", name.c_str());
+        B200CHK(handle, b200ls_set_csr(handle, nloc, rowptr.data(), col.data(), val.data()));
+        opKind = "csr";
+    }
+
+    // 3. the null space the application attached with MatSetNullSpace (navierstokes.cpp:404-413, ibpm.cpp:251-267)
+    MatNullSpace nsp = nullptr;
+    ierr = MatGetNullSpace(A, &nsp); CHKERRQ(ierr);
+    if (nsp)
+    {
+        PetscBool hasConst;
+        PetscInt nv;
+        const Vec *vecs;
+        ierr = MatNullSpaceGetVecs(nsp, &hasConst, &nv, &vecs); CHKERRQ(ierr);
+        std::vector<double> flat;
+        for (PetscInt q = 0; q < nv; ++q)
+        {
+            const PetscScalar *arr;
+            ierr = VecGetArrayRead(vecs[q], &arr); CHKERRQ(ierr);
+            flat.insert(flat.end(), arr, arr + nloc);
+            ierr = VecRestoreArrayRead(vecs[q], &arr); CHKERRQ(ierr);
+        }
+        B200CHK(handle, b200ls_set_nullspace(handle, hasConst ? 1 : 0, (int)nv, nv ? flat.data() : nullptr));
+    }
+    else
+        B200CHK(handle, b200ls_set_nullspace(handle, 0, 0, nullptr));
+    PetscFunctionReturn(0);
+}
+
+// LinSolverKSP::solve (linsolverksp.cpp:85-105): KSPSolve with a zero initial guess, fatal if reason < 0.
+PetscErrorCode LinSolverB200::solve(Vec &x, Vec &b)
+{
+    PetscErrorCode ierr;
+    PetscFunctionBeginUser;
+    if (initStatus) SETERRQ1(PETSC_COMM_WORLD, initStatus, "B200 linear solver \"%s\" was not initialised.", name.c_str());
+    const PetscScalar *barr;
+    PetscScalar *xarr;
+    ierr = VecGetArrayRead(b, &barr); CHKERRQ(ierr);
+    ierr = VecGetArray(x, &xarr); CHKERRQ(ierr);
+    const int rc = b200ls_solve(handle, barr, xarr);
+    ierr = VecRestoreArray(x, &xarr); CHKERRQ(ierr);
+    ierr = VecRestoreArrayRead(b, &barr); CHKERRQ(ierr);
+    if (rc == B200LS_ERR_DIVERGED)
+    {
+        int reason = 0;
+        b200ls_get_reason(handle, &reason);
+        SETERRQ2(PETSC_COMM_WORLD, PETSC_ERR_CONV_FAILED,
+                 "PetIBM exited due to B200 solver %s diverged with reason %d.", name.c_str(), reason);
+    }
+    B200CHK(handle, rc);
+    PetscFunctionReturn(0);
+}
+
+PetscErrorCode LinSolverB200::getIters(PetscInt &iters)
+{
+    PetscFunctionBeginUser;
+    int its = 0;
+    B200CHK(handle, b200ls_get_iters(handle, &its));
+    iters = its;
+    PetscFunctionReturn(0);
+}
+
+PetscErrorCode LinSolverB200::getResidual(PetscReal &res)
+{
+    PetscFunctionBeginUser;
+    double r = 0.0;
+    B200CHK(handle, b200ls_get_residual(handle, &r));
+    res = r;
+    PetscFunctionReturn(0);
+}
+
+}  // end of namespace linsolver
+}  // end of namespace petibm
