@@ -91,12 +91,17 @@ def main():
     torch.cuda.set_device(comm.device)
     cases = [((24, 20, 44), (0, 0, 0)), ((16, 12, 31), (0, 0, 1)), ((70, 9, 17), (1, 1, 0))]
     modes = [("p2p", "store"), ("nccl", "memcpy"), ("nccl", "store")]
-    if len(sys.argv) > 1:
-        modes = [tuple(m.split("+")) for m in sys.argv[1:]]
+    args = [a for a in sys.argv[1:] if a != "--c4"]
+    if "--c4" in sys.argv:
+        # BASELINE.json config 4: 256 x 128 x 128 stretched grid, domain-decomposed (run on 4 GPUs)
+        cases = [((256, 128, 128), (0, 0, 0))]
+        orc.set_fast(True, 0)
+    if args:
+        modes = [tuple(m.split("+")) for m in args]
     allok = True
     for reduce, halo in modes:
         for shape, per in cases:
-            for pc in ("none", "jacobi"):
+            for pc in (("none",) if "--c4" in sys.argv else ("none", "jacobi")):
                 allok &= run_case(comm, shape, per, pc, reduce, halo)
     comm.barrier()
     if comm.rank == 0:
