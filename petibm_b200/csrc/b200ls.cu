@@ -147,6 +147,7 @@ struct b200ls_solver
     int upd_blocks = 0;      // 0 = auto
     int tile = -1;           // K1 tile variant (-1: cost model picks 10 or 18; 10+: k_spmv2; <10: k_spmv)
     int upd_variant = 0;     // 0: flat k_update2, 1: first-generation k_update
+    int upd_reverse = 1;     // k_update2 walks the owned range top-down (L2 reuse of what k_spmv2 wrote last)
     int use_graph = 1;
     int use_pdl = 1;
     bool in_loop = false;    // launches issued from the CG loop may overlap their predecessor (PDL)
@@ -339,34 +340,21 @@ inline TileCfg tile_dims(int tile)
 {
     switch (tile)
     {
-        case 0: return {32, 8};
-        case 1: return {32, 6};
-        case 2: return {32, 10};
-        case 3: return {16, 10};
-        case 4: return {32, 16};
-        case 11: return {32, 8};
-        case 12: return {32, 10};
-        case 13: return {32, 6};
-        case 14: return {32, 12};
-        case 15: return {32, 8};
-        case 16: return {32, 16};
-        case 17: return {32, 8};
-        case 18: return {32, 12};
-        case 19: return {32, 10};
-        case 20: return {32, 16};
-        default: return {32, 8};  // 10
+        case 0: return {32, 8};    // first-generation kernel (kept for the profile comparison)
+        case 13: return {32, 6};   // 64 x 4 tile, S = 4, 4 CTAs/SM
+        case 15: return {32, 8};   // 64 x 6 tile, S = 3, 3 CTAs/SM
+        case 18: return {32, 12};  // 64 x 10 tile, S = 3, 2 CTAs/SM
+        default: return {32, 8};   // 10: 64 x 6 tile, S = 4, 3 CTAs/SM
     }
 }
 inline int tile_ctas_per_sm(int tile)
 {
     switch (tile)
     {
-        case 10: case 15: return 3;
-        case 11: case 13: case 17: return 4;
-        case 16: return 1;
-        case 12: case 14: case 18: case 20: return 2;
-        case 19: return 3;
-        default: return 2;
+        case 13: return 4;
+        case 18: return 2;
+        case 0: return 2;
+        default: return 3;
     }
 }
 
@@ -468,20 +456,9 @@ int launch_spmv_t(b200ls_solver *h, const VecSet &v, int ghost_store)
     switch (tile)
     {
         case 0: B200_SPMV_CASE(32, 8); break;
-        case 1: B200_SPMV_CASE(32, 6); break;
-        case 2: B200_SPMV_CASE(32, 10); break;
-        case 3: B200_SPMV_CASE(16, 10); break;
-        case 4: B200_SPMV_CASE(32, 16); break;
-        case 11: return launch_spmv2_cfg<8, 2, 4, JAC, false>(h, v, ghost_store, grid, kz);
-        case 12: return launch_spmv2_cfg<10, 4, 2, JAC, false>(h, v, ghost_store, grid, kz);
         case 13: return launch_spmv2_cfg<6, 4, 4, JAC, false>(h, v, ghost_store, grid, kz);
-        case 14: return launch_spmv2_cfg<12, 2, 2, JAC, false>(h, v, ghost_store, grid, kz);
         case 15: return launch_spmv2_cfg<8, 3, 3, JAC, false>(h, v, ghost_store, grid, kz);
-        case 16: return launch_spmv2_cfg<16, 2, 1, JAC, false>(h, v, ghost_store, grid, kz);
-        case 17: return launch_spmv2_cfg<8, 3, 4, JAC, false>(h, v, ghost_store, grid, kz);
         case 18: return launch_spmv2_cfg<12, 3, 2, JAC, false>(h, v, ghost_store, grid, kz);
-        case 19: return launch_spmv2_cfg<10, 2, 3, JAC, false>(h, v, ghost_store, grid, kz);
-        case 20: return launch_spmv2_cfg<16, 2, 2, JAC, false>(h, v, ghost_store, grid, kz);
         default: return launch_spmv2_cfg<8, 4, 3, JAC, false>(h, v, ghost_store, grid, kz);
     }
 #undef B200_SPMV_CASE
@@ -510,7 +487,7 @@ int upd_grid_blocks(const b200ls_solver *h)
 template <bool JAC, bool INIT>
 void launch_update_t(b200ls_solver *h, int fin_kind, bool push)
 {
-    UpdVecs v{h->r, h->w, h->dinv};
+    UpdVecs v{h->r, h->w, h->dinv, h->upd_reverse};
     CommDev cm = h->cm;
     if (!push)
     {
@@ -1130,6 +1107,7 @@ int b200ls_set_tuning(b200ls_solver *h, const char *key, int value)
     else if (k == "upd_blocks") h->upd_blocks = value;
     else if (k == "tile") h->tile = value;
     else if (k == "upd_variant") h->upd_variant = value;
+    else if (k == "upd_reverse") h->upd_reverse = value;
     else if (k == "use_graph") h->use_graph = value;
     else if (k == "use_pdl") h->use_pdl = value;
     else return fail(h, B200LS_ERR_ARG, "unknown tuning key %s", key);

@@ -807,6 +807,7 @@ struct UpdVecs
     double *r;
     const double *w;
     const double *dinv;
+    int reverse;  // walk the owned range from the top: the planes k_spmv2 wrote last are still in L2
 };
 
 template <bool JACOBI, bool INIT, int UNROLL>
@@ -981,21 +982,26 @@ __global__ void __launch_bounds__(256) k_update2(GridDev g, UpdVecs v, int fin_k
     const unsigned int nx = (unsigned int)g.nx;
     double acc[6] = {0, 0, 0, 0, 0, 0};
     unsigned int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int top = n2 - 1u;
+    const bool rev = v.reverse != 0;
     // main loop: all U items in range (n2 - i0 > (U-1)*stride, written without overflow)
     while (i0 < n2 && n2 - i0 > (unsigned int)(U - 1) * stride)
     {
         double2 rr[U], wr[U], dr[U];
+        unsigned int idx[U];
 #pragma unroll
         for (int u = 0; u < U; ++u)
         {
-            rr[u] = r2[i0 + u * stride];
-            if (!INIT) wr[u] = w2[i0 + u * stride];
-            if (JACOBI) dr[u] = d2[i0 + u * stride];
+            const unsigned int j = i0 + u * stride;
+            idx[u] = rev ? top - j : j;
+            rr[u] = r2[idx[u]];
+            if (!INIT) wr[u] = w2[idx[u]];
+            if (JACOBI) dr[u] = d2[idx[u]];
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            UpdItem<JACOBI, INIT, PADDED, PUSH>::run(i0 + u * stride, rr[u], wr[u], dr[u], ma, c, r2, gdn, gup, plane2, last0,
-                                                     pxh, nx, acc);
+            UpdItem<JACOBI, INIT, PADDED, PUSH>::run(idx[u], rr[u], wr[u], dr[u], ma, c, r2, gdn, gup, plane2, last0, pxh, nx,
+                                                     acc);
         if (n2 - i0 <= (unsigned int)U * stride)
         {
             i0 = n2;
@@ -1005,10 +1011,11 @@ __global__ void __launch_bounds__(256) k_update2(GridDev g, UpdVecs v, int fin_k
     }
     for (; i0 < n2; i0 = (n2 - i0 > stride) ? i0 + stride : n2)
     {
-        double2 rr = r2[i0], wr = make_double2(0, 0), dr = make_double2(0, 0);
-        if (!INIT) wr = w2[i0];
-        if (JACOBI) dr = d2[i0];
-        UpdItem<JACOBI, INIT, PADDED, PUSH>::run(i0, rr, wr, dr, ma, c, r2, gdn, gup, plane2, last0, pxh, nx, acc);
+        const unsigned int i = rev ? top - i0 : i0;
+        double2 rr = r2[i], wr = make_double2(0, 0), dr = make_double2(0, 0);
+        if (!INIT) wr = w2[i];
+        if (JACOBI) dr = d2[i];
+        UpdItem<JACOBI, INIT, PADDED, PUSH>::run(i, rr, wr, dr, ma, c, r2, gdn, gup, plane2, last0, pxh, nx, acc);
     }
     grid_reduce_finalize<6>(acc, fin_kind, ws, cm, st, kc, hist, PUSH);
 }
