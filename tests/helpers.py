@@ -37,3 +37,66 @@ def mat_of(A, const_nullspace=True):
 
     rp, col, val = A.arrays()
     return Mat(rp, col, val, A.shape[1]).setNullSpace(const_nullspace)
+
+
+def velocity_system(widths, periodic, dt=0.01, nu=0.01, c=0.5, vmin=0.0):
+    """Test-side assembly of PetIBM's implicit velocity operator A = I/dt - c*nu*L in packed [u|v|w]
+    ordering: createLaplacian (src/operators/createlaplacian.cpp:108-162: 1/(dLNeg*dLSelf), 1/(dLPos*dLSelf),
+    diagonal = -sum incl. ghost-side terms; :232-243 ghost coefficient * a0 folded into the row's diagonal) with
+    all-Dirichlet walls (a0 = 0 normal, -1 tangential, singleboundarydirichlet.cpp:33-42), then MatScale(-c*nu)
+    and MatShift(1/dt) (navierstokes.cpp:342-344).  Returns a scipy CSR matrix with sorted columns."""
+    import scipy.sparse as sp
+
+    dim = len(widths)
+    per = list(periodic) + [0] * (3 - dim)
+    ext = [float(np.sum(w)) for w in widths]
+    ax = [[orc.velocity_axis(widths[d], vmin, vmin + ext[d], same_dir=(f == d), periodic=bool(per[d])) for d in range(dim)]
+          for f in range(dim)]
+    nn = [[ax[f][d][0] for d in range(dim)] + [1] * (3 - dim) for f in range(dim)]
+    off = np.concatenate([[0], np.cumsum([int(np.prod(nn[f])) for f in range(dim)])])
+    rows, cols, vals = [], [], []
+    for f in range(dim):
+        n0, n1, n2 = nn[f]
+        for k in range(n2):
+            for j in range(n1):
+                for i in range(n0):
+                    idx = (i, j, k)
+                    row = off[f] + i + n0 * (j + n1 * k)
+                    v = []
+                    for d in range(dim):
+                        _, dL, co = ax[f][d]
+                        s = idx[d]
+                        dls = dL[s + 1]
+                        v.append(1.0 / ((co[s + 1] - co[s]) * dls))
+                        v.append(1.0 / ((co[s + 2] - co[s + 1]) * dls))
+                    acc = 0.0
+                    for t in v:
+                        acc = acc + t
+                    diag = -acc
+                    entries = {}
+                    for d in range(dim):
+                        for side, coef in ((-1, v[2 * d]), (+1, v[2 * d + 1])):
+                            nb = list(idx)
+                            nb[d] += side
+                            nd = nn[f][d]
+                            if 0 <= nb[d] < nd:
+                                pass
+                            elif per[d]:
+                                nb[d] %= nd
+                            else:
+                                a0 = 0.0 if d == f else -1.0     # Dirichlet: normal / tangential ghost
+                                diag = diag + coef * a0
+                                continue
+                            col = off[f] + nb[0] + n0 * (nb[1] + n1 * nb[2])
+                            entries[col] = entries.get(col, 0.0) + coef
+                    entries[row] = diag
+                    for col in sorted(entries):
+                        rows.append(row)
+                        cols.append(col)
+                        vals.append(entries[col])
+    L = sp.csr_matrix((vals, (rows, cols)), shape=(off[-1], off[-1]))
+    A = L.copy()
+    A.data = (-(c * nu)) * A.data
+    A = (A + sp.identity(off[-1], format="csr") * (1.0 / dt)).tocsr()
+    A.sort_indices()
+    return A, L
