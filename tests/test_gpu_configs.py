@@ -23,8 +23,24 @@ def pb():
     return petibm_b200
 
 
-def test_c1_cavity32_through_the_config_files(pb, tmp_path, golden_dir):
-    node = yaml.safe_load(open(os.path.join(golden_dir, "cavity32_config.yaml")))
+def _cavity32_settings():
+    """The 32 x 32 lid-driven cavity case (BASELINE.json config 1): unit square, uniform cells, Dirichlet walls,
+    moving lid, dt = 0.01, both solvers switched to the B200 backend.  Built here and round-tripped through
+    YAML text, which is how the settings reach createLinSolver inside PetIBM."""
+    axis = lambda d: {"direction": d, "start": 0.0, "subDomains": [{"end": 1.0, "cells": 32, "stretchRatio": 1.0}]}
+    wall = lambda loc, lid=0.0: {"location": loc, "u": ["DIRICHLET", lid], "v": ["DIRICHLET", 0.0]}
+    node = {"mesh": [axis("x"), axis("y")],
+            "flow": {"nu": 0.01, "initialVelocity": [0.0, 0.0],
+                     "boundaryConditions": [wall("xMinus"), wall("xPlus"), wall("yMinus"), wall("yPlus", 1.0)]},
+            "parameters": {"dt": 0.01, "startStep": 0, "nt": 1000, "nsave": 1000, "nrestart": 1000,
+                           "convection": "ADAMS_BASHFORTH_2", "diffusion": "CRANK_NICOLSON",
+                           "velocitySolver": {"type": "B200", "config": "config/velocity_solver.info"},
+                           "poissonSolver": {"type": "B200", "config": "config/poisson_solver.info"}}}
+    return yaml.safe_load(yaml.safe_dump(node))
+
+
+def test_c1_cavity32_through_the_config_files(pb, tmp_path):
+    node = _cavity32_settings()
     node["directory"] = str(tmp_path)
     (tmp_path / "config").mkdir()
     (tmp_path / "config" / "poisson_solver.info").write_text(
