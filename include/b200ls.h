@@ -132,6 +132,10 @@ int b200ls_set_tuning(b200ls_solver *h, const char *key, int value);
 int b200ls_comm_init(b200ls_solver *h, int rank, int nranks, int reduce_mode, int halo_mode);
 int b200ls_comm_export(b200ls_solver *h, void *handle64);
 int b200ls_comm_connect(b200ls_solver *h, const void *handles, int nranks);
+/* Collective: closes this rank's mappings of the peers' arenas. Call on every rank and barrier on the host
+ * transport BEFORE any rank replaces its operator (a second setMatrix), so that no arena is freed while a
+ * peer still maps it. No-op when not connected. */
+int b200ls_comm_disconnect(b200ls_solver *h);
 int b200ls_nccl_unique_id(void *id128);
 int b200ls_nccl_init(b200ls_solver *h, const void *id128);
 

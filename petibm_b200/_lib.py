@@ -57,6 +57,7 @@ SIGNATURES = {
     "b200ls_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "b200ls_comm_export": (C.c_int, [_vp, _vp]),
     "b200ls_comm_connect": (C.c_int, [_vp, _vp, C.c_int]),
+    "b200ls_comm_disconnect": (C.c_int, [_vp]),
     "b200ls_nccl_unique_id": (C.c_int, [_vp]),
     "b200ls_nccl_init": (C.c_int, [_vp, _vp]),
     "b200ls_set_poisson_stencil": (C.c_int, [_vp, C.c_int, _i64p, _ip, _dp, _dp, _dp, C.c_double, C.c_int64, C.c_int64]),

@@ -1199,6 +1199,24 @@ int b200ls_comm_connect(b200ls_solver *h, const void *handles, int nranks)
     return B200LS_OK;
 }
 
+// Drop the mappings of the peers' arenas (collective: every rank calls it, then the host transport
+// barriers, and only then may any rank free or replace its own arena, e.g. in a second setMatrix).
+int b200ls_comm_disconnect(b200ls_solver *h)
+{
+    if (!h) return B200LS_ERR_ARG;
+    if (!h->connected) return B200LS_OK;
+    cudaSetDevice(h->device);
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (int q = 0; q < (int)h->peer_base.size(); ++q)
+        if (q != h->rank && h->peer_base[q]) cudaIpcCloseMemHandle(h->peer_base[q]);
+    h->peer_base.clear();
+    h->connected = false;
+    h->ghost_dn = h->ghost_up = nullptr;
+    build_commdev(h);
+    invalidate_graph(h);
+    return B200LS_OK;
+}
+
 int b200ls_nccl_unique_id(void *id128)
 {
     if (!id128) return B200LS_ERR_ARG;

@@ -159,6 +159,12 @@ PetscErrorCode LinSolverB200::setMatrix(const Mat &A)
             lo = rank * base + (rank < rem ? rank : rem);
             hi = lo + base + (rank < rem ? 1 : 0);
         }
+        if (nranks > 1)
+        {
+            // a second setMatrix replaces the exchange arena: drop the peer mappings everywhere first
+            B200CHK(handle, b200ls_comm_disconnect(handle));
+            ierr = MPI_Barrier(PETSC_COMM_WORLD); CHKERRQ(ierr);
+        }
         if ((int64_t)nloc == gn[0] * gn[1] * (hi - lo) && (int64_t)rbeg == gn[0] * gn[1] * lo)
         {
             B200CHK(handle, b200ls_set_poisson_stencil(handle, (int)gdim, gn, gper, gdL[0].data(), gdL[1].data(),

@@ -183,6 +183,10 @@ class LinSolverB200(LinSolverBase):
         w = [np.ascontiguousarray(a, dtype=np.float64) for a in grid.widths]
         dz = w[2].ctypes.data_as(_lib._dp) if grid.dim == 3 else None
         lo, hi = self._slab(grid)
+        if self._comm is not None and self._comm.nranks > 1:
+            # replacing the operator frees the exchange arena: every rank first drops its mappings of the peers
+            _lib.check(self._L.b200ls_comm_disconnect(self._h), self._h)
+            self._comm.barrier()
         _lib.check(self._L.b200ls_set_poisson_stencil(
             self._h, grid.dim, n, per, w[0].ctypes.data_as(_lib._dp), w[1].ctypes.data_as(_lib._dp), dz,
             float(grid.dt), lo, hi), self._h)

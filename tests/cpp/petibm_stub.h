@@ -37,6 +37,7 @@ typedef int MPI_Op;
 inline PetscErrorCode PetscFinalized(PetscBool *f) { *f = PETSC_FALSE; return 0; }
 inline int MPI_Comm_rank(MPI_Comm, int *r) { *r = 0; return 0; }
 inline int MPI_Comm_size(MPI_Comm, int *s) { *s = 1; return 0; }
+inline int MPI_Barrier(MPI_Comm) { return 0; }
 inline int MPI_Allreduce(const void *s, void *r, int n, MPI_Datatype, MPI_Op, MPI_Comm) { for (int i = 0; i < n; ++i) ((int *)r)[i] = ((const int *)s)[i]; return 0; }
 inline int MPI_Allgather(const void *s, int n, MPI_Datatype, void *r, int, MPI_Datatype, MPI_Comm) { for (int i = 0; i < n; ++i) ((char *)r)[i] = ((const char *)s)[i]; return 0; }
 
