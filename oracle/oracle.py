@@ -79,6 +79,8 @@ def lib():
     L.orc_assemble_gradient.restype = vp
     L.orc_bnhead_order1.argtypes = [C.c_int64, C.c_double]
     L.orc_bnhead_order1.restype = vp
+    L.orc_bnhead.argtypes = [vp, C.c_double, C.c_double, C.c_int]
+    L.orc_bnhead.restype = vp
     L.orc_matmatmult.argtypes = [vp, vp]
     L.orc_matmatmult.restype = vp
     L.orc_assemble_dbng_literal.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_double, _dp]
@@ -226,6 +228,11 @@ def assemble_gradient(widths, periodic):
 
 def bnhead_order1(n, dt):
     return Csr(lib().orc_bnhead_order1(n, dt))
+
+
+def bnhead(Op: Csr, dt, coeff, N):
+    """createBnHead for any order N (createbn.cpp:19-95)."""
+    return Csr(lib().orc_bnhead(Op.h, float(dt), float(coeff), int(N)))
 
 
 def matmatmult(A: Csr, B: Csr):

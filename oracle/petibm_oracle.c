@@ -8,7 +8,9 @@
  *
  * PARITY STATUS: the grid / operator part is PINNED against the reference's own
  * golden vectors (tests/mesh/cartesianmesh2d_dirichlet.cpp:171-284,
- * tests/mesh/cartesianmesh2d_yperiodic.cpp:180-290) by tests/test_oracle_mesh.py.
+ * tests/mesh/cartesianmesh2d_yperiodic.cpp:180-290) by tests/test_oracle_mesh.py, and
+ * createBnHead (any order) against the reference's row-sum known-answer test
+ * (tests/operators/createbnhead_test.cpp:17-61) by tests/test_oracle_operator.py.
  * The Krylov part (KSPSolve_CG / KSPSolve_BCGS / KSPConvergedDefault /
  * MatNullSpaceRemove / PCApply_Jacobi) lives in PETSc 3.16 (pinned by
  * /root/reference/CMakeLists.txt:78-83, ">=3.16,<3.17"), which is NOT vendored
@@ -506,6 +508,81 @@ ORC_API orc_csr *orc_matmatmult(const orc_csr *A, const orc_csr *B)
     free(mark);
     free(acc);
     return C;
+}
+
+/* MatAXPY(Y, a, X, DIFFERENT_NONZERO_PATTERN): Y <- Y + a*X on the union pattern, columns sorted. */
+static orc_csr *csr_axpy(const orc_csr *Y, double a, const orc_csr *X)
+{
+    const int64_t n = Y->nrows;
+    int64_t nnz = 0;
+    for (int64_t i = 0; i < n; ++i)
+    {
+        int64_t p = Y->rowptr[i], q = X->rowptr[i];
+        while (p < Y->rowptr[i + 1] || q < X->rowptr[i + 1])
+        {
+            const int32_t cy = (p < Y->rowptr[i + 1]) ? Y->col[p] : INT32_MAX;
+            const int32_t cx = (q < X->rowptr[i + 1]) ? X->col[q] : INT32_MAX;
+            if (cy <= cx) ++p;
+            if (cx <= cy) ++q;
+            ++nnz;
+        }
+    }
+    orc_csr *Z = csr_alloc(n, Y->ncols, nnz);
+    nnz = 0;
+    for (int64_t i = 0; i < n; ++i)
+    {
+        Z->rowptr[i] = nnz;
+        int64_t p = Y->rowptr[i], q = X->rowptr[i];
+        while (p < Y->rowptr[i + 1] || q < X->rowptr[i + 1])
+        {
+            const int32_t cy = (p < Y->rowptr[i + 1]) ? Y->col[p] : INT32_MAX;
+            const int32_t cx = (q < X->rowptr[i + 1]) ? X->col[q] : INT32_MAX;
+            double v = 0.0;
+            int32_t c = (cy <= cx) ? cy : cx;
+            if (cy <= cx) v = Y->val[p++];
+            if (cx <= cy) v += a * X->val[q++];
+            Z->col[nnz] = c;
+            Z->val[nnz] = v;
+            ++nnz;
+        }
+    }
+    Z->rowptr[n] = nnz;
+    return Z;
+}
+
+static orc_csr *csr_copy(const orc_csr *A)
+{
+    orc_csr *B = csr_alloc(A->nrows, A->ncols, A->nnz);
+    memcpy(B->rowptr, A->rowptr, sizeof(int64_t) * (size_t)(A->nrows + 1));
+    memcpy(B->col, A->col, sizeof(int32_t) * (size_t)A->nnz);
+    memcpy(B->val, A->val, sizeof(double) * (size_t)A->nnz);
+    return B;
+}
+
+/* createBnHead for any order N (createbn.cpp:19-95):
+ *   BnHead = dt*I + sum_{term=2..N} dt^term * coeff^(term-1) * Op^(term-1)
+ * with the reference's evaluation order: rightMat = Op, then (term-2) products Op*rightMat,
+ * a = pow(dt,term)*pow(coeff,term-1), MatAXPY(BnHead, a, rightMat). */
+ORC_API orc_csr *orc_bnhead(const orc_csr *Op, double dt, double coeff, int N)
+{
+    if (N < 1 || Op->nrows != Op->ncols) return NULL;
+    orc_csr *B = orc_bnhead_order1(Op->nrows, dt);
+    for (int term = 2; term <= N; ++term)
+    {
+        orc_csr *right = csr_copy(Op);
+        for (int c = 2; c < term; ++c)
+        {
+            orc_csr *tmp = orc_matmatmult(Op, right);
+            orc_csr_free(right);
+            right = tmp;
+        }
+        const double a = pow(dt, term) * pow(coeff, term - 1);
+        orc_csr *Z = csr_axpy(B, a, right);
+        orc_csr_free(B);
+        orc_csr_free(right);
+        B = Z;
+    }
+    return B;
 }
 
 /* The literal pipeline of NavierStokesSolver::createOperators for BN order 1

@@ -101,3 +101,43 @@ def test_spmv_matches_scipy():
     A = orc.assemble_dbng(widths, (0, 1, 0), 0.01)
     x = rng.standard_normal(A.shape[0])
     np.testing.assert_allclose(A.spmv(x), A.to_scipy() @ x, rtol=0, atol=1e-15 * abs(A.to_scipy()).max() * 10)
+
+
+def test_bnhead_row_sum_kat_of_the_reference():
+    """The reference's own known-answer test for createBnHead (tests/operators/createbnhead_test.cpp:17-61):
+    Op = (2/dt) I on a 10 x 12 grid, dt = 2.3, c = 0.5; the sum of all entries of the N-th order BnHead is
+    nx*ny*dt * sum_{t=1..N} (c*dt*val)^(t-1), checked to 1e-11 for N = 1..10."""
+    dt, c = 2.3, 0.5
+    val = 2.0 / dt
+    nx, ny = 10, 12
+    n = nx * ny
+    Op = orc.Csr.from_arrays(n, n, np.arange(n + 1), np.arange(n), np.full(n, val))
+    ans = nx * ny * dt
+    for N in range(1, 11):
+        B = orc.bnhead(Op, dt, c, N)
+        assert B.shape == (n, n)
+        if N > 1:
+            ans += dt * nx * ny * (c * dt * val) ** (N - 1)
+        assert abs(B.to_scipy().sum() - ans) <= 1.0e-11
+
+
+def test_bnhead_order1_is_dt_identity_and_order2_widens_the_poisson_stencil():
+    import scipy.sparse as sp
+    from tests import helpers as H
+
+    widths = H.make_widths((7, 6, 5))
+    per = [0, 0, 0]
+    A, Lap = H.velocity_system(widths, per, dt=0.01, nu=0.01, c=0.5)
+    Lo = orc.Csr.from_arrays(Lap.shape[0], Lap.shape[1], Lap.indptr, Lap.indices, Lap.data)
+    B1 = orc.bnhead(Lo, 0.01, 0.5 * 0.01, 1).to_scipy()
+    assert abs(B1 - 0.01 * sp.identity(Lap.shape[0])).max() == 0.0
+    D = orc.assemble_divergence(widths, per)
+    G = orc.assemble_gradient(widths, per)
+    B2 = orc.bnhead(Lo, 0.01, 0.5 * 0.01, 2)
+    dbng1 = orc.assemble_dbng(widths, per, 0.01).to_scipy()
+    dbng2 = orc.matmatmult(D, orc.matmatmult(B2, G)).to_scipy()
+    # order 2 = order 1 + dt^2 c nu D L G: wider rows (up to 25 points), constants still in the null space
+    assert dbng2.getnnz(axis=1).max() > dbng1.getnnz(axis=1).max() >= 7 - 1
+    assert abs(dbng2 @ np.ones(dbng2.shape[0])).max() < 1e-12 * abs(dbng2).max()
+    ref = dbng1 + (0.01 ** 2) * (0.5 * 0.01) * (D.to_scipy() @ Lap @ G.to_scipy())
+    assert abs(dbng2 - ref).max() < 1e-13 * abs(dbng2).max()
