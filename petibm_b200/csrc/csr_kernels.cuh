@@ -9,7 +9,6 @@
 // BiCGStab follows KSPSolve_BCGS (bcgs.c) with left preconditioning: 4 kernels and 3 grid reductions per
 // iteration (PETSc: 2 MatMult, 2 PCApply, 6 vector passes, 4 reductions).
 #pragma once
-#include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "kernels.cuh"

@@ -25,8 +25,9 @@
 // (oracle: orc_assemble_dbng_literal + orc_spmv).  Only the reduction
 // order of the dot products differs from a serial CPU sum.
 #pragma once
-#include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "hw.cuh"
 
 namespace b200 {
 
@@ -76,12 +77,6 @@ struct CommDev
     double *r_ghost_up;          // neighbour above: address of ITS bottom ghost plane of r (or null)
 };
 
-__device__ __forceinline__ unsigned long long global_timer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 
 struct ReduceWs
 {
@@ -99,31 +94,7 @@ __device__ __forceinline__ void trace_kernel_start(const ReduceWs &ws)
         ws.trace[1] = global_timer_ns();
 }
 
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ double ld_volatile(const double *p)
-{
-    double v;
-    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
 
-// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute
-// may start while its predecessor is still draining; everything before pdl_sync() must not touch memory the
-// predecessor writes.  The trigger is issued AFTER the wait, so at most two grids are ever co-resident.
-__device__ __forceinline__ void pdl_sync()
-{
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -242,16 +213,6 @@ __device__ inline void finalize_scalars(int kind, const double *S, DevState &s, 
 // ------------------------------------------------------------------------------------------
 #define B200_LLW (2 * B200_NSUM)  // words per record
 
-__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // S: this rank's sums on entry (valid in every lane), the global sums on exit (valid in lane 0).
 // seq: sequence number of THIS reduction (previous + 1), identical on every rank.

@@ -19,40 +19,6 @@
 
 namespace b200 {
 
-__device__ __forceinline__ void cp_async16(unsigned int smem_dst, const void *gsrc)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async8(unsigned int smem_dst, const void *gsrc)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait()
-{
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ double2 lds128(unsigned int a)
-{
-    double2 v;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ double lds64(unsigned int a)
-{
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts128(unsigned int a, double2 v)
-{
-    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
-}
-__device__ __forceinline__ void sts64(unsigned int a, double v)
-{
-    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
-}
 
 template <int TXT, int TYT, int S, bool JACOBI, bool APPLY>
 struct Spmv2Smem
@@ -94,8 +60,8 @@ __global__ void __launch_bounds__(TXT *TYT, MINB)
     constexpr int BX = L::BX, TY = TYT - 2, SROW = L::SROW;
     constexpr unsigned A_R = 0, A_P = L::ARR_BYTES, A_X = 2 * L::ARR_BYTES, A_D = (APPLY ? 1 : 3) * L::ARR_BYTES;
     constexpr unsigned H_R = 0, H_P = L::HARR_BYTES, H_D = (APPLY ? 1 : 2) * L::HARR_BYTES;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const unsigned int smem_base = (unsigned int)__cvta_generic_to_shared(smem_raw);
+    B200_DYNAMIC_SMEM(smem_raw);
+    const unsigned int smem_base = smem_u32(smem_raw);
 
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int i0 = blockIdx.x * BX, j0 = blockIdx.y * TY;

@@ -1,0 +1,212 @@
+// emu_solver.cpp -- TEST SCAFFOLDING: drives the UNMODIFIED kernel sources of petibm_b200/csrc (kernels.cuh,
+// spmv2.cuh) under the fiber emulation of tests/emu/cuda_emu.h, single rank, with a host loop that mirrors
+// solve_stencil_cg of b200ls.cu (state reset, scatter, init passes, {k_spmv2, k_update2} until done, x tail,
+// gather).  Built by tests/test_emulated_kernels.py with g++ -DB200_EMULATE -ffp-contract=off; never shipped.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "spmv2.cuh"
+
+using namespace b200;
+
+namespace {
+
+struct Problem
+{
+    GridDev g{};
+    std::vector<double> axes;
+    size_t vec_elems = 0;
+    int64_t nlocal = 0;
+    int per[3] = {0, 0, 0};
+};
+
+void build(Problem &P, int dim, const int64_t *n, const int *per, const double *dx, const double *dy, const double *dz,
+           double dt)
+{
+    const int64_t nx = n[0], ny = n[1], nz = dim == 3 ? n[2] : 1;
+    std::vector<double> hdx(dx, dx + nx), hdy(dy, dy + ny), hdz;
+    if (dim == 3) hdz.assign(dz, dz + nz);
+    else hdz.assign(1, 1.0);
+    auto faces = [&](const std::vector<double> &d, bool periodic, bool active) {
+        const size_t m = d.size();
+        std::vector<double> gg(m + 1, 0.0);
+        if (!active) return gg;
+        for (size_t s = 1; s < m; ++s)
+        {
+            const double hh = 0.5 * (d[s] + d[s - 1]);
+            const double inv = 1.0 / hh;
+            gg[s] = dt * inv;
+        }
+        if (periodic)
+        {
+            const double hh = 0.5 * (d[0] + d[m - 1]);
+            const double inv = 1.0 / hh;
+            gg[0] = gg[m] = dt * inv;
+        }
+        return gg;
+    };
+    for (int d = 0; d < 3; ++d) P.per[d] = d < dim ? (per[d] != 0) : 0;
+    const auto gx = faces(hdx, P.per[0], true), gy = faces(hdy, P.per[1], true), gz = faces(hdz, P.per[2], dim == 3);
+    P.axes.clear();
+    size_t o[6];
+    const std::vector<double> *parts[6] = {&hdx, &hdy, &hdz, &gx, &gy, &gz};
+    for (int q = 0; q < 6; ++q)
+    {
+        o[q] = P.axes.size();
+        P.axes.insert(P.axes.end(), parts[q]->begin(), parts[q]->end());
+    }
+    GridDev &g = P.g;
+    g.nx = (int)nx;
+    g.ny = (int)ny;
+    g.nzl = (int)nz;
+    g.px = (int)((nx + 15) / 16 * 16);
+    g.plane = (long long)g.px * g.ny;
+    g.perx = P.per[0];
+    g.pery = P.per[1];
+    g.perz_wrap = P.per[2] ? 1 : 0;
+    g.kz0 = 0;
+    g.nzg = (int)nz;
+    g.wrapz_lo = P.per[2] ? 1 : 0;
+    g.wrapz_hi = P.per[2] ? 1 : 0;
+    g.dx = P.axes.data() + o[0];
+    g.dy = P.axes.data() + o[1];
+    g.dz = P.axes.data() + o[2];
+    g.gx = P.axes.data() + o[3];
+    g.gy = P.axes.data() + o[4];
+    g.gz = P.axes.data() + o[5];
+    P.nlocal = nx * ny * nz;
+    P.vec_elems = (size_t)g.plane * (size_t)(g.nzl + 2);
+}
+
+struct Ws
+{
+    std::vector<double> partials;
+    unsigned int counter[4] = {0, 0, 0, 0};
+    ReduceWs ws{};
+    CommDev cm{};
+    Ws()
+    {
+        partials.assign(8 * 65536, 0.0);
+        ws.partials = partials.data();
+        ws.counter = counter;
+        ws.trace = nullptr;
+        memset(&cm, 0, sizeof cm);
+        cm.nranks = 1;
+    }
+};
+
+template <int TYT, int S, int MINB, bool JAC, bool APPLY>
+void launch_spmv(const Problem &P, const VecSet &v, int kz, Ws &W, DevState *st, const SolveConsts &kc, double *hist)
+{
+    using L = Spmv2Smem<32, TYT, S, JAC, APPLY>;
+    const GridDev &g = P.g;
+    dim3 grid((unsigned)((g.nx + 63) / 64), (unsigned)((g.ny + TYT - 3) / (TYT - 2)), (unsigned)((g.nzl + kz - 1) / kz));
+    dim3 block(32, TYT);
+    const bool periodic = P.per[0] || P.per[1] || P.per[2];
+    if (periodic)
+        emu::launch(grid, block, L::total(kz), [&] { k_spmv2<32, TYT, S, MINB, JAC, APPLY, true>(g, v, kz, W.ws, W.cm, st, kc, hist, 0); });
+    else
+        emu::launch(grid, block, L::total(kz), [&] { k_spmv2<32, TYT, S, MINB, JAC, APPLY, false>(g, v, kz, W.ws, W.cm, st, kc, hist, 0); });
+}
+
+template <bool JAC, bool APPLY>
+void spmv(const Problem &P, int tile, const VecSet &v, int kz, Ws &W, DevState *st, const SolveConsts &kc, double *hist)
+{
+    if (tile == 18 && !APPLY) launch_spmv<12, 3, 2, JAC, APPLY>(P, v, kz, W, st, kc, hist);
+    else if (tile == 13 && !APPLY) launch_spmv<6, 4, 4, JAC, APPLY>(P, v, kz, W, st, kc, hist);
+    else if (tile == 15 && !APPLY) launch_spmv<8, 3, 3, JAC, APPLY>(P, v, kz, W, st, kc, hist);
+    else launch_spmv<8, 4, 3, JAC, APPLY>(P, v, kz, W, st, kc, hist);
+}
+
+template <bool JAC, bool INIT>
+void update(const Problem &P, const UpdVecs &v, int fin_kind, int blocks, Ws &W, DevState *st, const SolveConsts &kc,
+            double *hist)
+{
+    const GridDev &g = P.g;
+    if (g.px != g.nx)
+        emu::launch(dim3(blocks), dim3(256), 0, [&] { k_update2<JAC, INIT, true, false, 4>(g, v, fin_kind, W.ws, W.cm, st, kc, hist); });
+    else
+        emu::launch(dim3(blocks), dim3(256), 0, [&] { k_update2<JAC, INIT, false, false, 4>(g, v, fin_kind, W.ws, W.cm, st, kc, hist); });
+}
+
+}  // namespace
+
+extern "C" {
+
+// y = A x through k_spmv2 in APPLY mode (the b200ls_apply path)
+int emu_stencil_apply(int dim, const int64_t *n, const int *per, const double *dx, const double *dy, const double *dz,
+                      double dt, int kz, const double *x, double *y)
+{
+    Problem P;
+    build(P, dim, n, per, dx, dy, dz, dt);
+    Ws W;
+    std::vector<double> r(P.vec_elems, 0.0), w(P.vec_elems, 0.0);
+    DevState st{};
+    SolveConsts kc{};
+    emu::launch(dim3(4), dim3(256), 0, [&] { k_scatter(P.g, x, r.data(), nullptr); });
+    VecSet v{r.data(), nullptr, nullptr, w.data(), nullptr, nullptr};
+    if (kz <= 0) kz = P.g.nzl;
+    spmv<false, true>(P, 10, v, kz, W, &st, kc, nullptr);
+    emu::launch(dim3(4), dim3(256), 0, [&] { k_gather(P.g, w.data(), y); });
+    return 0;
+}
+
+// KSPSolve (CG) through the emulated kernels; mirrors solve_stencil_cg
+int emu_stencil_cg(int dim, const int64_t *n, const int *per, const double *dx, const double *dy, const double *dz, double dt,
+                   int jacobi, int has_const, int norm_type, double rtol, double atol, double divtol, int max_it, int tile,
+                   int kz, int upd_blocks, int upd_reverse, const double *b, double *x_out, double *hist, int hist_cap,
+                   int *nhist, int *its, int *reason, double *rnorm)
+{
+    Problem P;
+    build(P, dim, n, per, dx, dy, dz, dt);
+    Ws W;
+    const size_t ve = P.vec_elems;
+    std::vector<double> r(ve, 0.0), p0(ve, 0.0), p1(ve, 0.0), w(ve, 0.0), x(ve, 0.0), dinv;
+    if (jacobi)
+    {
+        dinv.assign(ve, 0.0);
+        emu::launch(dim3(4), dim3(256), 0, [&] { k_jacobi_setup(P.g, dinv.data()); });
+    }
+    SolveConsts kc{};
+    kc.rtol = rtol;
+    kc.atol = atol;
+    kc.divtol = divtol;
+    kc.nglobal = (double)P.nlocal;
+    kc.max_it = max_it;
+    kc.norm_type = norm_type;
+    kc.has_const = has_const;
+    kc.hist_cap = hist_cap;
+    DevState st{};
+    emu::launch(dim3(1), dim3(32), 0, [&] { k_state_reset(&st); });
+    emu::launch(dim3(4), dim3(256), 0, [&] { k_scatter(P.g, b, r.data(), x.data()); });
+    if (kz <= 0) kz = P.g.nzl;
+    if (upd_blocks <= 0) upd_blocks = 3;
+    UpdVecs uv{r.data(), w.data(), jacobi ? dinv.data() : nullptr, upd_reverse};
+    if (has_const)
+    {
+        if (jacobi) update<true, true>(P, uv, FIN_INIT_CENTRE, upd_blocks, W, &st, kc, hist);
+        else update<false, true>(P, uv, FIN_INIT_CENTRE, upd_blocks, W, &st, kc, hist);
+    }
+    if (jacobi) update<true, true>(P, uv, FIN_INIT, upd_blocks, W, &st, kc, hist);
+    else update<false, true>(P, uv, FIN_INIT, upd_blocks, W, &st, kc, hist);
+    double *pp[2] = {p0.data(), p1.data()};
+    for (int it = 0; it < max_it + 2 && !st.done; ++it)
+    {
+        VecSet v{r.data(), pp[it & 1], pp[(it & 1) ^ 1], w.data(), x.data(), jacobi ? dinv.data() : nullptr};
+        if (jacobi) spmv<true, false>(P, tile, v, kz, W, &st, kc, hist);
+        else spmv<false, false>(P, tile, v, kz, W, &st, kc, hist);
+        if (jacobi) update<true, false>(P, uv, FIN_UPDATE, upd_blocks, W, &st, kc, hist);
+        else update<false, false>(P, uv, FIN_UPDATE, upd_blocks, W, &st, kc, hist);
+    }
+    emu::launch(dim3(4), dim3(256), 0, [&] { k_xtail(P.g, x.data(), p0.data(), p1.data(), &st); });
+    emu::launch(dim3(4), dim3(256), 0, [&] { k_gather(P.g, x.data(), x_out); });
+    *nhist = st.nhist;
+    *its = st.its;
+    *reason = st.reason;
+    *rnorm = st.dp;
+    return st.done ? 0 : 1;
+}
+
+}  // extern "C"

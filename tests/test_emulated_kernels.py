@@ -1,0 +1,127 @@
+"""Kernel LOGIC on a CPU-only machine: the unmodified sources of petibm_b200/csrc/{kernels,spmv2}.cuh are compiled
+with g++ against tests/emu/cuda_emu.h (fiber emulation of threads, barriers, warp shuffles and late-completing
+cp.async copies; -DB200_EMULATE swaps csrc/hw.cuh) and driven by tests/emu/emu_solver.cpp, then compared with the
+oracle exactly like the GPU parity tests.  This is test scaffolding -- not a fallback: libb200ls.so cannot reach
+it -- and it says nothing about timing or the GPU memory model; it lets the indexing / halo / ring-buffer / KSP
+state-machine logic of a kernel change be checked before GPU time is spent on it."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu")
+LIB = os.path.join(EMU, "libb200emu.so")
+SRC = [os.path.join(EMU, f) for f in ("emu_solver.cpp", "cuda_emu.h")] + \
+      [os.path.join(ROOT, "petibm_b200", "csrc", f) for f in ("kernels.cuh", "spmv2.cuh", "hw.cuh")]
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in SRC):
+        cmd = ["g++", "-std=c++17", "-O1", "-DB200_EMULATE", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+               "-I", EMU, "-I", os.path.join(ROOT, "petibm_b200", "csrc"), "-o", LIB, SRC[0]]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr[-3000:]
+    L = C.CDLL(LIB)
+    L.emu_stencil_apply.argtypes = [C.c_int, C.POINTER(C.c_int64), _ip, _dp, _dp, _dp, C.c_double, C.c_int, _dp, _dp]
+    L.emu_stencil_cg.argtypes = [C.c_int, C.POINTER(C.c_int64), _ip, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_int,
+                                 C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp,
+                                 _dp, C.c_int, _ip, _ip, _ip, _dp]
+    return L
+
+
+def _grid_args(widths, per):
+    dim = len(widths)
+    n = (C.c_int64 * 3)(*([len(w) for w in widths] + [1] * (3 - dim)))
+    p = (C.c_int * 3)(*(list(per) + [0] * (3 - dim)))
+    w = [np.ascontiguousarray(a, dtype=np.float64) for a in widths]
+    dz = w[2].ctypes.data_as(_dp) if dim == 3 else None
+    return dim, n, p, w, dz
+
+
+def _apply(L, widths, per, x, kz=0):
+    dim, n, p, w, dz = _grid_args(widths, per)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    L.emu_stencil_apply(dim, n, p, w[0].ctypes.data_as(_dp), w[1].ctypes.data_as(_dp), dz, 0.01, kz,
+                        x.ctypes.data_as(_dp), y.ctypes.data_as(_dp))
+    return y
+
+
+def _cg(L, widths, per, b, pc="none", has_const=True, norm=1, rtol=0.0, atol=0.0, max_it=20, tile=10, kz=0, ub=3, rev=1):
+    dim, n, p, w, dz = _grid_args(widths, per)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.empty_like(b)
+    hist = np.zeros(max_it + 2)
+    nh, its, reason, rn = C.c_int(0), C.c_int(0), C.c_int(0), C.c_double(0)
+    rc = L.emu_stencil_cg(dim, n, p, w[0].ctypes.data_as(_dp), w[1].ctypes.data_as(_dp), dz, 0.01, int(pc == "jacobi"),
+                          int(has_const), norm, rtol, atol, 1e4, max_it, tile, kz, ub, rev, b.ctypes.data_as(_dp),
+                          x.ctypes.data_as(_dp), hist.ctypes.data_as(_dp), hist.size, C.byref(nh), C.byref(its),
+                          C.byref(reason), C.byref(rn))
+    assert rc == 0
+    return x, hist[: nh.value].copy(), its.value, reason.value, rn.value
+
+
+SHAPES = [((12, 10, 8), (0, 0, 0)), ((9, 7, 5), (1, 1, 1)), ((70, 13, 6), (0, 1, 0)), ((67, 9, 7), (1, 0, 1)),
+          ((33, 15), (0, 0)), ((20, 12), (1, 1)), ((5, 3, 3), (0, 0, 0))]
+
+
+@pytest.mark.parametrize("shape,per", SHAPES)
+def test_emulated_spmv_is_bit_exact(emu, shape, per):
+    widths = H.make_widths(shape)
+    A = H.oracle_matrix(widths, per)
+    x = np.random.default_rng(3).standard_normal(A.shape[0])
+    for kz in (0, 3):                      # one z-chunk and several (chunk halos)
+        if len(shape) == 2 and kz:
+            continue
+        assert np.array_equal(_apply(emu, widths, per, x, kz), A.spmv(x))
+
+
+@pytest.mark.parametrize("tile", [10, 18, 13, 15])
+@pytest.mark.parametrize("pc", ["none", "jacobi"])
+def test_emulated_cg_matches_oracle(emu, tile, pc):
+    for shape, per, kz in (((12, 10, 8), (0, 0, 0), 3), ((70, 9, 5), (0, 1, 1), 0)):
+        widths = H.make_widths(shape)
+        A = H.oracle_matrix(widths, per)
+        b, _ = H.consistent_rhs(A)
+        nit = 15
+        ref = orc.ksp_solve(A, b, pc_type=pc, rtol=0, atol=0, max_it=nit, const_nullspace=True)
+        x, hist, its, reason, rn = _cg(emu, widths, per, b, pc=pc, max_it=nit, tile=tile, kz=kz)
+        assert (its, reason) == (ref.its, ref.reason) == (nit, -3) and hist.size == nit + 1 and rn == hist[-1]
+        np.testing.assert_allclose(hist, ref.history, rtol=1e-10)
+        np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-9 * np.abs(ref.x).max())
+
+
+def test_emulated_convergence_logic_and_traversal_order(emu):
+    shape, per = (10, 8, 6), (0, 0, 0)
+    widths = H.make_widths(shape)
+    A = H.oracle_matrix(widths, per)
+    b, _ = H.consistent_rhs(A)
+    ref = orc.ksp_solve(A, b, rtol=1e-6, atol=1e-50, max_it=500, const_nullspace=True)
+    out = {}
+    for rev in (0, 1):
+        x, hist, its, reason, _ = _cg(emu, widths, per, b, rtol=1e-6, atol=1e-50, max_it=500, rev=rev, ub=2)
+        assert reason == ref.reason == 2 and its == ref.its and hist.size == its + 1
+        np.testing.assert_allclose(hist[:25], ref.history[:25], rtol=1e-10)
+        np.testing.assert_allclose(hist, ref.history, rtol=1e-5)   # round-off is amplified towards convergence
+        np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-7 * np.abs(ref.x).max())
+        out[rev] = x
+    # zero right-hand side: converged at iteration 0 with x = 0; NaN: KSP_DIVERGED_NANORINF
+    x, hist, its, reason, _ = _cg(emu, widths, per, np.zeros_like(b), rtol=1e-5, atol=1e-50)
+    assert (its, reason, hist.size) == (0, 3, 1) and np.all(x == 0.0)
+    bn = b.copy()
+    bn[7] = np.nan
+    assert _cg(emu, widths, per, bn, rtol=1e-5, atol=1e-50)[3] == -9
+    # without a null space, unpreconditioned norm
+    refu = orc.ksp_solve(A, b, pc_type="jacobi", norm_type="unpreconditioned", rtol=0, atol=0, max_it=12, const_nullspace=False)
+    _, hist, _, _, _ = _cg(emu, widths, per, b, pc="jacobi", has_const=False, norm=2, max_it=12)
+    np.testing.assert_allclose(hist, refu.history, rtol=1e-10)
