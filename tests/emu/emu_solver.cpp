@@ -133,10 +133,12 @@ void update(const Problem &P, const UpdVecs &v, int fin_kind, int blocks, Ws &W,
 
 }  // namespace
 
+#define EMU_API __attribute__((visibility("default")))
+
 extern "C" {
 
 // y = A x through k_spmv2 in APPLY mode (the b200ls_apply path)
-int emu_stencil_apply(int dim, const int64_t *n, const int *per, const double *dx, const double *dy, const double *dz,
+EMU_API int emu_stencil_apply(int dim, const int64_t *n, const int *per, const double *dx, const double *dy, const double *dz,
                       double dt, int kz, const double *x, double *y)
 {
     Problem P;
@@ -154,7 +156,7 @@ int emu_stencil_apply(int dim, const int64_t *n, const int *per, const double *d
 }
 
 // KSPSolve (CG) through the emulated kernels; mirrors solve_stencil_cg
-int emu_stencil_cg(int dim, const int64_t *n, const int *per, const double *dx, const double *dy, const double *dz, double dt,
+EMU_API int emu_stencil_cg(int dim, const int64_t *n, const int *per, const double *dx, const double *dy, const double *dz, double dt,
                    int jacobi, int has_const, int norm_type, double rtol, double atol, double divtol, int max_it, int tile,
                    int kz, int upd_blocks, int upd_reverse, const double *b, double *x_out, double *hist, int hist_cap,
                    int *nhist, int *its, int *reason, double *rnorm)

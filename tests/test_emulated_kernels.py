@@ -27,7 +27,10 @@ _ip = C.POINTER(C.c_int)
 @pytest.fixture(scope="module")
 def emu():
     if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in SRC):
+        # hidden visibility + -Bsymbolic: the kernel functions must bind inside this library, not to the CUDA host
+        # stubs of the same (mangled) names that libb200ls.so exports when it is loaded in the same process
         cmd = ["g++", "-std=c++17", "-O1", "-DB200_EMULATE", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+               "-fvisibility=hidden", "-fvisibility-inlines-hidden", "-Wl,-Bsymbolic",
                "-I", EMU, "-I", os.path.join(ROOT, "petibm_b200", "csrc"), "-o", LIB, SRC[0]]
         res = subprocess.run(cmd, capture_output=True, text=True)
         assert res.returncode == 0, res.stderr[-3000:]
