@@ -22,6 +22,7 @@
 
 #include "kernels.cuh"
 #include "spmv2.cuh"
+#include "spmv3.cuh"
 #include "csr_kernels.cuh"
 
 using namespace b200;
@@ -344,6 +345,8 @@ inline TileCfg tile_dims(int tile)
         case 13: return {32, 6};   // 64 x 4 tile, S = 4, 4 CTAs/SM
         case 15: return {32, 8};   // 64 x 6 tile, S = 3, 3 CTAs/SM
         case 18: return {32, 12};  // 64 x 10 tile, S = 3, 2 CTAs/SM
+        case 30: return {32, 12};  // k_spmv3 (balanced split), 64 x 10 tile, 2 CTAs/SM -- round-2 candidate
+        case 31: return {32, 8};   // k_spmv3 (balanced split), 64 x 6 tile, 3 CTAs/SM  -- round-2 candidate
         default: return {32, 8};   // 10: 64 x 6 tile, S = 4, 3 CTAs/SM
     }
 }
@@ -352,7 +355,7 @@ inline int tile_ctas_per_sm(int tile)
     switch (tile)
     {
         case 13: return 4;
-        case 18: return 2;
+        case 18: case 30: return 2;
         case 0: return 2;
         default: return 3;
     }
@@ -438,6 +441,55 @@ int launch_spmv2_cfg(b200ls_solver *h, const VecSet &v, int ghost_store, dim3 gr
     return B200LS_OK;
 }
 
+// k_spmv3: one resident wave of CTAs, equal ranges of the linearised (tile, plane) space
+struct K3Cfg { int nctas, planes_per_cta, max_seg; };
+inline K3Cfg k3_config(const b200ls_solver *h, int tyt, int ctas_per_sm)
+{
+    const int ty = tyt - 2;
+    const int64_t ntiles = (int64_t)((h->g.nx + 63) / 64) * ((h->g.ny + ty - 1) / ty);
+    const int64_t total = ntiles * h->g.nzl;
+    int64_t nctas = std::min<int64_t>((int64_t)h->num_sms * ctas_per_sm, std::max<int64_t>(1, total / 4));
+    int64_t ppc = (total + nctas - 1) / nctas;
+    ppc = std::min<int64_t>(ppc, 512);  // the coefficient table of a segment holds 512 planes
+    nctas = (total + ppc - 1) / ppc;
+    return {(int)nctas, (int)ppc, (int)std::min<int64_t>(ppc, h->g.nzl)};
+}
+
+template <int TYT, int S, int MINB, bool JAC>
+int launch_spmv3_cfg(b200ls_solver *h, const VecSet &v, int ghost_store)
+{
+    using L = Spmv2Smem<32, TYT, S, JAC, false>;
+    const K3Cfg c = k3_config(h, TYT, MINB);
+    const SolveConsts kc = make_consts(h);
+    dim3 grid((unsigned)c.nctas), block(32, TYT);
+    const size_t smem = L::total(c.max_seg);
+    if (grid_periodic(h))
+    {
+        auto kern = k_spmv3<32, TYT, S, MINB, JAC, false, true>;
+        static bool attr_done = false;
+        if (!attr_done)
+        {
+            CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total(512)));
+            attr_done = true;
+        }
+        CU(h, launch_k(h, h->in_loop && pdl_on(h), kern, grid, block, smem, h->g, v, c.planes_per_cta, c.max_seg, h->ws, h->cm,
+                       h->d_state, kc, h->d_hist, ghost_store));
+    }
+    else
+    {
+        auto kern = k_spmv3<32, TYT, S, MINB, JAC, false, false>;
+        static bool attr_done = false;
+        if (!attr_done)
+        {
+            CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total(512)));
+            attr_done = true;
+        }
+        CU(h, launch_k(h, h->in_loop && pdl_on(h), kern, grid, block, smem, h->g, v, c.planes_per_cta, c.max_seg, h->ws, h->cm,
+                       h->d_state, kc, h->d_hist, ghost_store));
+    }
+    return B200LS_OK;
+}
+
 template <bool JAC, bool APPLY>
 int launch_spmv_t(b200ls_solver *h, const VecSet &v, int ghost_store)
 {
@@ -459,6 +511,8 @@ int launch_spmv_t(b200ls_solver *h, const VecSet &v, int ghost_store)
         case 13: return launch_spmv2_cfg<6, 4, 4, JAC, false>(h, v, ghost_store, grid, kz);
         case 15: return launch_spmv2_cfg<8, 3, 3, JAC, false>(h, v, ghost_store, grid, kz);
         case 18: return launch_spmv2_cfg<12, 3, 2, JAC, false>(h, v, ghost_store, grid, kz);
+        case 30: return launch_spmv3_cfg<12, 3, 2, JAC>(h, v, ghost_store);
+        case 31: return launch_spmv3_cfg<8, 4, 3, JAC>(h, v, ghost_store);
         default: return launch_spmv2_cfg<8, 4, 3, JAC, false>(h, v, ghost_store, grid, kz);
     }
 #undef B200_SPMV_CASE

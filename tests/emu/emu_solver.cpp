@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "spmv2.cuh"
+#include "spmv3.cuh"
 
 using namespace b200;
 
@@ -111,9 +112,33 @@ void launch_spmv(const Problem &P, const VecSet &v, int kz, Ws &W, DevState *st,
         emu::launch(grid, block, L::total(kz), [&] { k_spmv2<32, TYT, S, MINB, JAC, APPLY, false>(g, v, kz, W.ws, W.cm, st, kc, hist, 0); });
 }
 
+// k_spmv3 (balanced split): `kz` is reused as the number of CTAs so that tests can force multi-segment ranges
+template <int TYT, int S, int MINB, bool JAC>
+void launch_spmv3(const Problem &P, const VecSet &v, int nctas, Ws &W, DevState *st, const SolveConsts &kc, double *hist)
+{
+    using L = Spmv2Smem<32, TYT, S, JAC, false>;
+    const GridDev &g = P.g;
+    const long long ntiles = (long long)((g.nx + 63) / 64) * ((g.ny + TYT - 3) / (TYT - 2));
+    const long long total = ntiles * g.nzl;
+    if (nctas <= 0) nctas = 3;
+    const int ppc = (int)((total + nctas - 1) / nctas);
+    const int grid = (int)((total + ppc - 1) / ppc) + 1;   // one CTA without work on purpose
+    const int max_seg = ppc < g.nzl ? ppc : g.nzl;
+    const bool periodic = P.per[0] || P.per[1] || P.per[2];
+    if (periodic)
+        emu::launch(dim3(grid), dim3(32, TYT), L::total(max_seg), [&] { k_spmv3<32, TYT, S, MINB, JAC, false, true>(g, v, ppc, max_seg, W.ws, W.cm, st, kc, hist, 0); });
+    else
+        emu::launch(dim3(grid), dim3(32, TYT), L::total(max_seg), [&] { k_spmv3<32, TYT, S, MINB, JAC, false, false>(g, v, ppc, max_seg, W.ws, W.cm, st, kc, hist, 0); });
+}
+
 template <bool JAC, bool APPLY>
 void spmv(const Problem &P, int tile, const VecSet &v, int kz, Ws &W, DevState *st, const SolveConsts &kc, double *hist)
 {
+    if constexpr (!APPLY)
+    {
+        if (tile == 30) return launch_spmv3<12, 3, 2, JAC>(P, v, kz, W, st, kc, hist);
+        if (tile == 31) return launch_spmv3<8, 4, 3, JAC>(P, v, kz, W, st, kc, hist);
+    }
     if (tile == 18 && !APPLY) launch_spmv<12, 3, 2, JAC, APPLY>(P, v, kz, W, st, kc, hist);
     else if (tile == 13 && !APPLY) launch_spmv<6, 4, 4, JAC, APPLY>(P, v, kz, W, st, kc, hist);
     else if (tile == 15 && !APPLY) launch_spmv<8, 3, 3, JAC, APPLY>(P, v, kz, W, st, kc, hist);
@@ -183,7 +208,7 @@ EMU_API int emu_stencil_cg(int dim, const int64_t *n, const int *per, const doub
     DevState st{};
     emu::launch(dim3(1), dim3(32), 0, [&] { k_state_reset(&st); });
     emu::launch(dim3(4), dim3(256), 0, [&] { k_scatter(P.g, b, r.data(), x.data()); });
-    if (kz <= 0) kz = P.g.nzl;
+    if (kz <= 0 && tile < 30) kz = P.g.nzl;
     if (upd_blocks <= 0) upd_blocks = 3;
     UpdVecs uv{r.data(), w.data(), jacobi ? dinv.data() : nullptr, upd_reverse};
     if (has_const)

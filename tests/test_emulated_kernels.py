@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
 LIB = os.path.join(EMU, "libb200emu.so")
 SRC = [os.path.join(EMU, f) for f in ("emu_solver.cpp", "cuda_emu.h")] + \
-      [os.path.join(ROOT, "petibm_b200", "csrc", f) for f in ("kernels.cuh", "spmv2.cuh", "hw.cuh")]
+      [os.path.join(ROOT, "petibm_b200", "csrc", f) for f in ("kernels.cuh", "spmv2.cuh", "spmv3.cuh", "hw.cuh")]
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -128,3 +128,20 @@ def test_emulated_convergence_logic_and_traversal_order(emu):
     refu = orc.ksp_solve(A, b, pc_type="jacobi", norm_type="unpreconditioned", rtol=0, atol=0, max_it=12, const_nullspace=False)
     _, hist, _, _, _ = _cg(emu, widths, per, b, pc="jacobi", has_const=False, norm=2, max_it=12)
     np.testing.assert_allclose(hist, refu.history, rtol=1e-10)
+
+
+@pytest.mark.parametrize("tile", [30, 31])
+@pytest.mark.parametrize("pc", ["none", "jacobi"])
+def test_emulated_balanced_split_kernel(emu, tile, pc):
+    """k_spmv3 (round-2 candidate): CTA ranges that start mid-tile, span two tiles, or are empty."""
+    for shape, per, nctas in (((12, 10, 8), (0, 0, 0), 3), ((70, 25, 7), (0, 1, 1), 5), ((130, 9, 5), (1, 0, 0), 4),
+                              ((33, 31), (0, 0), 2)):
+        widths = H.make_widths(shape)
+        A = H.oracle_matrix(widths, per)
+        b, _ = H.consistent_rhs(A)
+        nit = 12
+        ref = orc.ksp_solve(A, b, pc_type=pc, rtol=0, atol=0, max_it=nit, const_nullspace=True)
+        x, hist, its, reason, _ = _cg(emu, widths, per, b, pc=pc, max_it=nit, tile=tile, kz=nctas)
+        assert (its, reason) == (nit, -3)
+        np.testing.assert_allclose(hist, ref.history, rtol=1e-10)
+        np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-9 * np.abs(ref.x).max())
