@@ -236,4 +236,136 @@ EMU_API int emu_stencil_cg(int dim, const int64_t *n, const int *per, const doub
     return st.done ? 0 : 1;
 }
 
+// ---- R emulated ranks (z-slabs), NCCL-style transport: every rank's kernel leaves its partial sums in its send
+// buffer (CommDev.mode = 2), the "all-reduce" adds them in rank order, k_scalars finishes on every rank; the
+// update kernel pushes its boundary planes straight into the neighbours' ghost planes (HALO_STORE) and the SpMV
+// kernel keeps the ghost planes of p up to date (ghost_store).  Checks the slab / wrap / ghost logic of the
+// multi-GPU path without GPUs; the mailbox all-reduce itself needs real concurrency and is covered on hardware.
+EMU_API int emu_stencil_cg_ranks(int nranks, const int64_t *n, const int *per, const double *dx, const double *dy,
+                                 const double *dz, double dt, int jacobi, int has_const, double rtol, double atol, int max_it,
+                                 int tile, int kz, const double *b, double *x_out, double *hist, int hist_cap, int *nhist,
+                                 int *its, int *reason)
+{
+    struct Rank
+    {
+        Problem P;
+        Ws W;
+        std::vector<double> r, p0, p1, w, x, dinv, hist, sendrecv;
+        DevState st{};
+        int64_t lo = 0, hi = 0;
+    };
+    const int64_t nx = n[0], ny = n[1], nz = n[2];
+    std::vector<Rank> R((size_t)nranks);
+    for (int q = 0; q < nranks; ++q)
+    {
+        Rank &k = R[(size_t)q];
+        build(k.P, 3, n, per, dx, dy, dz, dt);
+        const int64_t base = nz / nranks, rem = nz % nranks;
+        k.lo = q * base + (q < rem ? q : rem);
+        k.hi = k.lo + base + (q < rem ? 1 : 0);
+        GridDev &g = k.P.g;
+        g.nzl = (int)(k.hi - k.lo);
+        g.kz0 = (int)k.lo;
+        g.perz_wrap = 0;
+        g.wrapz_lo = (per[2] && k.lo == 0) ? 1 : 0;
+        g.wrapz_hi = (per[2] && k.hi == nz) ? 1 : 0;
+        k.P.vec_elems = (size_t)g.plane * (size_t)(g.nzl + 2);
+        k.P.nlocal = nx * ny * (k.hi - k.lo);
+        const size_t ve = k.P.vec_elems;
+        k.r.assign(ve, 0.0); k.p0.assign(ve, 0.0); k.p1.assign(ve, 0.0); k.w.assign(ve, 0.0); k.x.assign(ve, 0.0);
+        k.hist.assign((size_t)hist_cap, 0.0);
+        k.sendrecv.assign(16, 0.0);
+        if (jacobi)
+        {
+            k.dinv.assign(ve, 0.0);
+            emu::launch(dim3(2), dim3(256), 0, [&] { k_jacobi_setup(k.P.g, k.dinv.data()); });
+        }
+        k.W.cm.rank = q;
+        k.W.cm.nranks = nranks;
+        k.W.cm.mode = 2;
+        k.W.cm.sendbuf = k.sendrecv.data();
+    }
+    // neighbours' ghost planes of r (periodic wrap closes the ring)
+    for (int q = 0; q < nranks; ++q)
+    {
+        int dn = q - 1, up = q + 1;
+        if (dn < 0) dn = per[2] ? nranks - 1 : -1;
+        if (up >= nranks) up = per[2] ? 0 : -1;
+        Rank &k = R[(size_t)q];
+        k.W.cm.r_ghost_up = up >= 0 ? R[(size_t)up].r.data() : nullptr;
+        k.W.cm.r_ghost_dn = dn >= 0 ? R[(size_t)dn].r.data() + (size_t)(R[(size_t)dn].P.g.nzl + 1) * (size_t)k.P.g.plane : nullptr;
+    }
+    SolveConsts kc{};
+    kc.rtol = rtol; kc.atol = atol; kc.divtol = 1e4;
+    kc.nglobal = (double)(nx * ny * nz);
+    kc.max_it = max_it; kc.norm_type = 1; kc.has_const = has_const; kc.hist_cap = hist_cap;
+    auto allreduce_and_finish = [&](int kind) {
+        double S[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (auto &k : R)
+            for (int s = 0; s < 8; ++s) S[s] += k.sendrecv[(size_t)s];
+        for (auto &k : R)
+        {
+            for (int s = 0; s < 8; ++s) k.sendrecv[8 + (size_t)s] = S[s];
+            emu::launch(dim3(1), dim3(32), 0, [&] { k_scalars(kind, k.sendrecv.data() + 8, &k.st, kc, k.hist.data()); });
+        }
+    };
+    auto update_all = [&](bool init, int kind) {
+        for (auto &k : R)
+        {
+            UpdVecs uv{k.r.data(), k.w.data(), jacobi ? k.dinv.data() : nullptr, 1};
+            const GridDev &g = k.P.g;
+#define EMU_UPD(JAC, INIT, PAD) emu::launch(dim3(3), dim3(256), 0, [&] { k_update2<JAC, INIT, PAD, true, 4>(g, uv, kind, k.W.ws, k.W.cm, &k.st, kc, k.hist.data()); })
+            const bool pad = g.px != g.nx;
+            if (jacobi) { if (init) { if (pad) EMU_UPD(true, true, true); else EMU_UPD(true, true, false); } else { if (pad) EMU_UPD(true, false, true); else EMU_UPD(true, false, false); } }
+            else { if (init) { if (pad) EMU_UPD(false, true, true); else EMU_UPD(false, true, false); } else { if (pad) EMU_UPD(false, false, true); else EMU_UPD(false, false, false); } }
+#undef EMU_UPD
+        }
+        allreduce_and_finish(kind);
+    };
+    for (auto &k : R)
+    {
+        emu::launch(dim3(1), dim3(32), 0, [&] { k_state_reset(&k.st); });
+        const double *bl = b + (size_t)(nx * ny * k.lo);
+        emu::launch(dim3(2), dim3(256), 0, [&] { k_scatter(k.P.g, bl, k.r.data(), k.x.data()); });
+    }
+    if (has_const) update_all(true, FIN_INIT_CENTRE);
+    update_all(true, FIN_INIT);
+    for (int it = 0; it < max_it + 2 && !R[0].st.done; ++it)
+    {
+        for (auto &k : R)
+        {
+            double *pp[2] = {k.p0.data(), k.p1.data()};
+            VecSet v{k.r.data(), pp[it & 1], pp[(it & 1) ^ 1], k.w.data(), k.x.data(), jacobi ? k.dinv.data() : nullptr};
+            const GridDev &g = k.P.g;
+            const int kzz = kz > 0 ? kz : g.nzl;
+            using L8 = Spmv2Smem<32, 8, 4, false, false>;
+            using L8J = Spmv2Smem<32, 8, 4, true, false>;
+            dim3 grid((unsigned)((g.nx + 63) / 64), (unsigned)((g.ny + 5) / 6), (unsigned)((g.nzl + kzz - 1) / kzz));
+            const bool periodic = per[0] || per[1] || per[2];
+            (void)tile;
+#define EMU_SPMV(JAC, PER, LL) emu::launch(grid, dim3(32, 8), LL::total(kzz), [&] { k_spmv2<32, 8, 4, 3, JAC, false, PER>(g, v, kzz, k.W.ws, k.W.cm, &k.st, kc, k.hist.data(), 1); })
+            if (jacobi) { if (periodic) EMU_SPMV(true, true, L8J); else EMU_SPMV(true, false, L8J); }
+            else { if (periodic) EMU_SPMV(false, true, L8); else EMU_SPMV(false, false, L8); }
+#undef EMU_SPMV
+        }
+        allreduce_and_finish(FIN_SPMV);
+        update_all(false, FIN_UPDATE);
+    }
+    for (auto &k : R)
+    {
+        emu::launch(dim3(2), dim3(256), 0, [&] { k_xtail(k.P.g, k.x.data(), k.p0.data(), k.p1.data(), &k.st); });
+        double *xl = x_out + (size_t)(nx * ny * k.lo);
+        emu::launch(dim3(2), dim3(256), 0, [&] { k_gather(k.P.g, k.x.data(), xl); });
+    }
+    // every rank must hold the same scalars
+    for (auto &k : R)
+        if (k.st.nhist != R[0].st.nhist || k.st.reason != R[0].st.reason || memcmp(k.hist.data(), R[0].hist.data(), sizeof(double) * (size_t)std::min(R[0].st.nhist, hist_cap)) != 0)
+            return 2;
+    *nhist = R[0].st.nhist;
+    *its = R[0].st.its;
+    *reason = R[0].st.reason;
+    memcpy(hist, R[0].hist.data(), sizeof(double) * (size_t)std::min(R[0].st.nhist, hist_cap));
+    return R[0].st.done ? 0 : 1;
+}
+
 }  // extern "C"

@@ -39,6 +39,8 @@ def emu():
     L.emu_stencil_cg.argtypes = [C.c_int, C.POINTER(C.c_int64), _ip, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_int,
                                  C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp,
                                  _dp, C.c_int, _ip, _ip, _ip, _dp]
+    L.emu_stencil_cg_ranks.argtypes = [C.c_int, C.POINTER(C.c_int64), _ip, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_double,
+                                       C.c_double, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _ip, _ip, _ip]
     return L
 
 
@@ -144,4 +146,28 @@ def test_emulated_balanced_split_kernel(emu, tile, pc):
         x, hist, its, reason, _ = _cg(emu, widths, per, b, pc=pc, max_it=nit, tile=tile, kz=nctas)
         assert (its, reason) == (nit, -3)
         np.testing.assert_allclose(hist, ref.history, rtol=1e-10)
+        np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-9 * np.abs(ref.x).max())
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+@pytest.mark.parametrize("pc", ["none", "jacobi"])
+def test_emulated_multi_rank_slabs(emu, nranks, pc):
+    """Slab partition, ghost planes of p (recomputed) and r (pushed by the update kernel), periodic-z ring, scalars
+    identical on every rank -- the multi-GPU kernel logic with an emulated NCCL-style all-reduce."""
+    for shape, per, kz in (((12, 10, 11), (0, 0, 0), 0), ((70, 9, 10), (0, 1, 1), 2), ((9, 8, 7), (1, 0, 1), 0)):
+        widths = H.make_widths(shape)
+        A = H.oracle_matrix(widths, per)
+        b, _ = H.consistent_rhs(A)
+        nit = 12
+        ref = orc.ksp_solve(A, b, pc_type=pc, rtol=0, atol=0, max_it=nit, const_nullspace=True)
+        dim, n, p, w, dz = _grid_args(widths, per)
+        x = np.empty_like(b)
+        hist = np.zeros(nit + 2)
+        nh, its, reason = C.c_int(0), C.c_int(0), C.c_int(0)
+        rc = emu.emu_stencil_cg_ranks(nranks, n, p, w[0].ctypes.data_as(_dp), w[1].ctypes.data_as(_dp), dz, 0.01,
+                                      int(pc == "jacobi"), 1, 0.0, 0.0, nit, 10, kz, b.ctypes.data_as(_dp),
+                                      x.ctypes.data_as(_dp), hist.ctypes.data_as(_dp), hist.size, C.byref(nh), C.byref(its),
+                                      C.byref(reason))
+        assert rc == 0 and (its.value, reason.value, nh.value) == (nit, -3, nit + 1)
+        np.testing.assert_allclose(hist[: nh.value], ref.history, rtol=1e-10)
         np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-9 * np.abs(ref.x).max())
