@@ -5,14 +5,16 @@
 // MatMult_MPIAIJ, VecXDot, 2x VecAXPY, PCApply, MatNullSpaceRemove (VecSum + VecShift), VecNorm,
 // VecXDot, VecAYPX -- is expressed here as TWO kernels and 72 B/row of HBM traffic:
 //
-//   k_spmv   (class 0):  x <- x + a' p'   (the PREVIOUS iteration's VecAXPY(X,a,P), deferred so that
+//   class 0 (k_spmv2 in spmv2.cuh; k_spmv below is its first generation, k_spmv3 a round-2 candidate):
+//                        x <- x + a' p'   (the PREVIOUS iteration's VecAXPY(X,a,P), deferred so that
 //                                          p' is read once for both uses)
 //                        p <- z + b p'    (z = B r + shift recomputed on the fly, halo included)
 //                        w <- A p         (matrix-free 5/7-point stencil from 1-D arrays)
 //                        dpi <- p.w       (warp-shuffle -> block -> last-block reduction)
 //                        a <- beta/dpi    (+ KSP_DIVERGED_INDEFINITE_MAT test) by the last block
 //                        reads r,p',x  writes p,w,x                                   = 48 B/row
-//   k_update (class 1):  r <- r - a w
+//   class 1 (k_update2 below; k_update is its first generation):
+//                        r <- r - a w
 //                        {sum z0, sum d, sum d^2, sum d r, sum r, sum r^2}, d = z0 - c
 //                        -> shift, dp = ||z||, beta = z.r, KSPConvergedDefault, b = beta/betaold
 //                        (+ multi-GPU: boundary planes of r stored straight into the neighbour's
@@ -24,6 +26,10 @@
 // assembled CSR path, so that the matrix-free SpMV is bit-identical to MatMult on D*(dt*G)
 // (oracle: orc_assemble_dbng_literal + orc_spmv).  Only the reduction
 // order of the dot products differs from a serial CPU sum.
+//
+// File map: hw.cuh (inline PTX + the emulation switch), kernels.cuh (state machine of cg.c / iterativ.c,
+// grid reduction + LL mailbox all-reduce, update kernels, layout helpers), spmv2.cuh / spmv3.cuh (fused SpMV),
+// csr_kernels.cuh (assembled-operator path, BiCGStab).
 #pragma once
 #include <stdint.h>
 
