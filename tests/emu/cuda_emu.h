@@ -55,6 +55,7 @@ struct Fiber
     int lane = 0, warp = 0;
     long ncoll = 0;               // warp collectives executed
     long committed = 0;           // cp.async groups committed
+    int sleep = 0;                // schedule fuzzing: scheduler passes to sit out
     std::vector<PendingCopy> pending;
 };
 struct Warp
@@ -72,8 +73,28 @@ inline int bar_arrived = 0;
 inline unsigned char *dyn_smem = nullptr;
 inline unsigned long long fake_clock = 0;
 inline long progress = 0;
+// schedule fuzzing (emu_set_schedule): shuffled fiber order and random preemption at shared-memory accesses, so
+// that a missing barrier shows up as a result that depends on the schedule
+inline unsigned long long rng = 0;
+inline bool fuzz = false;
+inline unsigned int rnd()
+{
+    rng ^= rng << 13;
+    rng ^= rng >> 7;
+    rng ^= rng << 17;
+    return (unsigned int)(rng >> 11);
+}
 
 inline void yield() { swapcontext(&cur->ctx, &sched_ctx); }
+inline void maybe_yield()
+{
+    if (fuzz && (rnd() & 3u) == 0u)
+    {
+        ++progress;
+        if ((rnd() & 15u) == 0u) cur->sleep = (int)(rnd() % 6u);  // occasionally fall far behind
+        yield();
+    }
+}
 
 inline void trampoline()
 {
@@ -155,10 +176,21 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F &&kernel_body)
                 while (done < nthr)
                 {
                     const long before = progress;
-                    for (size_t q = 0; q < nthr; ++q)
+                    static std::vector<size_t> order;
+                    order.resize(nthr);
+                    for (size_t q = 0; q < nthr; ++q) order[q] = q;
+                    if (fuzz)
+                        for (size_t q = nthr - 1; q > 0; --q) std::swap(order[q], order[rnd() % (q + 1)]);
+                    for (size_t oq = 0; oq < nthr; ++oq)
                     {
-                        Fiber &f = fibers[q];
+                        Fiber &f = fibers[order[oq]];
                         if (f.state != RUN) continue;
+                        if (f.sleep > 0)
+                        {
+                            --f.sleep;
+                            ++progress;
+                            continue;
+                        }
                         cur = &f;
                         threadIdx = f.tid;
                         blockIdx = {bx, by, bz};
@@ -257,6 +289,7 @@ inline void cp_async_commit() { emu::cur->committed++; }
 template <int N>
 inline void cp_async_wait()
 {
+    emu::maybe_yield();
     auto &pend = emu::cur->pending;
     const long limit = emu::cur->committed - N;  // groups < limit must be complete
     size_t keep = 0;
@@ -267,9 +300,9 @@ inline void cp_async_wait()
     }
     pend.resize(keep);
 }
-inline double2 lds128(unsigned int a) { double2 v; memcpy(&v, smem_ptr(a), 16); return v; }
-inline double lds64(unsigned int a) { double v; memcpy(&v, smem_ptr(a), 8); return v; }
-inline void sts128(unsigned int a, double2 v) { memcpy(smem_ptr(a), &v, 16); }
-inline void sts64(unsigned int a, double v) { memcpy(smem_ptr(a), &v, 8); }
+inline double2 lds128(unsigned int a) { emu::maybe_yield(); double2 v; memcpy(&v, smem_ptr(a), 16); return v; }
+inline double lds64(unsigned int a) { emu::maybe_yield(); double v; memcpy(&v, smem_ptr(a), 8); return v; }
+inline void sts128(unsigned int a, double2 v) { emu::maybe_yield(); memcpy(smem_ptr(a), &v, 16); }
+inline void sts64(unsigned int a, double v) { emu::maybe_yield(); memcpy(smem_ptr(a), &v, 8); }
 
 }  // namespace b200

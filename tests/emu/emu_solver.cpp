@@ -162,6 +162,13 @@ void update(const Problem &P, const UpdVecs &v, int fin_kind, int blocks, Ws &W,
 
 extern "C" {
 
+// seed != 0: shuffled fiber order + random preemption at shared-memory accesses; 0: deterministic round-robin
+EMU_API void emu_set_schedule(unsigned long long seed)
+{
+    emu::fuzz = seed != 0;
+    emu::rng = seed * 0x9E3779B97F4A7C15ull + 1ull;
+}
+
 // y = A x through k_spmv2 in APPLY mode (the b200ls_apply path)
 EMU_API int emu_stencil_apply(int dim, const int64_t *n, const int *per, const double *dx, const double *dy, const double *dz,
                       double dt, int kz, const double *x, double *y)

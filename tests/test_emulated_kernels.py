@@ -41,6 +41,7 @@ def emu():
                                  _dp, C.c_int, _ip, _ip, _ip, _dp]
     L.emu_stencil_cg_ranks.argtypes = [C.c_int, C.POINTER(C.c_int64), _ip, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_double,
                                        C.c_double, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _ip, _ip, _ip]
+    L.emu_set_schedule.argtypes = [C.c_uint64]
     return L
 
 
@@ -171,3 +172,24 @@ def test_emulated_multi_rank_slabs(emu, nranks, pc):
         assert rc == 0 and (its.value, reason.value, nh.value) == (nit, -3, nit + 1)
         np.testing.assert_allclose(hist[: nh.value], ref.history, rtol=1e-10)
         np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-9 * np.abs(ref.x).max())
+
+
+@pytest.mark.parametrize("tile", [10, 18, 30])
+def test_results_do_not_depend_on_the_thread_schedule(emu, tile):
+    """Race check: shuffled fiber order and random preemption at every shared-memory access must not change a
+    single bit (a missing barrier in the tile ring / stage ring / coefficient table / state staging would)."""
+    # tile 30: 6 tiles x 7 planes over 5 CTAs -> ranges that end one tile and start the next (segment boundary)
+    shape, per = ((70, 13, 9), (0, 1, 0)) if tile < 30 else ((70, 25, 7), (0, 1, 0))
+    widths = H.make_widths(shape)
+    A = H.oracle_matrix(widths, per)
+    b, _ = H.consistent_rhs(A)
+    kz = 3 if tile < 30 else 5
+    emu.emu_set_schedule(0)
+    x0, h0, its0, reason0, _ = _cg(emu, widths, per, b, pc="jacobi", max_it=8, tile=tile, kz=kz)
+    try:
+        for seed in (1, 2, 3):
+            emu.emu_set_schedule(seed)
+            x, h, its, reason, _ = _cg(emu, widths, per, b, pc="jacobi", max_it=8, tile=tile, kz=kz)
+            assert np.array_equal(h, h0) and np.array_equal(x, x0) and (its, reason) == (its0, reason0)
+    finally:
+        emu.emu_set_schedule(0)
