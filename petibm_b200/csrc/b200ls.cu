@@ -345,8 +345,8 @@ inline TileCfg tile_dims(int tile)
         case 13: return {32, 6};   // 64 x 4 tile, S = 4, 4 CTAs/SM
         case 15: return {32, 8};   // 64 x 6 tile, S = 3, 3 CTAs/SM
         case 18: return {32, 12};  // 64 x 10 tile, S = 3, 2 CTAs/SM
-        case 30: return {32, 12};  // k_spmv3 (balanced split), 64 x 10 tile, 2 CTAs/SM -- round-2 candidate
-        case 31: return {32, 8};   // k_spmv3 (balanced split), 64 x 6 tile, 3 CTAs/SM  -- round-2 candidate
+        case 30: case 32: return {32, 12};  // k_spmv3 (balanced split; 32: + split barrier), 64 x 10 tile -- round-2 candidates
+        case 31: case 33: return {32, 8};   // k_spmv3 (balanced split; 33: + split barrier), 64 x 6 tile  -- round-2 candidates
         default: return {32, 8};   // 10: 64 x 6 tile, S = 4, 3 CTAs/SM
     }
 }
@@ -355,7 +355,7 @@ inline int tile_ctas_per_sm(int tile)
     switch (tile)
     {
         case 13: return 4;
-        case 18: case 30: return 2;
+        case 18: case 30: case 32: return 2;
         case 0: return 2;
         default: return 3;
     }
@@ -455,17 +455,17 @@ inline K3Cfg k3_config(const b200ls_solver *h, int tyt, int ctas_per_sm)
     return {(int)nctas, (int)ppc, (int)std::min<int64_t>(ppc, h->g.nzl)};
 }
 
-template <int TYT, int S, int MINB, bool JAC>
+template <int TYT, int S, int MINB, bool JAC, bool SPLIT>
 int launch_spmv3_cfg(b200ls_solver *h, const VecSet &v, int ghost_store)
 {
-    using L = Spmv2Smem<32, TYT, S, JAC, false>;
+    using L = Spmv3Smem<32, TYT, S, JAC, false, SPLIT ? 4 : 3>;
     const K3Cfg c = k3_config(h, TYT, MINB);
     const SolveConsts kc = make_consts(h);
     dim3 grid((unsigned)c.nctas), block(32, TYT);
     const size_t smem = L::total(c.max_seg);
     if (grid_periodic(h))
     {
-        auto kern = k_spmv3<32, TYT, S, MINB, JAC, false, true>;
+        auto kern = k_spmv3<32, TYT, S, MINB, JAC, false, true, SPLIT>;
         static bool attr_done = false;
         if (!attr_done)
         {
@@ -477,7 +477,7 @@ int launch_spmv3_cfg(b200ls_solver *h, const VecSet &v, int ghost_store)
     }
     else
     {
-        auto kern = k_spmv3<32, TYT, S, MINB, JAC, false, false>;
+        auto kern = k_spmv3<32, TYT, S, MINB, JAC, false, false, SPLIT>;
         static bool attr_done = false;
         if (!attr_done)
         {
@@ -511,8 +511,10 @@ int launch_spmv_t(b200ls_solver *h, const VecSet &v, int ghost_store)
         case 13: return launch_spmv2_cfg<6, 4, 4, JAC, false>(h, v, ghost_store, grid, kz);
         case 15: return launch_spmv2_cfg<8, 3, 3, JAC, false>(h, v, ghost_store, grid, kz);
         case 18: return launch_spmv2_cfg<12, 3, 2, JAC, false>(h, v, ghost_store, grid, kz);
-        case 30: return launch_spmv3_cfg<12, 3, 2, JAC>(h, v, ghost_store);
-        case 31: return launch_spmv3_cfg<8, 4, 3, JAC>(h, v, ghost_store);
+        case 30: return launch_spmv3_cfg<12, 3, 2, JAC, false>(h, v, ghost_store);
+        case 31: return launch_spmv3_cfg<8, 4, 3, JAC, false>(h, v, ghost_store);
+        case 32: return launch_spmv3_cfg<12, 3, 2, JAC, true>(h, v, ghost_store);
+        case 33: return launch_spmv3_cfg<8, 4, 3, JAC, true>(h, v, ghost_store);
         default: return launch_spmv2_cfg<8, 4, 3, JAC, false>(h, v, ghost_store, grid, kz);
     }
 #undef B200_SPMV_CASE

@@ -91,6 +91,27 @@ __device__ __forceinline__ void sts64(unsigned int a, double v)
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
 
+// ---- mbarrier (shared-memory barrier object, sm_80+): arrive and wait are separate operations, so a CTA-wide
+// barrier can be ARRIVED at in step t and WAITED for in step t+1 (k_spmv3 SPLITBAR)
+__device__ __forceinline__ void mbar_init(unsigned int a, unsigned int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned int a)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned int a, unsigned int parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "MBAR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MBAR_DONE;\n\t"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n\t}" ::"r"(a), "r"(parity) : "memory");
+}
+
 #define B200_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 __device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
 

@@ -8,18 +8,34 @@
 // the tail of a tile followed by the head of the next (at most ceil(range/nz)+1 segments).  All CTAs start and end
 // together and a segment is as long as the slab allows.  The per-segment body is the k_spmv2 body verbatim.
 // Verified on the CPU emulation (tests/test_emulated_kernels.py); not yet timed on a GPU.
+//
+// SPLITBAR (tile = 32 | 33): the CTA barrier of a plane step is split with an mbarrier pair -- every thread ARRIVES
+// right after publishing its p(t) row and WAITS, one step later, for the barrier of step t-1 only.  The stencil of
+// step t needs the rows written in step t-1, whose barrier everybody reached a whole step ago, so the wait is
+// (almost) never a stall; the tile ring is 4 planes deep so that the write of step t+2 cannot overtake a
+// neighbour's stencil reads of step t (which precede its arrival of step t+1).
 #pragma once
 #include "spmv2.cuh"
 
 namespace b200 {
 
-template <int TXT, int TYT, int S, int MINB, bool JACOBI, bool APPLY, bool PER>
+template <int TXT, int TYT, int S, bool JACOBI, bool APPLY, int NT>
+struct Spmv3Smem : Spmv2Smem<TXT, TYT, S, JACOBI, APPLY>
+{
+    using B = Spmv2Smem<TXT, TYT, S, JACOBI, APPLY>;
+    static constexpr unsigned mbar_off = B::tile_off + (unsigned)NT * B::TILE_BYTES;  // two 8-byte mbarriers
+    static constexpr unsigned coef_off = mbar_off + 16u;
+    static size_t total(int kz_chunk) { return coef_off + 16u * (size_t)(kz_chunk + 2); }
+};
+
+template <int TXT, int TYT, int S, int MINB, bool JACOBI, bool APPLY, bool PER, bool SPLITBAR>
 __global__ void __launch_bounds__(TXT *TYT, MINB)
     k_spmv3(GridDev g, VecSet v, int planes_per_cta, int kz_chunk, ReduceWs ws, CommDev cm, DevState *st, SolveConsts kc, double *hist,
             int ghost_store)
 {
     static_assert(TXT == 32, "one warp per tile row");
-    using L = Spmv2Smem<TXT, TYT, S, JACOBI, APPLY>;
+    constexpr int NT = SPLITBAR ? 4 : 3;  // planes in the tile ring
+    using L = Spmv3Smem<TXT, TYT, S, JACOBI, APPLY, NT>;
     constexpr int BX = L::BX, TY = TYT - 2, SROW = L::SROW;
     constexpr unsigned A_R = 0, A_P = L::ARR_BYTES, A_X = 2 * L::ARR_BYTES, A_D = (APPLY ? 1 : 3) * L::ARR_BYTES;
     constexpr unsigned H_R = 0, H_P = L::HARR_BYTES, H_D = (APPLY ? 1 : 2) * L::HARR_BYTES;
@@ -33,6 +49,18 @@ __global__ void __launch_bounds__(TXT *TYT, MINB)
     const long long w1 = min(w0 + (long long)planes_per_cta, total_work);
     double shift = 0.0, bcoef = 0.0, aprev = 0.0, acc0 = 0.0;
     bool xupd = false, state_read = false;
+    // SPLITBAR: steps are counted across segments (mbarrier phases and the 4-plane ring never restart)
+    unsigned int gstep = 0;
+    const unsigned int mbar0 = smem_base + L::mbar_off;
+    if (SPLITBAR)
+    {
+        if (tx == 0 && ty == 0)
+        {
+            mbar_init(mbar0, TXT * TYT);
+            mbar_init(mbar0 + 8u, TXT * TYT);
+        }
+        __syncthreads();
+    }
     while (w0 < w1)
     {
         const int tile = (int)(w0 / g.nzl);
@@ -204,7 +232,8 @@ __global__ void __launch_bounds__(TXT *TYT, MINB)
         // one plane: PH = t mod 3 (static); pnew/pcen/pmin = registers of planes kk, kk-1, kk-2
         auto step = [&](int t, auto ph, double2 &pnew, const double2 &pcen, const double2 &pmin) {
             constexpr int PH = decltype(ph)::value;
-            constexpr unsigned TB_NEW = PH * L::TILE_BYTES, TB_CEN = ((PH + 2) % 3) * L::TILE_BYTES;
+            const unsigned TB_NEW = SPLITBAR ? (gstep & 3u) * L::TILE_BYTES : (unsigned)PH * L::TILE_BYTES;
+            const unsigned TB_CEN = SPLITBAR ? ((gstep + 3u) & 3u) * L::TILE_BYTES : (unsigned)((PH + 2) % 3) * L::TILE_BYTES;
             issue(t + S - 1);
             const bool own = (t >= 1) && (t < nplanes - 1);
             cp_async_wait<S - 1>();
@@ -264,7 +293,14 @@ __global__ void __launch_bounds__(TXT *TYT, MINB)
                     else if (st0) *reinterpret_cast<double *>(bpo + so) = pnew.x;
                 }
             }
-            __syncthreads();
+            if (SPLITBAR)
+            {
+                mbar_arrive(mbar0 + 8u * (gstep & 1u));
+                if (gstep > 0) mbar_wait(mbar0 + 8u * ((gstep - 1u) & 1u), ((gstep - 1u) >> 1) & 1u);
+                ++gstep;
+            }
+            else
+                __syncthreads();
             // ---- w on plane k = kk-1 (needs p on kk-2, kk-1, kk)
             if (t >= 2)
             {

@@ -7,7 +7,7 @@ import petibm_b200 as pb
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, nargs=3, default=[256, 256, 256])
-ap.add_argument("--tiles", type=int, nargs="*", default=[0, 10, 13, 15, 18, 30, 31])
+ap.add_argument("--tiles", type=int, nargs="*", default=[0, 10, 13, 15, 18, 30, 31, 32, 33])
 ap.add_argument("--kz", type=int, nargs="*", default=[0])
 ap.add_argument("--upd", type=int, nargs="*", default=[0])
 ap.add_argument("--pc", default="none")

@@ -300,6 +300,31 @@ inline void cp_async_wait()
     }
     pend.resize(keep);
 }
+// mbarrier: {pending arrivals, expected count, parity of the current (incomplete) phase}; an arrival always counts
+// towards the CURRENT phase (as on hardware), so protocol errors show up as wrong results / deadlocks
+struct EmuMbar { unsigned int pending; unsigned short count; unsigned short phase; };
+inline void mbar_init(unsigned int a, unsigned int count)
+{
+    EmuMbar m = {count, (unsigned short)count, 0};
+    memcpy(smem_ptr(a), &m, 8);
+}
+inline void mbar_arrive(unsigned int a)
+{
+    emu::maybe_yield();
+    EmuMbar *m = reinterpret_cast<EmuMbar *>(smem_ptr(a));
+    if (--m->pending == 0)
+    {
+        m->phase ^= 1;
+        m->pending = m->count;
+    }
+    ++emu::progress;
+}
+inline void mbar_wait(unsigned int a, unsigned int parity)
+{
+    const EmuMbar *m = reinterpret_cast<const EmuMbar *>(smem_ptr(a));
+    while (m->phase == parity) emu::yield();
+    emu::maybe_yield();
+}
 inline double2 lds128(unsigned int a) { emu::maybe_yield(); double2 v; memcpy(&v, smem_ptr(a), 16); return v; }
 inline double lds64(unsigned int a) { emu::maybe_yield(); double v; memcpy(&v, smem_ptr(a), 8); return v; }
 inline void sts128(unsigned int a, double2 v) { emu::maybe_yield(); memcpy(smem_ptr(a), &v, 16); }

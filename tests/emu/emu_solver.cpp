@@ -113,10 +113,10 @@ void launch_spmv(const Problem &P, const VecSet &v, int kz, Ws &W, DevState *st,
 }
 
 // k_spmv3 (balanced split): `kz` is reused as the number of CTAs so that tests can force multi-segment ranges
-template <int TYT, int S, int MINB, bool JAC>
+template <int TYT, int S, int MINB, bool JAC, bool SPLIT>
 void launch_spmv3(const Problem &P, const VecSet &v, int nctas, Ws &W, DevState *st, const SolveConsts &kc, double *hist)
 {
-    using L = Spmv2Smem<32, TYT, S, JAC, false>;
+    using L = Spmv3Smem<32, TYT, S, JAC, false, SPLIT ? 4 : 3>;
     const GridDev &g = P.g;
     const long long ntiles = (long long)((g.nx + 63) / 64) * ((g.ny + TYT - 3) / (TYT - 2));
     const long long total = ntiles * g.nzl;
@@ -126,9 +126,9 @@ void launch_spmv3(const Problem &P, const VecSet &v, int nctas, Ws &W, DevState 
     const int max_seg = ppc < g.nzl ? ppc : g.nzl;
     const bool periodic = P.per[0] || P.per[1] || P.per[2];
     if (periodic)
-        emu::launch(dim3(grid), dim3(32, TYT), L::total(max_seg), [&] { k_spmv3<32, TYT, S, MINB, JAC, false, true>(g, v, ppc, max_seg, W.ws, W.cm, st, kc, hist, 0); });
+        emu::launch(dim3(grid), dim3(32, TYT), L::total(max_seg), [&] { k_spmv3<32, TYT, S, MINB, JAC, false, true, SPLIT>(g, v, ppc, max_seg, W.ws, W.cm, st, kc, hist, 0); });
     else
-        emu::launch(dim3(grid), dim3(32, TYT), L::total(max_seg), [&] { k_spmv3<32, TYT, S, MINB, JAC, false, false>(g, v, ppc, max_seg, W.ws, W.cm, st, kc, hist, 0); });
+        emu::launch(dim3(grid), dim3(32, TYT), L::total(max_seg), [&] { k_spmv3<32, TYT, S, MINB, JAC, false, false, SPLIT>(g, v, ppc, max_seg, W.ws, W.cm, st, kc, hist, 0); });
 }
 
 template <bool JAC, bool APPLY>
@@ -136,8 +136,10 @@ void spmv(const Problem &P, int tile, const VecSet &v, int kz, Ws &W, DevState *
 {
     if constexpr (!APPLY)
     {
-        if (tile == 30) return launch_spmv3<12, 3, 2, JAC>(P, v, kz, W, st, kc, hist);
-        if (tile == 31) return launch_spmv3<8, 4, 3, JAC>(P, v, kz, W, st, kc, hist);
+        if (tile == 30) return launch_spmv3<12, 3, 2, JAC, false>(P, v, kz, W, st, kc, hist);
+        if (tile == 31) return launch_spmv3<8, 4, 3, JAC, false>(P, v, kz, W, st, kc, hist);
+        if (tile == 32) return launch_spmv3<12, 3, 2, JAC, true>(P, v, kz, W, st, kc, hist);
+        if (tile == 33) return launch_spmv3<8, 4, 3, JAC, true>(P, v, kz, W, st, kc, hist);
     }
     if (tile == 18 && !APPLY) launch_spmv<12, 3, 2, JAC, APPLY>(P, v, kz, W, st, kc, hist);
     else if (tile == 13 && !APPLY) launch_spmv<6, 4, 4, JAC, APPLY>(P, v, kz, W, st, kc, hist);

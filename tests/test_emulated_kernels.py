@@ -133,7 +133,7 @@ def test_emulated_convergence_logic_and_traversal_order(emu):
     np.testing.assert_allclose(hist, refu.history, rtol=1e-10)
 
 
-@pytest.mark.parametrize("tile", [30, 31])
+@pytest.mark.parametrize("tile", [30, 31, 32, 33])
 @pytest.mark.parametrize("pc", ["none", "jacobi"])
 def test_emulated_balanced_split_kernel(emu, tile, pc):
     """k_spmv3 (round-2 candidate): CTA ranges that start mid-tile, span two tiles, or are empty."""
@@ -174,7 +174,7 @@ def test_emulated_multi_rank_slabs(emu, nranks, pc):
         np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-9 * np.abs(ref.x).max())
 
 
-@pytest.mark.parametrize("tile", [10, 18, 30])
+@pytest.mark.parametrize("tile", [10, 18, 30, 32, 33])
 def test_results_do_not_depend_on_the_thread_schedule(emu, tile):
     """Race check: shuffled fiber order and random preemption at every shared-memory access must not change a
     single bit (a missing barrier in the tile ring / stage ring / coefficient table / state staging would)."""
