@@ -173,10 +173,20 @@ __global__ void __launch_bounds__(TXT *TYT, MINB)
 
         // ---- producer: one cp.async group per plane; ld_stage = ring offset of the stage being filled
         unsigned int ld_stage = 0, ld_hstage = 0;
+        // non-periodic instantiation: consecutive planes are consecutive in storage, so the load offset is one
+        // loop-carried 64-bit add per plane instead of a 64-bit multiply-and-wrap per plane
+        long long ld_off = plane_off(0) + tB;
         auto issue = [&](int t) {
             if (t < nplanes)
             {
-                const long long o = plane_off(t) + tB;
+                long long o;
+                if (PER)
+                    o = plane_off(t) + tB;
+                else
+                {
+                    o = ld_off;
+                    ld_off += planeB;
+                }
                 const unsigned int sd = ring_thr + ld_stage;
                 if (vec_ok)
                 {
@@ -209,7 +219,7 @@ __global__ void __launch_bounds__(TXT *TYT, MINB)
                 }
                 if (!APPLY && xupd && t >= 1 && t < nplanes - 1)
                 {
-                    const long long xo = (long long)(k0 + t) * planeB + tB;
+                    const long long xo = PER ? (long long)(k0 + t) * planeB + tB : o;  // x never wraps
                     if (st1) cp_async16(sd + A_X, bx + xo);
                     else if (st0) cp_async8(sd + A_X, bx + xo);
                 }
