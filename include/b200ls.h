@@ -142,9 +142,9 @@ int b200ls_nccl_init(b200ls_solver *h, const void *id128);
 /* ---- operator ----
  * Matrix-free separable pressure-Poisson operator DBNG = D (dt I) G of a stretched Cartesian
  * staggered grid:  dx,dy,dz are the GLOBAL pressure-cell widths
- * (dz ignored when dim == 2), periodic[d] the periodicity flags, [zlo, zhi) the z-planes this
- * rank owns (0..nz for a single GPU; y-range for dim == 2 is always full, the slab axis is the
- * slowest axis: z in 3-D, y in 2-D).  Vectors passed to b200ls_solve are the rank-local part in
+ * (dz ignored when dim == 2), periodic[d] the periodicity flags, [slab_lo, slab_hi) the planes this
+ * rank owns along the slowest axis (z in 3-D, y in 2-D; ignored for a single GPU in 2-D, where the
+ * whole grid is owned).  Vectors passed to b200ls_solve are the rank-local part in
  * PETSc DMDA ordering (i fastest), length nx*ny*(zhi-zlo) (3-D) or nx*(yhi-ylo) (2-D). */
 int b200ls_set_poisson_stencil(b200ls_solver *h, int dim, const int64_t n[3], const int periodic[3],
                                const double *dx, const double *dy, const double *dz, double dt,

@@ -1311,9 +1311,18 @@ int b200ls_set_poisson_stencil(b200ls_solver *h, int dim, const int64_t n[3], co
         return fail(h, B200LS_ERR_UNSUPPORTED, "grid too large for 32-bit item indexing");
     for (int d = 0; d < dim; ++d)
         if (periodic[d] && n[d] < 3) return fail(h, B200LS_ERR_UNSUPPORTED, "periodic axis %d needs at least 3 cells", d);
+    if (dim == 2 && h->nranks > 1)
+    {
+        // several GPUs: a 2-D grid is the 3-D code on (nx, 1, ny) with y-slabs.  The arithmetic is bit-identical to
+        // the 2-D form: dy' = {1.0} makes every product an exact multiplication by one, the y' faces are walls
+        // (coefficient 0, exact additions of zero), the D-row / CSR-row orders keep x before the slab axis.
+        const int64_t n3[3] = {n[0], 1, n[1]};
+        const int per3[3] = {periodic[0], 0, periodic[1]};
+        const double one = 1.0;
+        return b200ls_set_poisson_stencil(h, 3, n3, per3, dx, &one, dy, dt, slab_lo, slab_hi);
+    }
     if (dim == 2)
     {
-        if (h->nranks > 1) return fail(h, B200LS_ERR_UNSUPPORTED, "2-D grids run on one GPU");
         slab_lo = 0;
         slab_hi = 1;
     }

@@ -149,7 +149,9 @@ PetscErrorCode LinSolverB200::setMatrix(const Mat &A)
     bool recognised = false;
     if (haveGrid)
     {
-        const int64_t nslow = (gdim == 3) ? gn[2] : 1;
+        // slabs along the slowest axis: z in 3-D; y in 2-D when several ranks share the grid
+        const int64_t nslow = (gdim == 3) ? gn[2] : (nranks > 1 ? gn[1] : 1);
+        const int64_t nfast = (gdim == 3 || nranks == 1) ? gn[0] * gn[1] : gn[0];
         int64_t lo = 0, hi = nslow;
         if (nranks > 1)
         {
@@ -165,7 +167,7 @@ PetscErrorCode LinSolverB200::setMatrix(const Mat &A)
             B200CHK(handle, b200ls_comm_disconnect(handle));
             ierr = MPI_Barrier(PETSC_COMM_WORLD); CHKERRQ(ierr);
         }
-        if ((int64_t)nloc == gn[0] * gn[1] * (hi - lo) && (int64_t)rbeg == gn[0] * gn[1] * lo)
+        if ((int64_t)nloc == nfast * (hi - lo) && (int64_t)rbeg == nfast * lo)
         {
             B200CHK(handle, b200ls_set_poisson_stencil(handle, (int)gdim, gn, gper, gdL[0].data(), gdL[1].data(),
                                                        gdim == 3 ? gdL[2].data() : nullptr, gdt, lo, hi));

@@ -106,8 +106,12 @@ class Comm:
 
     # ---- vector helpers (natural ordering <-> rank-local DMDA block) ------------------------
     def local_block(self, full: np.ndarray, n) -> np.ndarray:
-        """Rank-local part of a natural-ordering global vector for a z-slab partition."""
-        nx, ny, nz = n
+        """Rank-local part of a natural-ordering global vector for a slab partition along the slowest axis
+        (z in 3-D, y in 2-D)."""
+        if len(n) == 2:
+            nx, ny, nz = n[0], 1, n[1]
+        else:
+            nx, ny, nz = n
         lo, hi = slab_range(nz, self.rank, self.nranks)
         return np.ascontiguousarray(full.reshape(nz, ny, nx)[lo:hi].reshape(-1))
 

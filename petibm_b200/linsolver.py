@@ -168,10 +168,18 @@ class LinSolverB200(LinSolverBase):
         self._grid = grid
 
     def _slab(self, grid: Grid):
-        nslow = grid.n[2] if grid.dim == 3 else 1
-        if self._comm is not None and self._comm.nranks > 1:
+        multi = self._comm is not None and self._comm.nranks > 1
+        # slabs along the slowest axis: z in 3-D; y in 2-D when several GPUs share the grid
+        nslow = grid.n[2] if grid.dim == 3 else (grid.n[1] if multi else 1)
+        if multi:
             return slab_range(nslow, self._comm.rank, self._comm.nranks)
         return 0, nslow
+
+    def _local_size(self, grid: Grid, lo: int, hi: int) -> int:
+        multi = self._comm is not None and self._comm.nranks > 1
+        if grid.dim == 2:
+            return int(grid.n[0] * (hi - lo)) if multi else int(grid.n[0] * grid.n[1])
+        return int(grid.n[0] * grid.n[1] * (hi - lo))
 
     def setStencil(self, grid: Grid):
         """Matrix-free operator D (dt I) G straight from the grid (what setMatrix does after recognising
@@ -191,7 +199,7 @@ class LinSolverB200(LinSolverBase):
             self._h, grid.dim, n, per, w[0].ctypes.data_as(_lib._dp), w[1].ctypes.data_as(_lib._dp), dz,
             float(grid.dt), lo, hi), self._h)
         self.operator = "stencil"
-        self.nlocal = int(grid.n[0] * grid.n[1] * (hi - lo))
+        self.nlocal = self._local_size(grid, lo, hi)
         if self._comm is not None and self._comm.nranks > 1:
             self._comm.connect_solver(self)
 
@@ -203,7 +211,7 @@ class LinSolverB200(LinSolverBase):
         recognised = False
         if self._grid is not None:
             lo, hi = self._slab(self._grid)
-            if A.nrows == self._grid.n[0] * self._grid.n[1] * (hi - lo):
+            if A.nrows == self._local_size(self._grid, lo, hi):
                 self.setStencil(self._grid)
                 diff = C.c_double(0.0)
                 rc = self._L.b200ls_verify_csr(self._h, A.nrows, A.indptr.ctypes.data_as(_lib._i64p),

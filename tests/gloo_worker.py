@@ -27,6 +27,12 @@ def main():
     assert loc.size == n[0] * n[1] * (hi - lo) and loc[0] == lo * n[0] * n[1]
     back = comm.gather_blocks(loc)
     assert np.array_equal(back, full)
+    # 2-D grids are cut into y-slabs
+    full2 = np.arange(6 * 9, dtype=np.float64)
+    loc2 = comm.local_block(full2, (6, 9))
+    lo2, hi2 = slab_range(9, comm.rank, comm.nranks)
+    assert loc2.size == 6 * (hi2 - lo2) and loc2[0] == lo2 * 6
+    assert np.array_equal(comm.gather_blocks(loc2), full2)
     comm.barrier()
     import torch.distributed as dist
 

@@ -89,7 +89,8 @@ def main():
 
     comm = Comm.from_env()
     torch.cuda.set_device(comm.device)
-    cases = [((24, 20, 44), (0, 0, 0)), ((16, 12, 31), (0, 0, 1)), ((70, 9, 17), (1, 1, 0))]
+    cases = [((24, 20, 44), (0, 0, 0)), ((16, 12, 31), (0, 0, 1)), ((70, 9, 17), (1, 1, 0)),
+             ((40, 26), (0, 0)), ((33, 21), (1, 1))]   # 2-D grids: y-slabs through the (nx, 1, ny) mapping
     modes = [("p2p", "store"), ("nccl", "memcpy"), ("nccl", "store")]
     args = [a for a in sys.argv[1:] if a != "--c4"]
     if "--c4" in sys.argv:

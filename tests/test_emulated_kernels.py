@@ -193,3 +193,27 @@ def test_results_do_not_depend_on_the_thread_schedule(emu, tile):
             assert np.array_equal(h, h0) and np.array_equal(x, x0) and (its, reason) == (its0, reason0)
     finally:
         emu.emu_set_schedule(0)
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_emulated_2d_grid_on_several_ranks(emu, nranks):
+    """A 2-D grid on several GPUs is the 3-D code on (nx, 1, ny) with y-slabs (b200ls_set_poisson_stencil); the result
+    must match the 2-D oracle operator (bit-identical arithmetic: products with 1.0, additions of exact zeros)."""
+    for shape, per in (((33, 14), (0, 0)), ((20, 12), (1, 1))):
+        widths = H.make_widths(shape)
+        A = H.oracle_matrix(widths, per)                      # the 2-D reference operator
+        b, _ = H.consistent_rhs(A)
+        nit = 12
+        ref = orc.ksp_solve(A, b, pc_type="jacobi", rtol=0, atol=0, max_it=nit, const_nullspace=True)
+        n = (C.c_int64 * 3)(shape[0], 1, shape[1])
+        p = (C.c_int * 3)(per[0], 0, per[1])
+        wx = np.ascontiguousarray(widths[0]); wy = np.ones(1); wz = np.ascontiguousarray(widths[1])
+        x = np.empty_like(b)
+        hist = np.zeros(nit + 2)
+        nh, its, reason = C.c_int(0), C.c_int(0), C.c_int(0)
+        rc = emu.emu_stencil_cg_ranks(nranks, n, p, wx.ctypes.data_as(_dp), wy.ctypes.data_as(_dp), wz.ctypes.data_as(_dp),
+                                      0.01, 1, 1, 0.0, 0.0, nit, 10, 0, b.ctypes.data_as(_dp), x.ctypes.data_as(_dp),
+                                      hist.ctypes.data_as(_dp), hist.size, C.byref(nh), C.byref(its), C.byref(reason))
+        assert rc == 0 and (its.value, reason.value) == (nit, -3)
+        np.testing.assert_allclose(hist[: nh.value], ref.history, rtol=1e-10)
+        np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-9 * np.abs(ref.x).max())
