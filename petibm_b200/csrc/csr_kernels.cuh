@@ -443,9 +443,4 @@ __global__ void __launch_bounds__(256) k_bcgs_tail(int64_t n, const double *p, d
         x[i] = __dadd_rn(x[i], __dmul_rn(alpha, p[i]));
 }
 
-__global__ void __launch_bounds__(256) k_zero(int64_t n, double *a)
-{
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] = 0.0;
-}
-
 }  // namespace b200

@@ -1004,10 +1004,6 @@ __global__ void __launch_bounds__(256) k_xtail(GridDev g, double *x, const doubl
             x[base + i] = __dadd_rn(x[base + i], __dmul_rn(a, p[base + i]));
     }
 }
-__global__ void k_clear_pending(DevState *st)
-{
-    if (threadIdx.x == 0 && blockIdx.x == 0) st->pending = 0;
-}
 
 // ------------------------------------------------------------------------------------------
 // layout helpers: compact (i fastest, no padding, no ghosts) <-> solver layout

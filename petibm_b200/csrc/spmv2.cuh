@@ -40,16 +40,6 @@ struct Spmv2Smem
     static size_t total(int kz_chunk) { return total_fixed + 16u * (size_t)(kz_chunk + 2); }
 };
 
-// Everything a plane step needs, held in registers across the (manually unrolled) plane loop.
-template <bool JACOBI, bool APPLY>
-struct Spmv2Regs
-{
-    double2 p[3];        // search direction on planes kk-2, kk-1, kk (rotating, static index)
-    double czm0, czm1;   // minus-face z coefficients of the plane being finished
-    double dz_nx, gz_nx; // 1-D coefficients of the next plane to finish
-    double acc;
-};
-
 template <int TXT, int TYT, int S, int MINB, bool JACOBI, bool APPLY, bool PER>
 __global__ void __launch_bounds__(TXT *TYT, MINB)
     k_spmv2(GridDev g, VecSet v, int kz_chunk, ReduceWs ws, CommDev cm, DevState *st, SolveConsts kc, double *hist,
