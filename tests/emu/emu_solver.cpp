@@ -9,6 +9,7 @@
 
 #include "spmv2.cuh"
 #include "spmv3.cuh"
+#include "csr_kernels.cuh"
 
 using namespace b200;
 
@@ -375,6 +376,83 @@ EMU_API int emu_stencil_cg_ranks(int nranks, const int64_t *n, const int *per, c
     *reason = R[0].st.reason;
     memcpy(hist, R[0].hist.data(), sizeof(double) * (size_t)std::min(R[0].st.nhist, hist_cap));
     return R[0].st.done ? 0 : 1;
+}
+
+// ---- general CSR operator: CG (no / constant / one explicit null-space vector) and BiCGStab, mirroring
+// csr_solver.inc (csr_cg / csr_bcgs)
+EMU_API int emu_csr_solve(int64_t n, const int64_t *rowptr, const int32_t *col, const double *val, int bcgs, int jacobi,
+                          int has_const, const double *nullvec, double rtol, double atol, int max_it, const double *b,
+                          double *x_out, double *hist, int hist_cap, int *nhist, int *its, int *reason)
+{
+    Ws W;
+    CsrDev A{n, rowptr, col, val};
+    std::vector<double> dinv((size_t)n, 1.0);
+    for (int64_t i = 0; i < n; ++i)
+    {
+        double d = 0.0;
+        for (int64_t q = rowptr[i]; q < rowptr[i + 1]; ++q)
+            if (col[q] == i) d = val[q];
+        dinv[(size_t)i] = d != 0.0 ? 1.0 / d : 1.0;
+    }
+    SolveConsts kc{};
+    kc.rtol = rtol; kc.atol = atol; kc.divtol = 1e4; kc.nglobal = (double)n;
+    kc.max_it = max_it; kc.norm_type = 1; kc.has_const = has_const; kc.hist_cap = hist_cap;
+    DevState st{};
+    emu::launch(dim3(1), dim3(32), 0, [&] { k_state_reset(&st); });
+    std::vector<double> r((size_t)n), p0((size_t)n, 0.0), p1((size_t)n, 0.0), w((size_t)n, 0.0), x((size_t)n, 0.0);
+    const int blocks = 3;
+    const double *dv = jacobi ? dinv.data() : nullptr;
+    if (bcgs)
+    {
+        std::vector<double> rp((size_t)n), vv((size_t)n), s((size_t)n), t((size_t)n);
+        if (jacobi) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_init<true>(n, b, dv, r.data(), rp.data(), p0.data(), vv.data(), W.ws, &st, kc, hist); });
+        else emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_init<false>(n, b, dv, r.data(), rp.data(), p0.data(), vv.data(), W.ws, &st, kc, hist); });
+        for (int it = 0; it < max_it + 2 && !st.done; ++it)
+        {
+            emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_p(n, r.data(), vv.data(), p0.data(), &st); });
+            if (jacobi) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_spmv1<true>(A, p0.data(), dv, rp.data(), vv.data(), W.ws, &st, kc, hist); });
+            else emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_spmv1<false>(A, p0.data(), dv, rp.data(), vv.data(), W.ws, &st, kc, hist); });
+            if (jacobi) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_spmv2<true>(A, r.data(), vv.data(), dv, s.data(), t.data(), W.ws, &st, kc, hist); });
+            else emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_spmv2<false>(A, r.data(), vv.data(), dv, s.data(), t.data(), W.ws, &st, kc, hist); });
+            emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_upd(n, p0.data(), s.data(), t.data(), rp.data(), x.data(), r.data(), W.ws, &st, kc, hist); });
+        }
+        emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_tail(n, p0.data(), x.data(), &st); });
+    }
+    else
+    {
+        memcpy(r.data(), b, sizeof(double) * (size_t)n);
+        const int nm = nullvec ? 2 : (has_const ? 1 : 0);
+        auto upd = [&](bool init, int kind) {
+#define EMU_CU(JAC, NM, INIT) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_csr_cg_update<JAC, NM, INIT>(n, r.data(), w.data(), dv, nullvec, kind, W.ws, &st, kc, hist); })
+            if (jacobi) { if (nm == 2) { if (init) EMU_CU(true, 2, true); else EMU_CU(true, 2, false); } else if (nm == 1) { if (init) EMU_CU(true, 1, true); else EMU_CU(true, 1, false); } else { if (init) EMU_CU(true, 0, true); else EMU_CU(true, 0, false); } }
+            else { if (nm == 2) { if (init) EMU_CU(false, 2, true); else EMU_CU(false, 2, false); } else if (nm == 1) { if (init) EMU_CU(false, 1, true); else EMU_CU(false, 1, false); } else { if (init) EMU_CU(false, 0, true); else EMU_CU(false, 0, false); } }
+#undef EMU_CU
+        };
+        if (nm == 2) upd(true, FIN_CSR_INIT);
+        else
+        {
+            if (nm == 1) upd(true, FIN_INIT_CENTRE);
+            upd(true, FIN_INIT);
+        }
+        double *pp[2] = {p0.data(), p1.data()};
+        for (int it = 0; it < max_it + 2 && !st.done; ++it)
+        {
+            CsrVecs v{r.data(), pp[it & 1], pp[(it & 1) ^ 1], w.data(), x.data(), dv, nullvec};
+#define EMU_CS(JAC, NM) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_csr_cg_spmv<JAC, NM>(A, v, W.ws, &st, kc, hist); })
+            if (jacobi) { if (nm == 2) EMU_CS(true, 2); else if (nm == 1) EMU_CS(true, 1); else EMU_CS(true, 0); }
+            else { if (nm == 2) EMU_CS(false, 2); else if (nm == 1) EMU_CS(false, 1); else EMU_CS(false, 0); }
+#undef EMU_CS
+            upd(false, nm == 2 ? FIN_CSR_UPDATE : FIN_UPDATE);
+        }
+        GridDev g1{};
+        g1.nx = (int)n; g1.ny = 1; g1.nzl = 1; g1.px = (int)n; g1.plane = 0;
+        emu::launch(dim3(1), dim3(256), 0, [&] { k_xtail(g1, x.data(), p0.data(), p1.data(), &st); });
+    }
+    memcpy(x_out, x.data(), sizeof(double) * (size_t)n);
+    *nhist = st.nhist;
+    *its = st.its;
+    *reason = st.reason;
+    return st.done ? 0 : 1;
 }
 
 }  // extern "C"

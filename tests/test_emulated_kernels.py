@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
 LIB = os.path.join(EMU, "libb200emu.so")
 SRC = [os.path.join(EMU, f) for f in ("emu_solver.cpp", "cuda_emu.h")] + \
-      [os.path.join(ROOT, "petibm_b200", "csrc", f) for f in ("kernels.cuh", "spmv2.cuh", "spmv3.cuh", "hw.cuh")]
+      [os.path.join(ROOT, "petibm_b200", "csrc", f) for f in ("kernels.cuh", "spmv2.cuh", "spmv3.cuh", "hw.cuh", "csr_kernels.cuh")]
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -42,6 +42,8 @@ def emu():
     L.emu_stencil_cg_ranks.argtypes = [C.c_int, C.POINTER(C.c_int64), _ip, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_double,
                                        C.c_double, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _ip, _ip, _ip]
     L.emu_set_schedule.argtypes = [C.c_uint64]
+    L.emu_csr_solve.argtypes = [C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32), _dp, C.c_int, C.c_int, C.c_int, _dp,
+                                C.c_double, C.c_double, C.c_int, _dp, _dp, _dp, C.c_int, _ip, _ip, _ip]
     return L
 
 
@@ -217,3 +219,55 @@ def test_emulated_2d_grid_on_several_ranks(emu, nranks):
         assert rc == 0 and (its.value, reason.value) == (nit, -3)
         np.testing.assert_allclose(hist[: nh.value], ref.history, rtol=1e-10)
         np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-9 * np.abs(ref.x).max())
+
+
+def _csr_solve(L, M, b, bcgs=False, pc="none", has_const=False, nullvec=None, rtol=0.0, atol=0.0, max_it=20):
+    M = M.tocsr(); M.sort_indices()
+    rp = np.ascontiguousarray(M.indptr, dtype=np.int64); col = np.ascontiguousarray(M.indices, dtype=np.int32)
+    val = np.ascontiguousarray(M.data, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.empty_like(b); hist = np.zeros(max_it + 2)
+    nh, its, reason = C.c_int(0), C.c_int(0), C.c_int(0)
+    nvp = None if nullvec is None else np.ascontiguousarray(nullvec, dtype=np.float64).ctypes.data_as(_dp)
+    rc = L.emu_csr_solve(M.shape[0], rp.ctypes.data_as(C.POINTER(C.c_int64)), col.ctypes.data_as(C.POINTER(C.c_int32)),
+                         val.ctypes.data_as(_dp), int(bcgs), int(pc == "jacobi"), int(has_const), nvp, rtol, atol, max_it,
+                         b.ctypes.data_as(_dp), x.ctypes.data_as(_dp), hist.ctypes.data_as(_dp), hist.size, C.byref(nh),
+                         C.byref(its), C.byref(reason))
+    assert rc == 0
+    return x, hist[: nh.value].copy(), its.value, reason.value
+
+
+@pytest.mark.parametrize("pc", ["none", "jacobi"])
+def test_emulated_csr_paths(emu, pc):
+    """The assembled-operator kernels (csr_kernels.cuh) on the emulation: BiCGStab on a velocity system, CG with
+    the constant null space and with one explicit null-space vector."""
+    import scipy.sparse as sp
+
+    # velocity system, BiCGStab
+    A, _ = H.velocity_system(H.make_widths((8, 7, 6)), (0, 0, 0), dt=0.5, nu=1.0)
+    Ao = orc.Csr.from_arrays(A.shape[0], A.shape[1], A.indptr, A.indices, A.data)
+    b = np.random.default_rng(2).standard_normal(A.shape[0])
+    ref = orc.ksp_solve(Ao, b, ksp_type="bcgs", pc_type=pc, rtol=0.0, atol=1e-8, max_it=300)
+    x, hist, its, reason = _csr_solve(emu, A, b, bcgs=True, pc=pc, atol=1e-8, max_it=300)
+    assert reason == ref.reason == 3 and abs(its - ref.its) <= 2
+    np.testing.assert_allclose(hist[:8], ref.history[:8], rtol=1e-9)
+    np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-6 * np.abs(ref.x).max())
+    # pressure operator as CSR with the constant null space
+    P = H.oracle_matrix(H.make_widths((9, 8, 5)), (0, 1, 0))
+    bp, _ = H.consistent_rhs(P)
+    refp = orc.ksp_solve(P, bp, pc_type=pc, rtol=0, atol=0, max_it=15, const_nullspace=True)
+    x, hist, its, reason = _csr_solve(emu, P.to_scipy(), bp, pc=pc, has_const=True, max_it=15)
+    assert (its, reason) == (15, -3)
+    np.testing.assert_allclose(hist, refp.history, rtol=1e-10)
+    # IBPM-style modified Poisson with an explicit null-space vector
+    G = orc.assemble_gradient(H.make_widths((10, 9)), [0, 0, 0]).to_scipy()
+    R = sp.random(G.shape[0], 7, density=0.05, random_state=4, format="csr")
+    K = sp.hstack([G, -R]).tocsr()
+    M = (-(K.T @ K) * 0.01).tocsr(); M.sort_indices()
+    nv = np.zeros(M.shape[0]); nv[: G.shape[1]] = 1.0 / np.sqrt(G.shape[1])
+    Mo = orc.Csr.from_arrays(M.shape[0], M.shape[1], M.indptr, M.indices, M.data)
+    xs = np.random.default_rng(5).standard_normal(M.shape[0]); xs -= (xs @ nv) * nv
+    bm = M @ xs
+    refm = orc.ksp_solve(Mo, bm, pc_type=pc, rtol=0, atol=0, max_it=15, nullvecs=nv)
+    x, hist, its, reason = _csr_solve(emu, M, bm, pc=pc, nullvec=nv, max_it=15)
+    np.testing.assert_allclose(hist, refm.history, rtol=1e-10)
+    np.testing.assert_allclose(x, refm.x, rtol=0, atol=1e-9 * np.abs(refm.x).max())
