@@ -28,6 +28,9 @@
  *   b200ls_axis_from_subdomains           parser::parseSubDomains/parseOneSubDomain
  *                                         src/parser/parser.cpp:297-356, misc::stretchGrid
  *                                         include/petibm/misc.h:148-163
+ *   b200ls_repart_*                       the DMDA ownership the Vecs/Mat rows arrive in
+ *                                         src/mesh/cartesianmesh.cpp:500-538,709-721 (DMDACreate3d,
+ *                                         AOApplicationToPetsc) -> slab partition of the solver
  *   b200ls_comm_*                         PETSC_COMM_WORLD (MPI) inside KSP: VecScatter halos
  *                                         of MatMult_MPIAIJ and MPI_Allreduce of VecDot/VecNorm
  */
@@ -139,6 +142,39 @@ int b200ls_comm_disconnect(b200ls_solver *h);
 int b200ls_nccl_unique_id(void *id128);
 int b200ls_nccl_init(b200ls_solver *h, const void *id128);
 
+/* ---- DMDA box partition <-> slab partition (host only, no device needed) ----
+ * Inside PetIBM the pressure grid is distributed the way DMDACreate{2,3}d(PETSC_DECIDE) chose
+ * (src/mesh/cartesianmesh.cpp:500-538): an m x n x p process grid, rank = px + m*(py + n*pz), one box per rank
+ * numbered contiguously i-fastest (cartesianmesh.cpp:709-721), first (M mod m) ranks one cell longer per axis.
+ * The device solver works on slabs along the slowest axis.  A b200ls_repart plans the exchange between the two
+ * (the VecScatter PETSc would do); the caller moves the bytes with ONE all-to-all per direction on its host
+ * transport (MPI_Alltoallv in the PetIBM shim).  box -> slab: send box_counts[s] doubles from offset box_displs[s]
+ * of the local box-ordered vector to rank s (no packing: whole z-planes of the box), receive slab_counts[q] from
+ * rank q at slab_displs[q] of an exchange buffer, then b200ls_repart_unpack_slab.  slab -> box: b200ls_repart_pack_slab,
+ * send slab_counts/displs, receive straight into the box-ordered vector at box_counts/displs. */
+typedef struct b200ls_repart b200ls_repart;
+int b200ls_dmda_split(int64_t M, int m, int64_t *starts /* m + 1 */);
+/* n: global cells per axis (2-D: n[2] ignored); procs: (m, n, p) of the DMDA (2-D: procs[2] ignored). */
+int b200ls_repart_create(b200ls_repart **out, int dim, const int64_t n[3], const int procs[3], int rank);
+int b200ls_repart_destroy(b200ls_repart *p);
+/* box_lo/box_hi are reported on three axes with a 2-D grid normalised to (nx, 1, ny); identity != 0 when the box
+ * partition already is the slab partition (1 x 1 x P process grid: no exchange needed). Any pointer may be null. */
+int b200ls_repart_info(const b200ls_repart *p, int64_t box_lo[3], int64_t box_hi[3], int64_t *nbox, int64_t *slab_lo,
+                       int64_t *slab_hi, int64_t *nslab, int *identity);
+int b200ls_repart_counts(const b200ls_repart *p, int64_t *box_counts, int64_t *box_displs, int64_t *slab_counts,
+                         int64_t *slab_displs);
+int b200ls_repart_unpack_slab(const b200ls_repart *p, const double *recvbuf, double *slab);
+int b200ls_repart_pack_slab(const b200ls_repart *p, const double *slab, double *sendbuf);
+/* PETSc global indices (columns of the assembled Mat) -> natural indices; natural indices of the own rows. */
+int b200ls_repart_petsc_to_natural(const b200ls_repart *p, int64_t count, const int32_t *petsc_idx, int32_t *natural_idx);
+int b200ls_repart_box_rows(const b200ls_repart *p, int64_t *natural_rows);
+/* All process grids of nranks ranks whose boxes have exactly the local sizes the ranks report (sizes[q] = rows
+ * owned by rank q, e.g. from MatGetOwnershipRanges).  The Mat handed to setMatrix does not carry its DMDA, so the
+ * shim tries these candidates against the matrix entries (b200ls_verify_csr_rows) and keeps the one that matches.
+ * Writes min(cap, *found) triples to procs_out. */
+int b200ls_repart_candidates(int dim, const int64_t n[3], int nranks, const int64_t *sizes, int *procs_out, int cap,
+                             int *found);
+
 /* ---- operator ----
  * Matrix-free separable pressure-Poisson operator DBNG = D (dt I) G of a stretched Cartesian
  * staggered grid:  dx,dy,dz are the GLOBAL pressure-cell widths
@@ -155,6 +191,15 @@ int b200ls_set_poisson_stencil(b200ls_solver *h, int dim, const int64_t n[3], co
  * rows, columns are global natural indices.  Returns B200LS_ERR_MISMATCH on any difference. */
 int b200ls_verify_csr(b200ls_solver *h, int64_t nrows, const int64_t *rowptr, const int32_t *col,
                       const double *val, double *max_abs_diff);
+
+/* The same for rows given in ANY order (rows of a DMDA box, see b200ls_repart_*): natural_rows[r] is the natural
+ * index i + nx*(j + ny*k) of local row r, columns are natural indices.  Off-diagonal entries must match bitwise.
+ * diag_ulps > 0 lets the diagonal differ by that many units in the last place: on several ranks PETSc's
+ * MatMatMult (navierstokes.cpp:351-356) accumulates the off-process terms of a diagonal entry after the local
+ * ones, so the rounding of rows on a partition boundary depends on the partition -- PETSc's own result is not
+ * bitwise reproducible across process counts there.  0 = bitwise (what b200ls_verify_csr does). */
+int b200ls_verify_csr_rows(b200ls_solver *h, int64_t nrows, const int64_t *natural_rows, const int64_t *rowptr,
+                           const int32_t *col, const double *val, int diag_ulps, double *max_abs_diff);
 
 /* General assembled operator (any square CSR, single GPU): used for operators the separable
  * stencil cannot express (IBPM modified Poisson, BN order > 1, the velocity system A). */

@@ -60,8 +60,19 @@ SIGNATURES = {
     "b200ls_comm_disconnect": (C.c_int, [_vp]),
     "b200ls_nccl_unique_id": (C.c_int, [_vp]),
     "b200ls_nccl_init": (C.c_int, [_vp, _vp]),
+    "b200ls_dmda_split": (C.c_int, [C.c_int64, C.c_int, _i64p]),
+    "b200ls_repart_create": (C.c_int, [C.POINTER(_vp), C.c_int, _i64p, _ip, C.c_int]),
+    "b200ls_repart_destroy": (C.c_int, [_vp]),
+    "b200ls_repart_info": (C.c_int, [_vp, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p, _ip]),
+    "b200ls_repart_counts": (C.c_int, [_vp, _i64p, _i64p, _i64p, _i64p]),
+    "b200ls_repart_unpack_slab": (C.c_int, [_vp, _dp, _dp]),
+    "b200ls_repart_pack_slab": (C.c_int, [_vp, _dp, _dp]),
+    "b200ls_repart_petsc_to_natural": (C.c_int, [_vp, C.c_int64, _i32p, _i32p]),
+    "b200ls_repart_box_rows": (C.c_int, [_vp, _i64p]),
+    "b200ls_repart_candidates": (C.c_int, [C.c_int, _i64p, C.c_int, _i64p, _ip, C.c_int, _ip]),
     "b200ls_set_poisson_stencil": (C.c_int, [_vp, C.c_int, _i64p, _ip, _dp, _dp, _dp, C.c_double, C.c_int64, C.c_int64]),
     "b200ls_verify_csr": (C.c_int, [_vp, C.c_int64, _i64p, _i32p, _dp, _dp]),
+    "b200ls_verify_csr_rows": (C.c_int, [_vp, C.c_int64, _i64p, _i64p, _i32p, _dp, C.c_int, _dp]),
     "b200ls_set_csr": (C.c_int, [_vp, C.c_int64, _i64p, _i32p, _dp]),
     "b200ls_set_nullspace": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
     "b200ls_apply": (C.c_int, [_vp, _vp, _vp]),

@@ -42,6 +42,8 @@ LinSolverB200::~LinSolverB200()
     PetscBool finalized;
     PetscErrorCode ierr = PetscFinalized(&finalized);
     if (ierr || finalized) return;  // same guard as linsolverksp.cpp:30-31
+    if (plan) b200ls_repart_destroy(plan);
+    plan = nullptr;
     if (handle) b200ls_destroy(handle);
     handle = nullptr;
 }
@@ -50,6 +52,8 @@ PetscErrorCode LinSolverB200::destroy()
 {
     PetscErrorCode ierr;
     PetscFunctionBeginUser;
+    if (plan) b200ls_repart_destroy(plan);
+    plan = nullptr;
     if (handle) b200ls_destroy(handle);
     handle = nullptr;
     ierr = LinSolverBase::destroy(); CHKERRQ(ierr);
@@ -147,39 +151,70 @@ PetscErrorCode LinSolverB200::setMatrix(const Mat &A)
 
     // 1. try the matrix-free separable operator, verified entry by entry against A
     bool recognised = false;
-    if (haveGrid)
+    if (plan) b200ls_repart_destroy(plan);
+    plan = nullptr;
+    if (haveGrid && nranks == 1)
     {
-        // slabs along the slowest axis: z in 3-D; y in 2-D when several ranks share the grid
-        const int64_t nslow = (gdim == 3) ? gn[2] : (nranks > 1 ? gn[1] : 1);
-        const int64_t nfast = (gdim == 3 || nranks == 1) ? gn[0] * gn[1] : gn[0];
-        int64_t lo = 0, hi = nslow;
-        if (nranks > 1)
-        {
-            // z-slabs in natural ordering coincide with PETSc's DMDA ordering only for a 1 x 1 x P process
-            // grid (run with -da_processors_x 1 -da_processors_y 1); the range check below catches the rest
-            const int64_t base = nslow / nranks, rem = nslow % nranks;
-            lo = rank * base + (rank < rem ? rank : rem);
-            hi = lo + base + (rank < rem ? 1 : 0);
-        }
-        if (nranks > 1)
-        {
-            // a second setMatrix replaces the exchange arena: drop the peer mappings everywhere first
-            B200CHK(handle, b200ls_comm_disconnect(handle));
-            ierr = MPI_Barrier(PETSC_COMM_WORLD); CHKERRQ(ierr);
-        }
-        if ((int64_t)nloc == nfast * (hi - lo) && (int64_t)rbeg == nfast * lo)
+        const int64_t nslow = (gdim == 3) ? gn[2] : 1;   // one GPU owns the whole grid (2-D: a single "plane")
+        if ((int64_t)nloc == gn[0] * gn[1] * nslow)
         {
             B200CHK(handle, b200ls_set_poisson_stencil(handle, (int)gdim, gn, gper, gdL[0].data(), gdL[1].data(),
-                                                       gdim == 3 ? gdL[2].data() : nullptr, gdt, lo, hi));
+                                                       gdim == 3 ? gdL[2].data() : nullptr, gdt, 0, nslow));
             double diff = 0.0;
             const int rc = b200ls_verify_csr(handle, nloc, rowptr.data(), col.data(), val.data(), &diff);
             if (rc == B200LS_OK) recognised = true;
             else if (rc != B200LS_ERR_MISMATCH) B200CHK(handle, rc);
         }
-        // every rank must agree, otherwise the transports would be mismatched
-        PetscMPIInt mine = recognised ? 1 : 0, all = 0;
-        ierr = MPI_Allreduce(&mine, &all, 1, MPI_INT, MPI_MIN, PETSC_COMM_WORLD); CHKERRQ(ierr);
-        recognised = (all == 1);
+    }
+    else if (haveGrid)
+    {
+        // Several ranks.  The rows are this rank's DMDA box and the columns PETSc global indices
+        // (cartesianmesh.cpp:500-538, 709-721); the device solver works on slabs along the slowest axis (z in 3-D,
+        // y in 2-D).  The Mat does not carry its DMDA, so every process grid that reproduces the ranks' local sizes
+        // is tried against the matrix entries; the one that verifies fixes the box <-> slab exchange of solve().
+        std::vector<int64_t> sizes((size_t)nranks, 0);
+        const int64_t mine = (int64_t)nloc;
+        ierr = MPI_Allgather(&mine, (int)sizeof(int64_t), MPI_BYTE, sizes.data(), (int)sizeof(int64_t), MPI_BYTE,
+                             PETSC_COMM_WORLD); CHKERRQ(ierr);
+        std::vector<int> cands(3 * 64, 1);
+        int found = 0;
+        B200CHK(handle, b200ls_repart_candidates((int)gdim, gn, nranks, sizes.data(), cands.data(), 64, &found));
+        if (found > 64) found = 64;
+        const int64_t nslow = (gdim == 3) ? gn[2] : gn[1];
+        if (found > 0 && nslow >= nranks)
+        {
+            // a second setMatrix replaces the exchange arena: drop the peer mappings everywhere first
+            B200CHK(handle, b200ls_comm_disconnect(handle));
+            ierr = MPI_Barrier(PETSC_COMM_WORLD); CHKERRQ(ierr);
+            const int64_t base = nslow / nranks, rem = nslow % nranks;
+            const int64_t lo = rank * base + (rank < rem ? rank : rem), hi = lo + base + (rank < rem ? 1 : 0);
+            B200CHK(handle, b200ls_set_poisson_stencil(handle, (int)gdim, gn, gper, gdL[0].data(), gdL[1].data(),
+                                                       gdim == 3 ? gdL[2].data() : nullptr, gdt, lo, hi));
+            std::vector<int64_t> natRows((size_t)nloc);
+            std::vector<int32_t> natCols(col.size());
+            for (int c = 0; c < found && !recognised; ++c)
+            {
+                b200ls_repart *cand = nullptr;
+                B200CHK(handle, b200ls_repart_create(&cand, (int)gdim, gn, &cands[(size_t)3 * c], rank));
+                int rc = b200ls_repart_box_rows(cand, natRows.data());
+                if (rc == B200LS_OK) rc = b200ls_repart_petsc_to_natural(cand, (int64_t)col.size(), col.data(), natCols.data());
+                double diff = 0.0;
+                // diagonal within 4 ulp: PETSc's parallel MatMatMult adds the off-process terms of a diagonal entry
+                // after the local ones, so rows on a partition boundary round differently per partition (b200ls.h)
+                if (rc == B200LS_OK)
+                    rc = b200ls_verify_csr_rows(handle, nloc, natRows.data(), rowptr.data(), natCols.data(), val.data(), 4, &diff);
+                // every rank must agree, otherwise the exchange plans would be mismatched
+                PetscMPIInt ok = (rc == B200LS_OK) ? 1 : 0, all = 0;
+                ierr = MPI_Allreduce(&ok, &all, 1, MPI_INT, MPI_MIN, PETSC_COMM_WORLD); CHKERRQ(ierr);
+                if (all == 1)
+                {
+                    plan = cand;
+                    recognised = true;
+                }
+                else
+                    b200ls_repart_destroy(cand);
+            }
+        }
     }
     if (recognised)
     {
@@ -191,6 +226,30 @@ PetscErrorCode LinSolverB200::setMatrix(const Mat &A)
             B200CHK(handle, b200ls_comm_export(handle, mine.data()));
             ierr = MPI_Allgather(mine.data(), 64, MPI_BYTE, all.data(), 64, MPI_BYTE, PETSC_COMM_WORLD); CHKERRQ(ierr);
             B200CHK(handle, b200ls_comm_connect(handle, all.data(), nranks));
+            // box <-> slab exchange of solve(): counts/displacements for MPI_Alltoallv and the slab-side buffers
+            int identity = 1;
+            int64_t nslab = 0;
+            B200CHK(handle, b200ls_repart_info(plan, nullptr, nullptr, nullptr, nullptr, nullptr, &nslab, &identity));
+            planIdentity = identity != 0;
+            std::vector<int64_t> c64[4];
+            for (auto &v : c64) v.assign((size_t)nranks, 0);
+            B200CHK(handle, b200ls_repart_counts(plan, c64[0].data(), c64[1].data(), c64[2].data(), c64[3].data()));
+            for (int q = 0; q < 4; ++q)
+            {
+                xcounts[q].assign((size_t)nranks, 0);
+                for (int r = 0; r < nranks; ++r)
+                {
+                    if (c64[q][(size_t)r] > 2147483647LL)
+                        SETERRQ(PETSC_COMM_WORLD, PETSC_ERR_SUP, "B200 linear solver: exchange block exceeds the MPI count range.");
+                    xcounts[q][(size_t)r] = (PetscMPIInt)c64[q][(size_t)r];
+                }
+            }
+            if (!planIdentity)
+            {
+                xbuf.assign((size_t)nslab, 0.0);
+                bslab.assign((size_t)nslab, 0.0);
+                xslab.assign((size_t)nslab, 0.0);
+            }
         }
     }
     else
@@ -239,7 +298,24 @@ PetscErrorCode LinSolverB200::solve(Vec &x, Vec &b)
     PetscScalar *xarr;
     ierr = VecGetArrayRead(b, &barr); CHKERRQ(ierr);
     ierr = VecGetArray(x, &xarr); CHKERRQ(ierr);
-    const int rc = b200ls_solve(handle, barr, xarr);
+    int rc;
+    if (plan && !planIdentity)
+    {
+        // DMDA boxes -> slabs, solve, slabs -> boxes: one MPI_Alltoallv per direction (what VecScatter does inside
+        // PETSc's MatMult); the box side needs no packing (b200ls.h, b200ls_repart_*)
+        ierr = MPI_Alltoallv(barr, xcounts[0].data(), xcounts[1].data(), MPI_DOUBLE, xbuf.data(), xcounts[2].data(),
+                             xcounts[3].data(), MPI_DOUBLE, PETSC_COMM_WORLD); CHKERRQ(ierr);
+        B200CHK(handle, b200ls_repart_unpack_slab(plan, xbuf.data(), bslab.data()));
+        rc = b200ls_solve(handle, bslab.data(), xslab.data());
+        if (rc == B200LS_OK || rc == B200LS_ERR_DIVERGED)
+        {
+            B200CHK(handle, b200ls_repart_pack_slab(plan, xslab.data(), xbuf.data()));
+            ierr = MPI_Alltoallv(xbuf.data(), xcounts[2].data(), xcounts[3].data(), MPI_DOUBLE, xarr, xcounts[0].data(),
+                                 xcounts[1].data(), MPI_DOUBLE, PETSC_COMM_WORLD); CHKERRQ(ierr);
+        }
+    }
+    else
+        rc = b200ls_solve(handle, barr, xarr);
     ierr = VecRestoreArray(x, &xarr); CHKERRQ(ierr);
     ierr = VecRestoreArrayRead(b, &barr); CHKERRQ(ierr);
     if (rc == B200LS_ERR_DIVERGED)

@@ -66,6 +66,11 @@ protected:
     double gdt = 0.0;
     PetscMPIInt rank = 0, nranks = 1;
     std::string opKind = "none";
+    // several ranks: exchange between the DMDA boxes the Vecs arrive in and the solver's slabs
+    b200ls_repart *plan = nullptr;
+    bool planIdentity = true;               // 1 x 1 x P process grid: the boxes are the slabs
+    std::vector<PetscMPIInt> xcounts[4];    // box counts / displs, slab counts / displs (MPI_Alltoallv)
+    std::vector<double> xbuf, bslab, xslab; // slab-side exchange buffer and slab-ordered b / x
 };  // LinSolverB200
 
 }  // end of namespace linsolver

@@ -1,4 +1,5 @@
-"""Multi-GPU wiring: one process per GPU, z-slab partition of the DMDA pressure grid.
+"""Multi-GPU wiring: one process per GPU, slab partition of the DMDA pressure grid (z-slabs in 3-D, y-slabs in
+2-D); vectors that arrive in the box partition PETSc's DMDA chose are re-partitioned on the host (Repart).
 
 torch.distributed is the host transport only (what MPI is inside PetIBM): it all-gathers the 64-byte
 CUDA IPC handles of the solvers' exchange arenas and broadcasts the NCCL unique id.  The data path
@@ -118,3 +119,98 @@ class Comm:
     def gather_blocks(self, local: np.ndarray) -> np.ndarray:
         parts = self.allgather_bytes(np.ascontiguousarray(local, dtype=np.float64).tobytes())
         return np.concatenate([np.frombuffer(p, dtype=np.float64) for p in parts])
+
+
+class Repart:
+    """DMDA box partition <-> slab partition (b200ls_repart_* of the C ABI; reference: the DMDA ownership of
+    src/mesh/cartesianmesh.cpp:500-538 and the PETSc ordering of :709-721).  Index planning happens in libb200ls.so;
+    this class only carries the plan of ONE rank and moves bytes with the host transport."""
+
+    def __init__(self, dim: int, n, procs, rank: int):
+        self._L = _lib.lib()
+        self._p = C.c_void_p()
+        n3 = (C.c_int64 * 3)(*(list(n) + [1] * (3 - len(n))))
+        p3 = (C.c_int * 3)(*(list(procs) + [1] * (3 - len(procs))))
+        _lib.check(self._L.b200ls_repart_create(C.byref(self._p), int(dim), n3, p3, int(rank)))
+        self.dim, self.rank = int(dim), int(rank)
+        self.procs = tuple(int(v) for v in list(procs)[:dim]) + (1,) * (3 - dim)
+        self.nranks = int(np.prod(self.procs))
+        lo, hi = (C.c_int64 * 3)(), (C.c_int64 * 3)()
+        nbox, slo, shi, nslab, ident = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
+        _lib.check(self._L.b200ls_repart_info(self._p, lo, hi, C.byref(nbox), C.byref(slo), C.byref(shi), C.byref(nslab),
+                                              C.byref(ident)))
+        self.box_lo, self.box_hi = tuple(lo), tuple(hi)
+        self.nbox, self.nslab = nbox.value, nslab.value
+        self.slab = (slo.value, shi.value)
+        self.identity = bool(ident.value)
+        arr = [np.zeros(self.nranks, dtype=np.int64) for _ in range(4)]
+        _lib.check(self._L.b200ls_repart_counts(self._p, *[a.ctypes.data_as(_lib._i64p) for a in arr]))
+        self.box_counts, self.box_displs, self.slab_counts, self.slab_displs = arr
+
+    def __del__(self):
+        if getattr(self, "_p", None) is not None and self._p:
+            self._L.b200ls_repart_destroy(self._p)
+            self._p = C.c_void_p()
+
+    # ---- index maps
+    def box_rows(self) -> np.ndarray:
+        out = np.empty(self.nbox, dtype=np.int64)
+        _lib.check(self._L.b200ls_repart_box_rows(self._p, out.ctypes.data_as(_lib._i64p)))
+        return out
+
+    def petsc_to_natural(self, idx) -> np.ndarray:
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        out = np.empty_like(idx)
+        _lib.check(self._L.b200ls_repart_petsc_to_natural(self._p, idx.size, idx.ctypes.data_as(_lib._i32p),
+                                                          out.ctypes.data_as(_lib._i32p)))
+        return out
+
+    @staticmethod
+    def candidates(dim: int, n, sizes) -> list:
+        """Process grids whose boxes have exactly the per-rank sizes `sizes` (the Mat does not carry its DMDA)."""
+        L = _lib.lib()
+        n3 = (C.c_int64 * 3)(*(list(n) + [1] * (3 - len(n))))
+        sz = np.ascontiguousarray(sizes, dtype=np.int64)
+        out = np.zeros(3 * 64, dtype=np.int32)
+        found = C.c_int(0)
+        _lib.check(L.b200ls_repart_candidates(int(dim), n3, int(sz.size), sz.ctypes.data_as(_lib._i64p),
+                                              out.ctypes.data_as(_lib._ip), 64, C.byref(found)))
+        return [tuple(int(v) for v in out[3 * c: 3 * c + 3]) for c in range(min(found.value, 64))]
+
+    # ---- local halves of the exchange
+    def unpack_slab(self, recvbuf: np.ndarray) -> np.ndarray:
+        recvbuf = np.ascontiguousarray(recvbuf, dtype=np.float64)
+        assert recvbuf.size == self.nslab
+        out = np.empty(self.nslab, dtype=np.float64)
+        _lib.check(self._L.b200ls_repart_unpack_slab(self._p, recvbuf.ctypes.data_as(_lib._dp), out.ctypes.data_as(_lib._dp)))
+        return out
+
+    def pack_slab(self, slab: np.ndarray) -> np.ndarray:
+        slab = np.ascontiguousarray(slab, dtype=np.float64)
+        assert slab.size == self.nslab
+        out = np.empty(self.nslab, dtype=np.float64)
+        _lib.check(self._L.b200ls_repart_pack_slab(self._p, slab.ctypes.data_as(_lib._dp), out.ctypes.data_as(_lib._dp)))
+        return out
+
+    # ---- the exchange itself: ONE all-to-all per direction on the host transport (MPI_Alltoallv in the shim)
+    def _alltoall(self, send: np.ndarray, send_counts, recv_counts, group=None) -> np.ndarray:
+        import torch
+        import torch.distributed as dist
+
+        out = torch.empty(int(np.sum(recv_counts)), dtype=torch.float64)
+        inp = torch.from_numpy(np.ascontiguousarray(send, dtype=np.float64))
+        # PetIBM's shim: MPI_Alltoallv(send, counts, displs, MPI_DOUBLE, recv, counts, displs, MPI_DOUBLE, PETSC_COMM_WORLD)
+        dist.all_to_all_single(out, inp, [int(c) for c in recv_counts], [int(c) for c in send_counts], group=group)
+        return out.numpy()
+
+    def box_to_slab(self, box: np.ndarray, group=None) -> np.ndarray:
+        """Box-ordered local vector (PETSc ordering) -> slab-ordered local vector (natural order inside the slab)."""
+        if self.nranks == 1 or self.identity:
+            return np.ascontiguousarray(box, dtype=np.float64)
+        assert box.size == self.nbox
+        return self.unpack_slab(self._alltoall(box, self.box_counts, self.slab_counts, group))
+
+    def slab_to_box(self, slab: np.ndarray, group=None) -> np.ndarray:
+        if self.nranks == 1 or self.identity:
+            return np.ascontiguousarray(slab, dtype=np.float64)
+        return self._alltoall(self.pack_slab(slab), self.slab_counts, self.box_counts, group)

@@ -20,8 +20,9 @@ from .mesh import Grid, slab_range
 
 
 class Mat:
-    """What ``setMatrix`` receives: the rank-local rows of an assembled AIJ matrix (CSR, global column
-    indices in natural/DMDA ordering) plus the null space the application attached with
+    """What ``setMatrix`` receives: the rank-local rows of an assembled AIJ matrix (CSR; global column
+    indices in the PETSc ordering of the DMDA, which is the natural ordering on one rank and for a 1 x 1 x P
+    process grid) plus the null space the application attached with
     ``MatSetNullSpace`` (navierstokes.cpp:404-413, ibpm.cpp:251-267)."""
 
     def __init__(self, indptr, indices, data, ncols=None):
@@ -104,6 +105,8 @@ class LinSolverB200(LinSolverBase):
         self._node = node
         self._comm = comm
         self._grid = None
+        self._procs = None     # DMDA process grid, if the caller knows it (setProcessGrid)
+        self._repart = None    # box <-> slab exchange plan when the vectors arrive as DMDA boxes
         self.operator = None   # "stencil" | "csr" after setMatrix
         if device is None:
             device = comm.device if comm is not None else 0
@@ -203,13 +206,56 @@ class LinSolverB200(LinSolverBase):
         if self._comm is not None and self._comm.nranks > 1:
             self._comm.connect_solver(self)
 
+    def setProcessGrid(self, procs):
+        """Process grid (m, n[, p]) of the DMDA the vectors and matrix rows arrive in (PetIBM: mesh->nProc,
+        cartesianmesh.cpp:547-553).  Optional: without it setMatrix tries every grid that reproduces the ranks'
+        local sizes against the matrix entries."""
+        self._procs = None if procs is None else tuple(int(v) for v in procs)
+
+    def _verify_boxes(self, A: Mat):
+        """Several ranks: the rows of A are this rank's DMDA box, its columns PETSc global indices (for a
+        1 x 1 x P process grid that IS the natural ordering).  Finds the process grid under which A is the
+        separable stencil of the mesh; returns the exchange plan or None.  Collective."""
+        from .dist import Repart
+
+        comm, grid = self._comm, self._grid
+        sizes = [int(v) for v in comm.allgather_bytes(int(A.nrows))]
+        cands = Repart.candidates(grid.dim, grid.n, sizes)
+        if getattr(self, "_procs", None) is not None:
+            want = self._procs + (1,) * (3 - len(self._procs))
+            cands = [c for c in cands if c == want]
+        if not cands:
+            return None
+        self.setStencil(grid)   # slab partition; allocates and connects the exchange arenas
+        for c in cands:
+            plan = Repart(grid.dim, grid.n, c[: grid.dim], comm.rank)
+            rows = plan.box_rows()
+            cols = plan.petsc_to_natural(A.indices)
+            diff = C.c_double(0.0)
+            # diag_ulps = 4: partition-dependent accumulation order of PETSc's parallel MatMatMult (b200ls.h)
+            rc = self._L.b200ls_verify_csr_rows(self._h, A.nrows, rows.ctypes.data_as(_lib._i64p),
+                                                A.indptr.ctypes.data_as(_lib._i64p), cols.ctypes.data_as(_lib._i32p),
+                                                A.data.ctypes.data_as(_lib._dp), 4, C.byref(diff))
+            if rc not in (_lib.OK, _lib.ERR_MISMATCH):
+                _lib.check(rc, self._h)
+            if all(comm.allgather_bytes(rc == _lib.OK)):   # every rank must agree on the mapping
+                return plan
+        return None
+
     def setMatrix(self, A: Mat):
         """LinSolverKSP::setMatrix (linsolverksp.cpp:72-82).  The matrix is copied/recognised here, the
         caller keeps ownership (as with AmgXSolver::setA, linsolveramgx.cpp:84)."""
         if not isinstance(A, Mat):
             A = Mat.from_scipy(A)
         recognised = False
-        if self._grid is not None:
+        self._repart = None
+        multi = self._comm is not None and self._comm.nranks > 1
+        if self._grid is not None and multi:
+            self._repart = self._verify_boxes(A)
+            recognised = self._repart is not None
+            if recognised:
+                self.nlocal = self._repart.nbox    # what the caller's vectors hold: its DMDA box
+        elif self._grid is not None:
             lo, hi = self._slab(self._grid)
             if A.nrows == self._local_size(self._grid, lo, hi):
                 self.setStencil(self._grid)
@@ -222,6 +268,9 @@ class LinSolverB200(LinSolverBase):
                 elif rc != _lib.ERR_MISMATCH:
                     _lib.check(rc, self._h)
         if not recognised:
+            if multi:
+                raise B200Error(_lib.ERR_UNSUPPORTED, "the matrix is not the separable pressure stencil of the mesh "
+                                "and the general CSR operator runs on one GPU only")
             # general assembled operator, still on the GPU (IBPM modified Poisson, velocity system, BN > 1)
             _lib.check(self._L.b200ls_set_csr(self._h, A.nrows, A.indptr.ctypes.data_as(_lib._i64p),
                                               A.indices.ctypes.data_as(_lib._i32p), A.data.ctypes.data_as(_lib._dp)),
@@ -240,6 +289,21 @@ class LinSolverB200(LinSolverBase):
 
     # ---- LinSolverKSP::solve (linsolverksp.cpp:85-105): zero initial guess, error if reason < 0
     def solve(self, x, b):
+        rp = getattr(self, "_repart", None)
+        if rp is not None and not rp.identity:
+            # the caller's vectors are DMDA boxes: one all-to-all into the solver's slabs and one back (what
+            # VecScatter does inside PETSc; MPI_Alltoallv in the C++ shim)
+            if _is_torch_cuda(b) or _is_torch_cuda(x) or not isinstance(x, np.ndarray):
+                raise ValueError("box-partitioned vectors are host numpy arrays")
+            if np.size(b) != rp.nbox or x.size != rp.nbox:
+                raise ValueError("vector length does not match the operator")
+            bs = rp.box_to_slab(np.asarray(b, dtype=np.float64), self._comm.group)
+            xs = np.empty(rp.nslab, dtype=np.float64)
+            rc = self._L.b200ls_solve(self._h, C.c_void_p(bs.ctypes.data), C.c_void_p(xs.ctypes.data))
+            if rc in (_lib.OK, _lib.ERR_DIVERGED):
+                x[...] = rp.slab_to_box(xs, self._comm.group).reshape(x.shape)
+            _lib.check(rc, self._h)
+            return x
         if _is_torch_cuda(b) or _is_torch_cuda(x):
             if not (_is_torch_cuda(b) and _is_torch_cuda(x)):
                 raise ValueError("x and b must live on the same side")

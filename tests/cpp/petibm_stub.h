@@ -19,6 +19,7 @@ typedef int MPI_Op;
 #define PETSC_COMM_WORLD 0
 #define MPI_INT 1
 #define MPI_BYTE 2
+#define MPI_DOUBLE 3
 #define MPI_MIN 1
 #define PETSC_ERR_SUP 56
 #define PETSC_ERR_ARG_WRONG 62
@@ -39,6 +40,7 @@ inline int MPI_Comm_rank(MPI_Comm, int *r) { *r = 0; return 0; }
 inline int MPI_Comm_size(MPI_Comm, int *s) { *s = 1; return 0; }
 inline int MPI_Barrier(MPI_Comm) { return 0; }
 inline int MPI_Allreduce(const void *s, void *r, int n, MPI_Datatype, MPI_Op, MPI_Comm) { for (int i = 0; i < n; ++i) ((int *)r)[i] = ((const int *)s)[i]; return 0; }
+inline int MPI_Alltoallv(const void *s, const int *sc, const int *sd, MPI_Datatype, void *r, const int *, const int *rd, MPI_Datatype, MPI_Comm) { for (int i = 0; i < sc[0]; ++i) ((double *)r)[rd[0] + i] = ((const double *)s)[sd[0] + i]; return 0; }
 inline int MPI_Allgather(const void *s, int n, MPI_Datatype, void *r, int, MPI_Datatype, MPI_Comm) { for (int i = 0; i < n; ++i) ((char *)r)[i] = ((const char *)s)[i]; return 0; }
 
 struct _p_Vec { std::vector<double> a; };

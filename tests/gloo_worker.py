@@ -33,6 +33,19 @@ def main():
     lo2, hi2 = slab_range(9, comm.rank, comm.nranks)
     assert loc2.size == 6 * (hi2 - lo2) and loc2[0] == lo2 * 6
     assert np.array_equal(comm.gather_blocks(loc2), full2)
+    # DMDA boxes <-> solver slabs through ONE all-to-all per direction (tests/test_repartition.py checks the plan
+    # itself; this is the transport): 2 x 1 x 1 or 2 x 2 x 1 process grid, uneven cuts
+    from petibm_b200.dist import Repart
+
+    n3 = (7, 6, 9)
+    procs = {2: (2, 1, 1), 4: (2, 2, 1)}.get(comm.nranks, (1, 1, comm.nranks))
+    plan = Repart(3, n3, procs, comm.rank)
+    field = 100.0 + np.arange(np.prod(n3), dtype=np.float64)
+    box = field[plan.box_rows()]
+    slab = plan.box_to_slab(box)
+    lo3, hi3 = plan.slab
+    assert np.array_equal(slab, field[lo3 * 42: hi3 * 42])
+    assert np.array_equal(plan.slab_to_box(slab), box)
     comm.barrier()
     import torch.distributed as dist
 

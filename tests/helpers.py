@@ -100,3 +100,31 @@ def velocity_system(widths, periodic, dt=0.01, nu=0.01, c=0.5, vmin=0.0):
     A = (A + sp.identity(off[-1], format="csr") * (1.0 / dt)).tocsr()
     A.sort_indices()
     return A, L
+
+
+def box_local_system(A, b, dim, n, procs, rank):
+    """What one MPI rank of PetIBM holds when the DMDA uses the process grid `procs` (cartesianmesh.cpp:500-538,
+    709-721): the rows of its box in PETSc ordering with PETSc global column indices, and its part of b.
+    A: oracle matrix in natural ordering.  Returns (Mat, b_local, plan)."""
+    from petibm_b200 import Mat
+    from petibm_b200.dist import Repart
+
+    plan = Repart(dim, n, procs, rank)
+    total = int(np.prod(n))
+    to_nat = plan.petsc_to_natural(np.arange(total))
+    to_petsc = np.empty(total, dtype=np.int64)
+    to_petsc[to_nat] = np.arange(total)
+    rp, col, val = A.arrays()
+    rows = plan.box_rows()
+    cnt = rp[rows + 1] - rp[rows]
+    indptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    take = np.concatenate([np.arange(rp[r], rp[r + 1]) for r in rows]) if rows.size else np.zeros(0, dtype=np.int64)
+    cols_p = to_petsc[col[take]]
+    vals = val[take].copy()
+    # PETSc keeps every row sorted by (PETSc) column index
+    for q in range(rows.size):
+        a, e = indptr[q], indptr[q + 1]
+        o = np.argsort(cols_p[a:e], kind="stable")
+        cols_p[a:e] = cols_p[a:e][o]
+        vals[a:e] = vals[a:e][o]
+    return Mat(indptr, cols_p.astype(np.int32), vals, total), np.ascontiguousarray(b[rows]), plan

@@ -84,6 +84,48 @@ def run_case(comm, shape, per, pc, reduce, halo):
     return allok
 
 
+def run_box_case(comm, shape, per, procs):
+    """The solver behind a DMDA whose process grid is NOT 1 x 1 x P: matrix rows and vectors arrive as boxes in PETSc
+    ordering; setMatrix finds the process grid from the matrix itself and solve() re-partitions into slabs and back."""
+    dim = len(shape)
+    widths = H.make_widths(shape)
+    A = H.oracle_matrix(widths, per)
+    b, xs = H.consistent_rhs(A)
+    Aloc, bl, plan = H.box_local_system(A, b, dim, shape, procs, comm.rank)
+    c = Comm(comm.rank, comm.nranks, comm.device, "p2p", "store")
+    s = pb.LinSolverB200("poisson", "None", comm=c, device=comm.device)
+    nit = 25
+    s.setOptions(rtol=0.0, atol=0.0, max_it=nit)
+    s.setGrid(H.grid_of(widths, per))
+    s.setMatrix(Aloc.setNullSpace(True))
+    msgs = []
+    ok = s.operator == "stencil" and s._repart is not None and not s._repart.identity
+    if not ok:
+        msgs.append(f"operator {s.operator}, plan {s._repart and s._repart.procs}")
+    else:
+        ref = orc.ksp_solve(A, b, rtol=0, atol=0, max_it=nit, const_nullspace=True)
+        x = np.empty_like(bl)
+        try:
+            s.solve(x, bl)
+        except pb.B200Error as e:
+            if e.code != -5:
+                raise
+        hist = s.getHistory()
+        xo = ref.x[plan.box_rows()]
+        if hist.size != nit + 1 or (np.abs(hist - ref.history) / ref.history).max() > 1e-10:
+            ok = False
+            msgs.append("history differs from the oracle")
+        if np.abs(x - xo).max() > 1e-9 * np.abs(ref.x).max():
+            ok = False
+            msgs.append(f"x diff {np.abs(x - xo).max():.3e}")
+    s.destroy()
+    allok = all(c.allgather_bytes(ok))
+    if comm.rank == 0:
+        print(f"[{'PASS' if allok else 'FAIL'}] DMDA boxes: shape {shape} per {per} process grid {procs} {'; '.join(msgs)}",
+              flush=True)
+    return allok
+
+
 def main():
     import torch
 
@@ -104,6 +146,15 @@ def main():
         for shape, per in cases:
             for pc in (("none",) if "--c4" in sys.argv else ("none", "jacobi")):
                 allok &= run_case(comm, shape, per, pc, reduce, halo)
+    if "--c4" not in sys.argv and not args:
+        # process grids PETSc's DMDA may pick instead of 1 x 1 x P
+        grids3 = {2: [(2, 1, 1), (1, 2, 1)], 4: [(2, 2, 1), (2, 1, 2)], 8: [(2, 2, 2)]}.get(comm.nranks, [])
+        for procs in grids3:
+            allok &= run_box_case(comm, (22, 18, 19), (0, 0, 0), procs)
+            allok &= run_box_case(comm, (16, 14, 12), (1, 0, 1), procs)
+        grids2 = {2: [(2, 1)], 4: [(2, 2)], 8: [(4, 2)]}.get(comm.nranks, [])
+        for procs in grids2:
+            allok &= run_box_case(comm, (30, 23), (0, 0), procs)
     comm.barrier()
     if comm.rank == 0:
         print("MGPU_CHECK", "PASS" if allok else "FAIL", flush=True)
