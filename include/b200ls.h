@@ -19,6 +19,9 @@
  *   b200ls_set_csr                        (KSPSetOperators on the MPIAIJ Mat assembled by
  *                                          createDivergence/createGradient/createBnHead +
  *                                          MatMatMult, navierstokes.cpp:347-356)
+ *   b200ls_set_staggered                  the same call for the velocity system A = I/dt - c nu L
+ *                                         (navierstokes.cpp:342-344, createlaplacian.cpp:134-159) and IBPM's
+ *                                         modified Poisson system (ibpm.cpp:100-203)
  *   b200ls_set_nullspace                  MatSetNullSpace on DBNG            navierstokes.cpp:404-413
  *   b200ls_solve                          LinSolverKSP::solve -> KSPSolve    linsolverksp.cpp:85-105
  *   b200ls_get_iters / _get_residual      LinSolverKSP::getIters/getResidual linsolverksp.cpp:110-132
@@ -205,6 +208,27 @@ int b200ls_verify_csr_rows(b200ls_solver *h, int64_t nrows, const int64_t *natur
  * stencil cannot express (IBPM modified Poisson, BN order > 1, the velocity system A). */
 int b200ls_set_csr(b200ls_solver *h, int64_t nrows, const int64_t *rowptr, const int32_t *col,
                    const double *val);
+
+/* Line-coefficient form of an assembled staggered-grid operator (single GPU).  For the two matrices PetIBM hands
+ * to setMatrix that are stencils with one-dimensional coefficients but not the separable pressure operator:
+ * the velocity system A = I/dt - c nu L on [u | v | w] (navierstokes.cpp:342-344, createlaplacian.cpp:134-159,
+ * solved with bcgs + jacobi) and IBPM's modified Poisson system [D;E] BN [G,-H] (ibpm.cpp:100-203: pressure block +
+ * Lagrangian coupling).  nfields (1..3) stencil blocks stored one after the other, dims[3*f + d] points of field f
+ * along axis d (1 for the missing axis in 2-D), periodic[d] per axis; rows behind the blocks and columns >= the
+ * blocks' total size form a CSR remainder.  The structure (two 1-D arrays per field and axis, the diagonal as a
+ * vector, the remainder) is READ OUT OF THE MATRIX and every entry is checked bitwise against it; if anything does
+ * not fit, B200LS_ERR_MISMATCH is returned, the solver is left untouched and the caller falls back to
+ * b200ls_set_csr.  The device operator is bit-identical to MatMult on the assembled matrix (terms added in
+ * ascending column order, no FMA) at 24 B/row instead of ~100. */
+int b200ls_set_staggered(b200ls_solver *h, int nfields, const int64_t *dims, const int *periodic, int64_t nrows,
+                         const int64_t *rowptr, const int32_t *col, const double *val);
+/* The analysis itself (host only, no device needed).  coef: b200ls_staggered_coef_size(nfields, dims) doubles, per
+ * field and axis cm[n] then cp[n]; diag: one double per stencil row; rem_rowptr: nrows + 1; rem_col / rem_val:
+ * capacity nnz (may be null to only count).  errbuf receives the first mismatch as text. */
+int64_t b200ls_staggered_coef_size(int nfields, const int64_t *dims);
+int b200ls_staggered_analyze(int nfields, const int64_t *dims, const int *periodic, int64_t nrows, const int64_t *rowptr,
+                             const int32_t *col, const double *val, double *coef, double *diag, int64_t *rem_rowptr,
+                             int32_t *rem_col, double *rem_val, char *errbuf, size_t errlen);
 
 /* Null space attached to the operator: has_const != 0 -> the constant vector
  * (MatNullSpaceCreate(comm, PETSC_TRUE, 0, ...), navierstokes.cpp:404-413); nvecs explicit

@@ -24,6 +24,7 @@
 #include "spmv2.cuh"
 #include "spmv3.cuh"
 #include "csr_kernels.cuh"
+#include "sep_kernels.cuh"
 
 using namespace b200;
 
@@ -79,7 +80,7 @@ constexpr int kNcclSum = 0;     // ncclSum
 // ------------------------------------------------------------------------------------------
 // solver object
 // ------------------------------------------------------------------------------------------
-enum OperatorKind { OP_NONE = 0, OP_STENCIL = 1, OP_CSR = 2 };
+enum OperatorKind { OP_NONE = 0, OP_STENCIL = 1, OP_CSR = 2, OP_SEP = 3 };
 
 struct b200ls_solver
 {
@@ -107,6 +108,13 @@ struct b200ls_solver
     int64_t *d_rowptr = nullptr;
     int32_t *d_col = nullptr;
     double *d_val = nullptr;
+
+    // ---- operator: line-coefficient form of an assembled staggered-grid matrix (single GPU, sep_kernels.cuh)
+    SepDev sep{};
+    double *d_sep_coef = nullptr, *d_sep_diag = nullptr;
+    int64_t *d_rem_rowptr = nullptr;
+    int32_t *d_rem_col = nullptr;
+    double *d_rem_val = nullptr;
 
     // ---- vectors (solver layout)
     double *arena = nullptr;  // [mailboxes | flags | r]; exported over CUDA IPC
@@ -228,6 +236,11 @@ void free_vectors(b200ls_solver *h)
     fr(h->d_col);
     fr(h->d_val);
     fr(h->d_nullvecs);
+    fr(h->d_sep_coef);
+    fr(h->d_sep_diag);
+    fr(h->d_rem_rowptr);
+    fr(h->d_rem_col);
+    fr(h->d_rem_val);
     if (h->graph_exec)
     {
         cudaGraphExecDestroy(h->graph_exec);
@@ -852,6 +865,7 @@ int solve_stencil_cg(b200ls_solver *h, const double *b_dev, double *x_dev)
 }  // namespace
 
 #include "csr_solver.inc"
+#include "sep_solver.inc"
 
 // ------------------------------------------------------------------------------------------
 // C ABI
@@ -1550,7 +1564,7 @@ int b200ls_set_nullspace(b200ls_solver *h, int has_const, int nvecs, const doubl
     cudaSetDevice(h->device);
     if (h->op == OP_STENCIL && nvecs > 0) return fail(h, B200LS_ERR_UNSUPPORTED, "explicit null-space vectors need the CSR operator");
     h->has_const = has_const ? 1 : 0;
-    if (h->op == OP_CSR) TRY(csr_set_nullvecs(h, nvecs, vecs));
+    if (h->op == OP_CSR || h->op == OP_SEP) TRY(csr_set_nullvecs(h, nvecs, vecs));
     invalidate_graph(h);
     return B200LS_OK;
 }
@@ -1560,6 +1574,7 @@ int b200ls_apply(b200ls_solver *h, const double *x_host, double *y_host)
     if (!h || !x_host || !y_host) return B200LS_ERR_ARG;
     cudaSetDevice(h->device);
     if (h->op == OP_CSR) return csr_apply_host(h, x_host, y_host);
+    if (h->op == OP_SEP) return sep_apply_host(h, x_host, y_host);
     if (h->op != OP_STENCIL) return fail(h, B200LS_ERR_ARG, "no operator");
     if (h->nranks > 1 && !h->connected) return fail(h, B200LS_ERR_ARG, "not connected");
     const size_t nb = sizeof(double) * (size_t)h->nlocal;
@@ -1610,6 +1625,8 @@ int b200ls_solve_device(b200ls_solver *h, const double *b_dev, double *x_dev)
     }
     else if (h->op == OP_CSR)
         rc = csr_solve(h, b_dev, x_dev);
+    else if (h->op == OP_SEP)
+        rc = sep_solve(h, b_dev, x_dev);
     else
         return fail(h, B200LS_ERR_ARG, "no operator set");
     if (rc != B200LS_OK) return rc;

@@ -254,17 +254,51 @@ PetscErrorCode LinSolverB200::setMatrix(const Mat &A)
     }
     else
     {
-        // 2. verified fallback: the assembled operator itself, still on the GPU (IBPM's modified Poisson
-        //    system, the velocity system, BN order > 1)
         if (nranks > 1)
             SETERRQ1(PETSC_COMM_WORLD, PETSC_ERR_SUP,
                      "B200 linear solver \"%s\": the matrix is not the separable pressure stencil of the mesh and the "
-                     "general CSR operator runs on one GPU only.", name.c_str());
-        B200CHK(handle, b200ls_set_csr(handle, nloc, rowptr.data(), col.data(), val.data()));
-        opKind = "csr";
+                     "assembled-operator paths run on one GPU only.", name.c_str());
+        // 2. a staggered-grid matrix with one-dimensional coefficients: the packed velocity system [u | v | w]
+        //    (cartesianmesh.cpp:251-273: one point fewer than cells along the field's own direction unless periodic)
+        //    or the pressure block followed by IBPM's Lagrangian force rows (ibpm.cpp:164-194).  The structure is read
+        //    out of A and verified against every entry by b200ls_set_staggered.
+        bool staggered = false;
+        if (haveGrid)
+        {
+            const int64_t n3[3] = {gn[0], gn[1], gdim == 3 ? gn[2] : 1};
+            int64_t vel[9], velTotal = 0;
+            bool velOk = true;
+            for (int f = 0; f < (int)gdim; ++f)
+            {
+                int64_t sz = 1;
+                for (int d = 0; d < 3; ++d)
+                {
+                    vel[3 * f + d] = n3[d] - ((d == f && !gper[d]) ? 1 : 0);
+                    velOk = velOk && vel[3 * f + d] >= 1;
+                    sz *= vel[3 * f + d];
+                }
+                velTotal += sz;
+            }
+            const int64_t pN = n3[0] * n3[1] * n3[2];
+            int rc = B200LS_ERR_MISMATCH;
+            if (velOk && (int64_t)nloc == velTotal)
+                rc = b200ls_set_staggered(handle, (int)gdim, vel, gper, nloc, rowptr.data(), col.data(), val.data());
+            if (rc == B200LS_ERR_MISMATCH && (int64_t)nloc > pN)
+                rc = b200ls_set_staggered(handle, 1, n3, gper, nloc, rowptr.data(), col.data(), val.data());
+            if (rc == B200LS_OK) staggered = true;
+            else if (rc != B200LS_ERR_MISMATCH) B200CHK(handle, rc);
+        }
+        if (staggered)
+            opKind = "staggered";
+        else
+        {
+            // 3. verified fallback: the assembled operator itself, still on the GPU (BN order > 1, anything else)
+            B200CHK(handle, b200ls_set_csr(handle, nloc, rowptr.data(), col.data(), val.data()));
+            opKind = "csr";
+        }
     }
 
-    // 3. the null space the application attached with MatSetNullSpace (navierstokes.cpp:404-413, ibpm.cpp:251-267)
+    // 4. the null space the application attached with MatSetNullSpace (navierstokes.cpp:404-413, ibpm.cpp:251-267)
     MatNullSpace nsp = nullptr;
     ierr = MatGetNullSpace(A, &nsp); CHKERRQ(ierr);
     if (nsp)

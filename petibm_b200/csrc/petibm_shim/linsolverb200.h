@@ -50,7 +50,8 @@ public:
     PetscErrorCode getIters(PetscInt &iters) override;
     PetscErrorCode getResidual(PetscReal &res) override;
 
-    /** "stencil" (matrix-free separable operator verified against A) or "csr". */
+    /** "stencil" (matrix-free separable pressure operator verified against A), "staggered" (line-coefficient form
+     *  read out of A: velocity system, IBPM modified Poisson) or "csr". */
     const std::string &getOperatorKind() const { return opKind; }
 
 protected:

@@ -107,7 +107,8 @@ class LinSolverB200(LinSolverBase):
         self._grid = None
         self._procs = None     # DMDA process grid, if the caller knows it (setProcessGrid)
         self._repart = None    # box <-> slab exchange plan when the vectors arrive as DMDA boxes
-        self.operator = None   # "stencil" | "csr" after setMatrix
+        self._staggered = True # setMatrix may use the line-coefficient form for velocity / IBPM matrices
+        self.operator = None   # "stencil" | "staggered" | "csr" after setMatrix
         if device is None:
             device = comm.device if comm is not None else 0
         _lib.check(self._L.b200ls_create(C.byref(self._h), int(device)))
@@ -242,6 +243,42 @@ class LinSolverB200(LinSolverBase):
                 return plan
         return None
 
+    def setStaggered(self, enable: bool):
+        """Whether setMatrix may keep a staggered-grid matrix that is not the pressure stencil in line-coefficient
+        form (b200ls_set_staggered) instead of plain CSR.  On by default; the structure is verified against the
+        matrix either way."""
+        self._staggered = bool(enable)
+
+    def _staggered_layouts(self, nrows: int):
+        """Field layouts the matrix may have, from the mesh: the packed velocity vector [u | v | w]
+        (cartesianmesh.cpp:251-273: one point fewer than cells along the field's own direction unless periodic), or
+        the pressure block followed by IBPM's Lagrangian force rows (ibpm.cpp:164-194)."""
+        g = self._grid
+        n = list(g.n) + [1] * (3 - g.dim)
+        per = [int(bool(p)) for p in g.periodic][:3]
+        vel = [[n[d] - (1 if (d == f and not per[d]) else 0) for d in range(3)] for f in range(g.dim)]
+        out = []
+        if nrows == sum(int(np.prod(v)) for v in vel) and all(min(v) >= 1 for v in vel):
+            out.append(vel)
+        if nrows > g.size:
+            out.append([n])
+        return out, per
+
+    def _try_staggered(self, A: Mat) -> bool:
+        layouts, per = self._staggered_layouts(A.nrows)
+        for dims in layouts:
+            d = np.ascontiguousarray(dims, dtype=np.int64).reshape(-1)
+            rc = self._L.b200ls_set_staggered(self._h, len(dims), d.ctypes.data_as(_lib._i64p), (C.c_int * 3)(*per), A.nrows,
+                                              A.indptr.ctypes.data_as(_lib._i64p), A.indices.ctypes.data_as(_lib._i32p),
+                                              A.data.ctypes.data_as(_lib._dp))
+            if rc == _lib.OK:
+                self.operator = "staggered"
+                self.nlocal = A.nrows
+                return True
+            if rc != _lib.ERR_MISMATCH:
+                _lib.check(rc, self._h)
+        return False
+
     def setMatrix(self, A: Mat):
         """LinSolverKSP::setMatrix (linsolverksp.cpp:72-82).  The matrix is copied/recognised here, the
         caller keeps ownership (as with AmgXSolver::setA, linsolveramgx.cpp:84)."""
@@ -267,6 +304,8 @@ class LinSolverB200(LinSolverBase):
                     recognised = True
                 elif rc != _lib.ERR_MISMATCH:
                     _lib.check(rc, self._h)
+        if not recognised and not multi and self._grid is not None and self._staggered:
+            recognised = self._try_staggered(A)
         if not recognised:
             if multi:
                 raise B200Error(_lib.ERR_UNSUPPORTED, "the matrix is not the separable pressure stencil of the mesh "

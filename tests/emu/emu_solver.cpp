@@ -10,6 +10,7 @@
 #include "spmv2.cuh"
 #include "spmv3.cuh"
 #include "csr_kernels.cuh"
+#include "sep_kernels.cuh"
 
 using namespace b200;
 
@@ -439,6 +440,107 @@ EMU_API int emu_csr_solve(int64_t n, const int64_t *rowptr, const int32_t *col, 
         {
             CsrVecs v{r.data(), pp[it & 1], pp[(it & 1) ^ 1], w.data(), x.data(), dv, nullvec};
 #define EMU_CS(JAC, NM) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_csr_cg_spmv<JAC, NM>(A, v, W.ws, &st, kc, hist); })
+            if (jacobi) { if (nm == 2) EMU_CS(true, 2); else if (nm == 1) EMU_CS(true, 1); else EMU_CS(true, 0); }
+            else { if (nm == 2) EMU_CS(false, 2); else if (nm == 1) EMU_CS(false, 1); else EMU_CS(false, 0); }
+#undef EMU_CS
+            upd(false, nm == 2 ? FIN_CSR_UPDATE : FIN_UPDATE);
+        }
+        GridDev g1{};
+        g1.nx = (int)n; g1.ny = 1; g1.nzl = 1; g1.px = (int)n; g1.plane = 0;
+        emu::launch(dim3(1), dim3(256), 0, [&] { k_xtail(g1, x.data(), p0.data(), p1.data(), &st); });
+    }
+    memcpy(x_out, x.data(), sizeof(double) * (size_t)n);
+    *nhist = st.nhist;
+    *its = st.its;
+    *reason = st.reason;
+    return st.done ? 0 : 1;
+}
+
+// ---- line-coefficient operator (sep_kernels.cuh): same Krylov drivers as emu_csr_solve with the row product swapped.
+// The structure comes from b200ls_staggered_analyze (host code of libb200ls.so), passed in as plain arrays.
+EMU_API int emu_sep_solve(int nfields, const int64_t *dims, const int *periodic, int64_t n, const double *coef, const double *diag,
+                          const int64_t *rem_rowptr, const int32_t *rem_col, const double *rem_val, const double *dinv_in,
+                          int mode /* 0 apply, 1 cg, 2 bcgs */, int jacobi, int has_const, const double *nullvec, double rtol,
+                          double atol, int max_it, const double *b, double *x_out, double *hist, int hist_cap, int *nhist,
+                          int *its, int *reason)
+{
+    Ws W;
+    SepDev A{};
+    A.nf = nfields;
+    A.nrows = n;
+    A.diag = diag;
+    long long off = 0, cpos = 0;
+    for (int f = 0; f < nfields; ++f)
+    {
+        SepField &F = A.f[f];
+        F.n0 = (int)dims[3 * f]; F.n1 = (int)dims[3 * f + 1]; F.n2 = (int)dims[3 * f + 2];
+        F.per0 = periodic[0] && F.n0 >= 3; F.per1 = periodic[1] && F.n1 >= 3; F.per2 = periodic[2] && F.n2 >= 3;
+        F.off = off;
+        off += (long long)F.n0 * F.n1 * F.n2;
+        for (int d = 0; d < 3; ++d)
+        {
+            F.cm[d] = coef + cpos;
+            F.cp[d] = coef + cpos + dims[3 * f + d];
+            cpos += 2 * dims[3 * f + d];
+        }
+    }
+    A.nsep = off;
+    if (rem_rowptr && rem_rowptr[n] > 0)
+    {
+        A.rem_rowptr = rem_rowptr;
+        A.rem_col = rem_col;
+        A.rem_val = rem_val;
+    }
+    const int blocks = 3;
+    if (mode == 0)
+    {
+        emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_apply(A, b, x_out); });
+        return 0;
+    }
+    SolveConsts kc{};
+    kc.rtol = rtol; kc.atol = atol; kc.divtol = 1e4; kc.nglobal = (double)n;
+    kc.max_it = max_it; kc.norm_type = 1; kc.has_const = has_const; kc.hist_cap = hist_cap;
+    DevState st{};
+    emu::launch(dim3(1), dim3(32), 0, [&] { k_state_reset(&st); });
+    std::vector<double> r((size_t)n), p0((size_t)n, 0.0), p1((size_t)n, 0.0), w((size_t)n, 0.0), x((size_t)n, 0.0);
+    const double *dv = jacobi ? dinv_in : nullptr;
+    if (mode == 2)
+    {
+        std::vector<double> rp((size_t)n), vv((size_t)n), s((size_t)n), t((size_t)n);
+        if (jacobi) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_init<true>(n, b, dv, r.data(), rp.data(), p0.data(), vv.data(), W.ws, &st, kc, hist); });
+        else emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_init<false>(n, b, dv, r.data(), rp.data(), p0.data(), vv.data(), W.ws, &st, kc, hist); });
+        for (int it = 0; it < max_it + 2 && !st.done; ++it)
+        {
+            emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_p(n, r.data(), vv.data(), p0.data(), &st); });
+            if (jacobi) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_bcgs_spmv1<true>(A, p0.data(), dv, rp.data(), vv.data(), W.ws, &st, kc, hist); });
+            else emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_bcgs_spmv1<false>(A, p0.data(), dv, rp.data(), vv.data(), W.ws, &st, kc, hist); });
+            if (jacobi) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_bcgs_spmv2<true>(A, r.data(), vv.data(), dv, s.data(), t.data(), W.ws, &st, kc, hist); });
+            else emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_bcgs_spmv2<false>(A, r.data(), vv.data(), dv, s.data(), t.data(), W.ws, &st, kc, hist); });
+            emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_upd(n, p0.data(), s.data(), t.data(), rp.data(), x.data(), r.data(), W.ws, &st, kc, hist); });
+        }
+        emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_tail(n, p0.data(), x.data(), &st); });
+    }
+    else
+    {
+        memcpy(r.data(), b, sizeof(double) * (size_t)n);
+        const int nm = nullvec ? 2 : (has_const ? 1 : 0);
+        auto upd = [&](bool init, int kind) {
+#define EMU_CU(JAC, NM, INIT) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_csr_cg_update<JAC, NM, INIT>(n, r.data(), w.data(), dv, nullvec, kind, W.ws, &st, kc, hist); })
+            if (jacobi) { if (nm == 2) { if (init) EMU_CU(true, 2, true); else EMU_CU(true, 2, false); } else if (nm == 1) { if (init) EMU_CU(true, 1, true); else EMU_CU(true, 1, false); } else { if (init) EMU_CU(true, 0, true); else EMU_CU(true, 0, false); } }
+            else { if (nm == 2) { if (init) EMU_CU(false, 2, true); else EMU_CU(false, 2, false); } else if (nm == 1) { if (init) EMU_CU(false, 1, true); else EMU_CU(false, 1, false); } else { if (init) EMU_CU(false, 0, true); else EMU_CU(false, 0, false); } }
+#undef EMU_CU
+        };
+        if (nm == 2) upd(true, FIN_CSR_INIT);
+        else
+        {
+            if (nm == 1) upd(true, FIN_INIT_CENTRE);
+            upd(true, FIN_INIT);
+        }
+        double *pp[2] = {p0.data(), p1.data()};
+        for (int it = 0; it < max_it + 2 && !st.done; ++it)
+        {
+            CsrVecs v{r.data(), pp[it & 1], pp[(it & 1) ^ 1], w.data(), x.data(), dv, nullvec};
+#define EMU_CS(JAC, NM) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_cg_spmv<JAC, NM>(A, v, W.ws, &st, kc, hist); })
             if (jacobi) { if (nm == 2) EMU_CS(true, 2); else if (nm == 1) EMU_CS(true, 1); else EMU_CS(true, 0); }
             else { if (nm == 2) EMU_CS(false, 2); else if (nm == 1) EMU_CS(false, 1); else EMU_CS(false, 0); }
 #undef EMU_CS

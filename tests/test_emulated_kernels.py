@@ -18,7 +18,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
 LIB = os.path.join(EMU, "libb200emu.so")
 SRC = [os.path.join(EMU, f) for f in ("emu_solver.cpp", "cuda_emu.h")] + \
-      [os.path.join(ROOT, "petibm_b200", "csrc", f) for f in ("kernels.cuh", "spmv2.cuh", "spmv3.cuh", "hw.cuh", "csr_kernels.cuh")]
+      [os.path.join(ROOT, "petibm_b200", "csrc", f) for f in ("kernels.cuh", "spmv2.cuh", "spmv3.cuh", "hw.cuh", "csr_kernels.cuh",
+                                                            "sep_kernels.cuh")]
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -44,6 +45,9 @@ def emu():
     L.emu_set_schedule.argtypes = [C.c_uint64]
     L.emu_csr_solve.argtypes = [C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32), _dp, C.c_int, C.c_int, C.c_int, _dp,
                                 C.c_double, C.c_double, C.c_int, _dp, _dp, _dp, C.c_int, _ip, _ip, _ip]
+    L.emu_sep_solve.argtypes = [C.c_int, C.POINTER(C.c_int64), _ip, C.c_int64, _dp, _dp, C.POINTER(C.c_int64),
+                                C.POINTER(C.c_int32), _dp, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_double, C.c_double, C.c_int,
+                                _dp, _dp, _dp, C.c_int, _ip, _ip, _ip]
     return L
 
 
@@ -269,5 +273,102 @@ def test_emulated_csr_paths(emu, pc):
     bm = M @ xs
     refm = orc.ksp_solve(Mo, bm, pc_type=pc, rtol=0, atol=0, max_it=15, nullvecs=nv)
     x, hist, its, reason = _csr_solve(emu, M, bm, pc=pc, nullvec=nv, max_it=15)
+    np.testing.assert_allclose(hist, refm.history, rtol=1e-10)
+    np.testing.assert_allclose(x, refm.x, rtol=0, atol=1e-9 * np.abs(refm.x).max())
+
+
+def _sep_solve(L, dims, per, M, b, mode="apply", pc="none", has_const=False, nullvec=None, rtol=0.0, atol=0.0, max_it=20):
+    """The line-coefficient operator (sep_kernels.cuh) on the emulation; the structure is read out of M by the host
+    code of libb200ls.so (b200ls_staggered_analyze), exactly as b200ls_set_staggered does before uploading it."""
+    from petibm_b200.staggered import analyze
+
+    M = M.tocsr(); M.sort_indices()
+    st = analyze(dims, per, M.indptr, M.indices, M.data)
+    d = np.ascontiguousarray(dims, dtype=np.int64).reshape(-1)
+    p3 = (C.c_int * 3)(*([int(v) for v in per] + [0] * 3)[:3])
+    coef = np.ascontiguousarray(np.concatenate([np.concatenate(ax) for f in st["coef"] for ax in f]))
+    diag = np.ascontiguousarray(st["diag"])
+    rp, rc, rv = st["rem"]
+    rc = np.ascontiguousarray(rc if rc.size else np.zeros(1, dtype=np.int32)); rv = np.ascontiguousarray(rv if rv.size else np.zeros(1))
+    dg = M.diagonal()
+    dinv = np.where(dg != 0.0, 1.0 / np.where(dg != 0.0, dg, 1.0), 1.0)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.empty_like(b); hist = np.zeros(max_it + 2)
+    nh, its, reason = C.c_int(0), C.c_int(0), C.c_int(0)
+    nvp = None if nullvec is None else np.ascontiguousarray(nullvec, dtype=np.float64).ctypes.data_as(_dp)
+    rcode = L.emu_sep_solve(len(dims), d.ctypes.data_as(C.POINTER(C.c_int64)), p3, M.shape[0], coef.ctypes.data_as(_dp),
+                            diag.ctypes.data_as(_dp), rp.ctypes.data_as(C.POINTER(C.c_int64)),
+                            rc.ctypes.data_as(C.POINTER(C.c_int32)), rv.ctypes.data_as(_dp), dinv.ctypes.data_as(_dp),
+                            {"apply": 0, "cg": 1, "bcgs": 2}[mode], int(pc == "jacobi"), int(has_const), nvp, rtol, atol, max_it,
+                            b.ctypes.data_as(_dp), x.ctypes.data_as(_dp), hist.ctypes.data_as(_dp), hist.size, C.byref(nh),
+                            C.byref(its), C.byref(reason))
+    assert rcode == 0
+    return x, hist[: nh.value].copy(), its.value, reason.value
+
+
+def _velocity_dims(shape, per):
+    dim = len(shape)
+    n = list(shape) + [1] * (3 - dim)
+    p = list(per) + [0] * (3 - dim)
+    return [[n[d] - (1 if (d == f and not p[d]) else 0) for d in range(3)] for f in range(dim)], p
+
+
+@pytest.mark.parametrize("shape,per", [((9, 8), (0, 0)), ((8, 7, 6), (0, 0, 0)), ((7, 6, 5), (1, 0, 1)), ((5, 6, 7), (1, 1, 1)),
+                                       ((40, 3, 3), (0, 1, 0))])
+def test_emulated_line_coefficient_spmv_is_bit_identical_to_the_assembled_matmult(emu, shape, per):
+    """Velocity system A = I/dt - c nu L (createlaplacian.cpp:134-159, navierstokes.cpp:342-344) in line-coefficient
+    form: y = A x equals the oracle's MatMult_SeqAIJ restatement on the assembled matrix bit for bit."""
+    A, _ = H.velocity_system(H.make_widths(shape), per, dt=0.01, nu=0.02)
+    Ao = orc.Csr.from_arrays(A.shape[0], A.shape[1], A.indptr, A.indices, A.data)
+    dims, p = _velocity_dims(shape, per)
+    rng = np.random.default_rng(3)
+    for _ in range(2):
+        x = rng.standard_normal(A.shape[0])
+        y, _, _, _ = _sep_solve(emu, dims, p, A, x, mode="apply")
+        assert np.array_equal(y, Ao.spmv(x))
+
+
+@pytest.mark.parametrize("pc", ["none", "jacobi"])
+def test_emulated_line_coefficient_krylov_paths(emu, pc):
+    """Same systems as test_emulated_csr_paths, through sep_kernels.cuh: the residual histories must equal those of the
+    CSR kernels EXACTLY (same row sums bit for bit, same reductions), and match the oracle like they do."""
+    import scipy.sparse as sp
+
+    # velocity system, BiCGStab (+ Jacobi): what vSolver->solve runs in the shipped configs
+    shape, per = (8, 7, 6), (0, 0, 0)
+    A, _ = H.velocity_system(H.make_widths(shape), per, dt=0.5, nu=1.0)
+    Ao = orc.Csr.from_arrays(A.shape[0], A.shape[1], A.indptr, A.indices, A.data)
+    dims, p = _velocity_dims(shape, per)
+    b = np.random.default_rng(2).standard_normal(A.shape[0])
+    ref = orc.ksp_solve(Ao, b, ksp_type="bcgs", pc_type=pc, rtol=0.0, atol=1e-8, max_it=300)
+    xc, hc, ic, rc = _csr_solve(emu, A, b, bcgs=True, pc=pc, atol=1e-8, max_it=300)
+    x, hist, its, reason = _sep_solve(emu, dims, p, A, b, mode="bcgs", pc=pc, atol=1e-8, max_it=300)
+    assert (its, reason) == (ic, rc) and np.array_equal(hist, hc) and np.array_equal(x, xc)
+    assert reason == ref.reason == 3 and abs(its - ref.its) <= 2
+    np.testing.assert_allclose(hist[:8], ref.history[:8], rtol=1e-9)
+    # periodic velocity system, CG is not what PetIBM uses there but the kernel exists: compare with the CSR kernels
+    shape, per = (7, 6, 5), (1, 0, 1)
+    A, _ = H.velocity_system(np.array([np.full(n, 1.0 / n) for n in shape], dtype=object).tolist(), per, dt=0.5, nu=1.0)
+    dims, p = _velocity_dims(shape, per)
+    b = np.random.default_rng(6).standard_normal(A.shape[0])
+    xc, hc, ic, rc = _csr_solve(emu, A, b, pc=pc, max_it=12)
+    x, hist, its, reason = _sep_solve(emu, dims, p, A, b, mode="cg", pc=pc, max_it=12)
+    assert (its, reason) == (ic, rc) and np.array_equal(hist, hc) and np.array_equal(x, xc)
+    # IBPM-style modified Poisson: stencil block + remainder, CG with the explicit null-space vector (ibpm.cpp:251-267)
+    gshape = (10, 9)
+    G = orc.assemble_gradient(H.make_widths(gshape), [0, 0, 0]).to_scipy()
+    R = sp.random(G.shape[0], 7, density=0.05, random_state=4, format="csr")
+    K = sp.hstack([G, -R]).tocsr()
+    M = (-(K.T @ K) * 0.01).tocsr(); M.sort_indices()
+    nv = np.zeros(M.shape[0]); nv[: G.shape[1]] = 1.0 / np.sqrt(G.shape[1])
+    Mo = orc.Csr.from_arrays(M.shape[0], M.shape[1], M.indptr, M.indices, M.data)
+    xs = np.random.default_rng(5).standard_normal(M.shape[0]); xs -= (xs @ nv) * nv
+    bm = M @ xs
+    refm = orc.ksp_solve(Mo, bm, pc_type=pc, rtol=0, atol=0, max_it=15, nullvecs=nv)
+    y, _, _, _ = _sep_solve(emu, [[10, 9, 1]], (0, 0, 0), M, xs, mode="apply")
+    assert np.array_equal(y, Mo.spmv(xs))
+    xc, hc, ic, rc = _csr_solve(emu, M, bm, pc=pc, nullvec=nv, max_it=15)
+    x, hist, its, reason = _sep_solve(emu, [[10, 9, 1]], (0, 0, 0), M, bm, mode="cg", pc=pc, nullvec=nv, max_it=15)
+    assert (its, reason) == (ic, rc) and np.array_equal(hist, hc) and np.array_equal(x, xc)
     np.testing.assert_allclose(hist, refm.history, rtol=1e-10)
     np.testing.assert_allclose(x, refm.x, rtol=0, atol=1e-9 * np.abs(refm.x).max())
