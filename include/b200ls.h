@@ -64,6 +64,7 @@ extern "C" {
 #define B200LS_KSP_BCGS 1
 #define B200LS_PC_NONE 0
 #define B200LS_PC_JACOBI 1
+#define B200LS_PC_MG 2 /* geometric multigrid on the separable pressure operator (extension, single GPU) */
 #define B200LS_NORM_NONE 0
 #define B200LS_NORM_PRECONDITIONED 1
 #define B200LS_NORM_UNPRECONDITIONED 2
@@ -98,6 +99,12 @@ typedef struct b200ls_options
     double divtol;  /* default 1e4 */
     int check_every; /* host polls the device convergence flag every this many iterations (default 32) */
     int variant;     /* kernel variant selector for experiments; 0 = default */
+    /* pc_type mg (PETSc's PCMG option names): -<name>_pc_mg_levels (0 = as many as the grid allows),
+     * -<name>_mg_levels_ksp_max_it (Chebyshev/Jacobi smoothing steps before and after the coarse correction, default 2),
+     * -<name>_mg_coarse_ksp_max_it (Chebyshev steps on the coarsest level, default 16) */
+    int mg_levels;
+    int mg_smooth_its;
+    int mg_coarse_its;
 } b200ls_options;
 
 /* ---- library-level ---- */

@@ -25,6 +25,8 @@
 #include "spmv3.cuh"
 #include "csr_kernels.cuh"
 #include "sep_kernels.cuh"
+#include "mg_kernels.cuh"
+#include "mg_schedule.h"
 
 using namespace b200;
 
@@ -115,6 +117,15 @@ struct b200ls_solver
     int64_t *d_rem_rowptr = nullptr;
     int32_t *d_rem_col = nullptr;
     double *d_rem_val = nullptr;
+
+    // ---- geometric multigrid preconditioner of the separable operator (mg_kernels.cuh, mg_schedule.h)
+    std::vector<MgHostLevel> mg_host;
+    std::vector<MgLevel> mg_dev;
+    std::vector<std::vector<double *>> mg_bufs;  // per level: 4 work vectors (+ the right-hand side of a coarse level)
+    std::vector<double *> mg_axes;               // per coarse level: its six 1-D arrays
+    MgParams mg_prm;
+    bool mg_ready = false;
+    int mg_built_levels = 0;
 
     // ---- vectors (solver layout)
     double *arena = nullptr;  // [mailboxes | flags | r]; exported over CUDA IPC
@@ -209,8 +220,11 @@ int fail(b200ls_solver *h, int code, const char *fmt, ...)
 
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
+void free_mg(b200ls_solver *h);
+
 void free_vectors(b200ls_solver *h)
 {
+    free_mg(h);
     auto fr = [](auto *&p) {
         if (p) cudaFree(p);
         p = nullptr;
@@ -866,6 +880,7 @@ int solve_stencil_cg(b200ls_solver *h, const double *b_dev, double *x_dev)
 
 #include "csr_solver.inc"
 #include "sep_solver.inc"
+#include "mg_solver.inc"
 
 // ------------------------------------------------------------------------------------------
 // C ABI
@@ -947,6 +962,9 @@ void b200ls_default_options(b200ls_options *o)
     o->divtol = 1e4;
     o->check_every = 32;
     o->variant = 0;
+    o->mg_levels = 0;
+    o->mg_smooth_its = 2;
+    o->mg_coarse_its = 16;
 }
 
 static void set_err(char *errbuf, size_t errlen, const char *fmt, ...)
@@ -1043,7 +1061,27 @@ int b200ls_parse_options(const char *text, const char *prefix, b200ls_options *o
             if (!need()) return B200LS_ERR_PARSE;
             if (val == "none") opts->pc_type = B200LS_PC_NONE;
             else if (val == "jacobi") opts->pc_type = B200LS_PC_JACOBI;
-            else { set_err(errbuf, errlen, "-%spc_type %s is not implemented by the B200 backend (none, jacobi)", prefix, val.c_str()); return B200LS_ERR_UNSUPPORTED; }
+            else if (val == "mg") opts->pc_type = B200LS_PC_MG;
+            else { set_err(errbuf, errlen, "-%spc_type %s is not implemented by the B200 backend (none, jacobi, mg)", prefix, val.c_str()); return B200LS_ERR_UNSUPPORTED; }
+        }
+        // geometric multigrid (extension; PETSc's PCMG option names, only the combination that is implemented)
+        else if (key == "pc_mg_levels") { if (!num(d)) return B200LS_ERR_PARSE; opts->mg_levels = (int)d; }
+        else if (key == "mg_levels_ksp_max_it") { if (!num(d)) return B200LS_ERR_PARSE; opts->mg_smooth_its = (int)d; }
+        else if (key == "mg_coarse_ksp_max_it") { if (!num(d)) return B200LS_ERR_PARSE; opts->mg_coarse_its = (int)d; }
+        else if (key == "mg_levels_ksp_type" || key == "mg_coarse_ksp_type")
+        {
+            if (!need()) return B200LS_ERR_PARSE;
+            if (val != "chebyshev") { set_err(errbuf, errlen, "-%s%s %s unsupported (chebyshev)", prefix, key.c_str(), val.c_str()); return B200LS_ERR_UNSUPPORTED; }
+        }
+        else if (key == "mg_levels_pc_type" || key == "mg_coarse_pc_type")
+        {
+            if (!need()) return B200LS_ERR_PARSE;
+            if (val != "jacobi") { set_err(errbuf, errlen, "-%s%s %s unsupported (jacobi)", prefix, key.c_str(), val.c_str()); return B200LS_ERR_UNSUPPORTED; }
+        }
+        else if (key == "pc_mg_cycle_type")
+        {
+            if (!need()) return B200LS_ERR_PARSE;
+            if (val != "v") { set_err(errbuf, errlen, "-%spc_mg_cycle_type %s unsupported (v)", prefix, val.c_str()); return B200LS_ERR_UNSUPPORTED; }
         }
         else if (key == "pc_jacobi_type")
         {
@@ -1621,7 +1659,7 @@ int b200ls_solve_device(b200ls_solver *h, const double *b_dev, double *x_dev)
     {
         if (h->opt.ksp_type != B200LS_KSP_CG)
             return fail(h, B200LS_ERR_UNSUPPORTED, "the separable stencil operator is solved with cg; bcgs needs the CSR operator");
-        rc = solve_stencil_cg(h, b_dev, x_dev);
+        rc = (h->opt.pc_type == B200LS_PC_MG) ? solve_stencil_pcg_mg(h, b_dev, x_dev) : solve_stencil_cg(h, b_dev, x_dev);
     }
     else if (h->op == OP_CSR)
         rc = csr_solve(h, b_dev, x_dev);

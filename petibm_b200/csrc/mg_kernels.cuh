@@ -1,0 +1,232 @@
+// mg_kernels.cuh -- geometric multigrid preconditioner for the separable pressure operator (single GPU).
+//
+// Why: every Poisson configuration PetIBM ships preconditions CG with algebraic multigrid (PETSc GAMG on the CPU,
+// AmgX classical AMG on the GPU: examples/*/config/poisson_solver.info, solversPetscOptions.info); without a
+// multilevel preconditioner CG needs O(n) iterations per time step.  The operator here
+// is not an arbitrary sparse matrix but D (dt I) G of a stretched Cartesian grid, fully described by six 1-D arrays,
+// so the hierarchy is GEOMETRIC and matrix-free on every level:
+//
+//   coarsening    cells are merged pairwise per axis (an odd last cell stays alone), widths add up;
+//   operator      the same closed form D (dt I) G on the merged cells (rediscretisation; appendix A.1 of SURVEY.md);
+//   restriction   sum over the merged cells (the rows are volume-integrated divergences), prolongation = its
+//                 transpose (piecewise constant), so the V-cycle is symmetric;
+//   smoother      Chebyshev polynomial in D^-1 A on [lambda_max / alpha, lambda_max] with lambda_max = 2 from
+//                 Gershgorin (every row of this operator sums to zero), same polynomial before and after the coarse
+//                 correction (symmetric), a longer polynomial on the coarsest grid -- a FIXED linear operator, as
+//                 PCG requires;
+//   null space    the constant is removed from z after the cycle exactly like PETSc does after any PCApply
+//                 (MatNullSpaceRemove: the shift computed by finalize_scalars and applied inside k_spmv2).
+//
+// This is an extension with PETSc's option names (-<name>_pc_type mg, -<name>_pc_mg_levels,
+// -<name>_mg_levels_ksp_max_it, -<name>_mg_coarse_ksp_max_it); the reference has no geometric multigrid to be
+// bit-compared with -- the checker is an independent numpy/scipy restatement of this algorithm in
+// tests/mg_reference.py (assembled level operators), and the converged solutions agree with plain CG.
+//
+// Kernels: one thread per cell, 7-point rows rebuilt from the 1-D arrays, neighbour values through L1/L2.  A Chebyshev
+// step is ONE pass (x + d formed on the fly at the seven points, residual, new d) with ping-pong buffers; the
+// prolongation is folded into the first post-smoothing step and the residual into the restriction.
+#pragma once
+#include <stdint.h>
+
+#include "kernels.cuh"
+
+namespace b200 {
+
+struct MgLevel
+{
+    int nx, ny, nz;           // cells of this level
+    int px;                   // row pitch of this level's vectors
+    long long plane, base;    // plane stride and offset of cell (0,0,0): index = base + i + px*j + plane*k
+    int perx, pery, perz;     // periodic axes (index wrap)
+    int cx, cy, cz;           // 1: the axis is coarsened on the way to the next level (cells 2I, 2I+1 -> I)
+    const double *dx, *dy, *dz;  // cell widths
+    const double *gx, *gy, *gz;  // face coefficients dt/h, n+1 entries, 0 at walls, wrap value at both ends if periodic
+};
+
+// one row of the level operator: slots 0..6 = z-, y-, x-, centre, x+, y+, z+ (ascending column order)
+struct MgRow
+{
+    double c[7];
+    long long j[7];            // vector indices of the seven points
+    int im, ip, jm, jp, km, kp;  // neighbour coordinates (wrapped / clamped)
+};
+
+__device__ __forceinline__ MgRow mg_row(const MgLevel &L, int i, int j, int k)
+{
+    MgRow r;
+    const double dxi = L.dx[i], dyj = L.dy[j], dzk = L.dz[k];
+    const double ayz = dyj * dzk, axz = dxi * dzk, axy = dxi * dyj;
+    r.c[2] = ayz * L.gx[i];
+    r.c[4] = ayz * L.gx[i + 1];
+    r.c[1] = axz * L.gy[j];
+    r.c[5] = axz * L.gy[j + 1];
+    r.c[0] = axy * L.gz[k];
+    r.c[6] = axy * L.gz[k + 1];
+    r.c[3] = -(((((r.c[2] + r.c[4]) + r.c[1]) + r.c[5]) + r.c[0]) + r.c[6]);
+    // neighbours: wrap on periodic axes; at a wall the coefficient is zero and the index stays on the cell itself
+    r.im = i > 0 ? i - 1 : (L.perx ? L.nx - 1 : i);
+    r.ip = i < L.nx - 1 ? i + 1 : (L.perx ? 0 : i);
+    r.jm = j > 0 ? j - 1 : (L.pery ? L.ny - 1 : j);
+    r.jp = j < L.ny - 1 ? j + 1 : (L.pery ? 0 : j);
+    r.km = k > 0 ? k - 1 : (L.perz ? L.nz - 1 : k);
+    r.kp = k < L.nz - 1 ? k + 1 : (L.perz ? 0 : k);
+    const long long rowj = L.base + (long long)L.px * j, pk = L.plane * k;
+    r.j[3] = rowj + pk + i;
+    r.j[2] = rowj + pk + r.im;
+    r.j[4] = rowj + pk + r.ip;
+    r.j[1] = L.base + (long long)L.px * r.jm + pk + i;
+    r.j[5] = L.base + (long long)L.px * r.jp + pk + i;
+    r.j[0] = rowj + L.plane * r.km + i;
+    r.j[6] = rowj + L.plane * r.kp + i;
+    return r;
+}
+
+// (A v)(cell); v(q) = value at slot q
+template <class V>
+__device__ __forceinline__ double mg_apply(const MgRow &r, V v)
+{
+    double t = r.c[0] * v(0);
+#pragma unroll
+    for (int q = 1; q < 7; ++q) t += r.c[q] * v(q);
+    return t;
+}
+
+__device__ __forceinline__ void mg_cell(const MgLevel &L, long long t, int &i, int &j, int &k)
+{
+    const unsigned int tt = (unsigned int)t;   // a level never has more than 2^31 cells (checked on the host)
+    const unsigned int row = tt / (unsigned int)L.nx;
+    i = (int)(tt - row * (unsigned int)L.nx);
+    k = (int)(row / (unsigned int)L.ny);
+    j = (int)(row - (unsigned int)k * (unsigned int)L.ny);
+}
+
+// index in the NEXT level's vectors of the coarse cell that holds fine cell (i, j, k)
+__device__ __forceinline__ long long mg_coarse_index(const MgLevel &L, const MgLevel &Lc, int i, int j, int k)
+{
+    const int I = L.cx ? (i >> 1) : i, J = L.cy ? (j >> 1) : j, K = L.cz ? (k >> 1) : k;
+    return Lc.base + I + (long long)Lc.px * J + Lc.plane * K;
+}
+
+// first Chebyshev step from a zero guess: d = (1/theta) D^-1 b   (x stays implicit zero)
+__global__ void __launch_bounds__(256) k_mg_cheb_first(MgLevel L, const double *b, double *dout, double inv_theta,
+                                                       const DevState *st)
+{
+    if (st->done) return;
+    const long long n = (long long)L.nx * L.ny * L.nz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+    {
+        int i, j, k;
+        mg_cell(L, t, i, j, k);
+        const MgRow r = mg_row(L, i, j, k);
+        dout[r.j[3]] = r.c[3] != 0.0 ? inv_theta * (b[r.j[3]] / r.c[3]) : 0.0;
+    }
+}
+
+// one Chebyshev step: the iterate is v = x + d (+ P e_c);  r = b - A v;  d' = c1 d + c2 D^-1 r;
+//   x' = v          (d' still to be added by the next pass), or
+//   x' = v + d'     when LAST (nothing follows).
+// XZERO / DZERO: x / d is implicitly zero (not read).  PROLONG: the coarse-grid correction e_c of the next level is
+// added on the fly (piecewise-constant prolongation folded into the first post-smoothing step).
+template <bool XZERO, bool DZERO, bool PROLONG, bool LAST>
+__global__ void __launch_bounds__(256) k_mg_cheb_step(MgLevel L, MgLevel Lc, const double *b, const double *xin,
+                                                      const double *din, const double *ec, double *xout, double *dout,
+                                                      double c1, double c2, const DevState *st)
+{
+    if (st->done) return;
+    const long long n = (long long)L.nx * L.ny * L.nz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+    {
+        int i, j, k;
+        mg_cell(L, t, i, j, k);
+        const MgRow r = mg_row(L, i, j, k);
+        long long cj[7];
+        if (PROLONG)
+        {
+            cj[3] = mg_coarse_index(L, Lc, i, j, k);
+            cj[2] = mg_coarse_index(L, Lc, r.im, j, k);
+            cj[4] = mg_coarse_index(L, Lc, r.ip, j, k);
+            cj[1] = mg_coarse_index(L, Lc, i, r.jm, k);
+            cj[5] = mg_coarse_index(L, Lc, i, r.jp, k);
+            cj[0] = mg_coarse_index(L, Lc, i, j, r.km);
+            cj[6] = mg_coarse_index(L, Lc, i, j, r.kp);
+        }
+        auto val = [&](int q) {
+            double v = 0.0;
+            if (!XZERO) v = xin[r.j[q]];
+            if (!DZERO) v += din[r.j[q]];
+            if (PROLONG) v += ec[cj[q]];
+            return v;
+        };
+        const double vc = val(3);
+        const double res = b[r.j[3]] - mg_apply(r, val);
+        const double dold = DZERO ? 0.0 : din[r.j[3]];
+        const double dnew = r.c[3] != 0.0 ? c1 * dold + c2 * (res / r.c[3]) : 0.0;
+        xout[r.j[3]] = LAST ? vc + dnew : vc;
+        if (!LAST) dout[r.j[3]] = dnew;
+    }
+}
+
+// residual + restriction: v = x + d is materialised (xsum), b_c(I,J,K) = sum over the merged fine cells of (b - A v).
+// One thread per COARSE cell.
+template <bool XZERO>
+__global__ void __launch_bounds__(256) k_mg_restrict(MgLevel L, MgLevel Lc, const double *b, const double *xin, const double *din,
+                                                     double *xsum, double *bc, const DevState *st)
+{
+    if (st->done) return;
+    const long long nc = (long long)Lc.nx * Lc.ny * Lc.nz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nc; t += (long long)gridDim.x * blockDim.x)
+    {
+        int I, J, K;
+        mg_cell(Lc, t, I, J, K);
+        const int i0 = L.cx ? 2 * I : I, i1 = L.cx ? min(2 * I + 1, L.nx - 1) : I;
+        const int j0 = L.cy ? 2 * J : J, j1 = L.cy ? min(2 * J + 1, L.ny - 1) : J;
+        const int k0 = L.cz ? 2 * K : K, k1 = L.cz ? min(2 * K + 1, L.nz - 1) : K;
+        double acc = 0.0;
+        for (int k = k0; k <= k1; ++k)
+            for (int j = j0; j <= j1; ++j)
+                for (int i = i0; i <= i1; ++i)
+                {
+                    const MgRow r = mg_row(L, i, j, k);
+                    auto val = [&](int q) { return XZERO ? din[r.j[q]] : xin[r.j[q]] + din[r.j[q]]; };
+                    xsum[r.j[3]] = val(3);
+                    acc += b[r.j[3]] - mg_apply(r, val);
+                }
+        bc[Lc.base + I + (long long)Lc.px * J + Lc.plane * K] = acc;
+    }
+}
+
+// PCG with an explicit z = M^-1 r: the residual update on its own (the sums need z, which the cycle produces next)
+__global__ void __launch_bounds__(256) k_mg_rupdate(long long n, double *r, const double *w, const DevState *st)
+{
+    if (st->done) return;
+    const double ma = -st->a;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        r[t] = __dadd_rn(r[t], __dmul_rn(ma, w[t]));  // VecAXPY(R, -a, W)
+}
+
+// the sums of k_update2 for z given as a vector: {sum z, sum d, sum d^2, sum d r, sum r, sum r^2}, d = z - c
+__global__ void __launch_bounds__(256) k_mg_zsums(MgLevel L, const double *z, const double *r, int fin_kind, ReduceWs ws, CommDev cm,
+                                                  DevState *st, SolveConsts kc, double *hist)
+{
+    if (st->done) return;
+    const double c = st->c;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    const long long n = (long long)L.nx * L.ny * L.nz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+    {
+        int i, j, k;
+        mg_cell(L, t, i, j, k);
+        const long long idx = L.base + i + (long long)L.px * j + L.plane * k;
+        const double z0 = z[idx], rn = r[idx];
+        const double d0 = z0 - c;
+        acc[0] += z0;
+        acc[1] += d0;
+        acc[2] = fma(d0, d0, acc[2]);
+        acc[3] = fma(d0, rn, acc[3]);
+        acc[4] += rn;
+        acc[5] = fma(rn, rn, acc[5]);
+    }
+    grid_reduce_finalize<6>(acc, fin_kind, ws, cm, st, kc, hist, false);
+}
+
+}  // namespace b200

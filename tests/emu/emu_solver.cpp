@@ -11,6 +11,8 @@
 #include "spmv3.cuh"
 #include "csr_kernels.cuh"
 #include "sep_kernels.cuh"
+#include "mg_kernels.cuh"
+#include "mg_schedule.h"
 
 using namespace b200;
 
@@ -551,6 +553,155 @@ EMU_API int emu_sep_solve(int nfields, const int64_t *dims, const int *periodic,
         emu::launch(dim3(1), dim3(256), 0, [&] { k_xtail(g1, x.data(), p0.data(), p1.data(), &st); });
     }
     memcpy(x_out, x.data(), sizeof(double) * (size_t)n);
+    *nhist = st.nhist;
+    *its = st.its;
+    *reason = st.reason;
+    return st.done ? 0 : 1;
+}
+
+}  // extern "C"
+
+// ---- geometric multigrid preconditioner (mg_kernels.cuh) through the SHARED schedule of mg_schedule.h: the launcher
+// below runs the kernels under the emulation instead of enqueueing them on a stream (MgCudaLauncher in mg_solver.inc).
+namespace {
+struct MgEmu
+{
+    std::vector<MgHostLevel> host;
+    std::vector<MgLevel> dev;
+    std::vector<std::vector<double>> axes;
+    std::vector<std::vector<std::vector<double>>> bufs;
+    MgParams prm;
+    DevState *st = nullptr;
+    int blocks = 3;
+    void first(int l, const double *b, double *dout, double inv_theta)
+    {
+        const MgLevel L = dev[(size_t)l];
+        emu::launch(dim3(blocks), dim3(256), 0, [&] { k_mg_cheb_first(L, b, dout, inv_theta, st); });
+    }
+    void step(int l, bool xzero, bool, bool prolong, bool last, const double *b, const double *xin, const double *din,
+              const double *ec, double *xout, double *dout, double c1, double c2)
+    {
+        const MgLevel L = dev[(size_t)l], Lc = dev[(size_t)std::min<int>(l + 1, (int)dev.size() - 1)];
+#define EMU_MG(XZ, DZ, PR, LA) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_mg_cheb_step<XZ, DZ, PR, LA>(L, Lc, b, xin, din, ec, xout, dout, c1, c2, st); })
+        if (prolong) { if (last) EMU_MG(false, true, true, true); else EMU_MG(false, true, true, false); }
+        else if (xzero) { if (last) EMU_MG(true, false, false, true); else EMU_MG(true, false, false, false); }
+        else { if (last) EMU_MG(false, false, false, true); else EMU_MG(false, false, false, false); }
+#undef EMU_MG
+    }
+    void restrict(int l, bool xzero, const double *b, const double *xin, const double *din, double *xsum, double *bc)
+    {
+        const MgLevel L = dev[(size_t)l], Lc = dev[(size_t)l + 1];
+        if (xzero) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_mg_restrict<true>(L, Lc, b, xin, din, xsum, bc, st); });
+        else emu::launch(dim3(blocks), dim3(256), 0, [&] { k_mg_restrict<false>(L, Lc, b, xin, din, xsum, bc, st); });
+    }
+    double *cycle(const double *r)
+    {
+        const int nl = (int)dev.size();
+        double *work[32][4];
+        double *rhs[32];
+        for (int l = 0; l < nl; ++l)
+        {
+            for (int q = 0; q < 4; ++q) work[l][q] = bufs[(size_t)l][(size_t)q].data();
+            rhs[l] = l > 0 ? bufs[(size_t)l][4].data() : nullptr;
+        }
+        return mg_cycle(0, nl, r, work, rhs, prm, *this);
+    }
+};
+
+void mg_setup(MgEmu &M, const Problem &P, int dim, const int64_t *n, double dt, int max_levels, int smooth_its, int coarse_its)
+{
+    const GridDev &g = P.g;
+    const int64_t n3[3] = {n[0], n[1], dim == 3 ? n[2] : 1};
+    std::vector<double> dx(g.dx, g.dx + n3[0]), dy(g.dy, g.dy + n3[1]), dz(g.dz, g.dz + n3[2]);
+    std::vector<double> gx(g.gx, g.gx + n3[0] + 1), gy(g.gy, g.gy + n3[1] + 1), gz(g.gz, g.gz + n3[2] + 1);
+    M.host = mg_build_hierarchy(n3, P.per, dx, dy, dz, gx, gy, gz, dt, max_levels);
+    const size_t nl = M.host.size();
+    M.dev.resize(nl);
+    M.axes.resize(nl);
+    M.bufs.resize(nl);
+    for (size_t l = 0; l < nl; ++l)
+    {
+        const MgHostLevel &H = M.host[l];
+        MgLevel &D = M.dev[l];
+        D.nx = H.n[0]; D.ny = H.n[1]; D.nz = H.n[2];
+        D.perx = H.per[0]; D.pery = H.per[1]; D.perz = H.per[2];
+        D.cx = H.coarsen[0]; D.cy = H.coarsen[1]; D.cz = H.coarsen[2];
+        size_t elems;
+        if (l == 0)
+        {
+            D.px = g.px; D.plane = g.plane; D.base = g.plane;
+            D.dx = g.dx; D.dy = g.dy; D.dz = g.dz; D.gx = g.gx; D.gy = g.gy; D.gz = g.gz;
+            elems = P.vec_elems;
+        }
+        else
+        {
+            D.px = D.nx; D.plane = (long long)D.nx * D.ny; D.base = 0;
+            size_t off[6];
+            const std::vector<double> *parts[6] = {&H.d[0], &H.d[1], &H.d[2], &H.g[0], &H.g[1], &H.g[2]};
+            for (int q = 0; q < 6; ++q)
+            {
+                off[q] = M.axes[l].size();
+                M.axes[l].insert(M.axes[l].end(), parts[q]->begin(), parts[q]->end());
+            }
+            const double *base = M.axes[l].data();
+            D.dx = base + off[0]; D.dy = base + off[1]; D.dz = base + off[2];
+            D.gx = base + off[3]; D.gy = base + off[4]; D.gz = base + off[5];
+            elems = (size_t)H.cells();
+        }
+        M.bufs[l].assign(5, std::vector<double>(elems, 0.0));
+    }
+    M.prm.smooth_its = smooth_its;
+    M.prm.coarse_its = coarse_its;
+}
+}  // namespace
+
+extern "C" {
+
+// mode 0: x_out = M^-1 b (one V-cycle);  mode 1: KSPSolve_CG preconditioned with the V-cycle (solve_stencil_pcg_mg)
+EMU_API int emu_mg(int dim, const int64_t *n, const int *per, const double *dx, const double *dy, const double *dz, double dt,
+                   int mode, int has_const, double rtol, double atol, int max_it, int max_levels, int smooth_its, int coarse_its,
+                   int tile, const double *b, double *x_out, double *hist, int hist_cap, int *nhist, int *its, int *reason,
+                   int *nlevels)
+{
+    Problem P;
+    build(P, dim, n, per, dx, dy, dz, dt);
+    Ws W;
+    MgEmu M;
+    mg_setup(M, P, dim, n, dt, max_levels, smooth_its, coarse_its);
+    *nlevels = (int)M.dev.size();
+    const size_t ve = P.vec_elems;
+    std::vector<double> r(ve, 0.0), p0(ve, 0.0), p1(ve, 0.0), w(ve, 0.0), x(ve, 0.0);
+    SolveConsts kc{};
+    kc.rtol = rtol; kc.atol = atol; kc.divtol = 1e4; kc.nglobal = (double)P.nlocal;
+    kc.max_it = max_it; kc.norm_type = 1; kc.has_const = has_const; kc.hist_cap = hist_cap;
+    DevState st{};
+    M.st = &st;
+    emu::launch(dim3(1), dim3(32), 0, [&] { k_state_reset(&st); });
+    emu::launch(dim3(4), dim3(256), 0, [&] { k_scatter(P.g, b, r.data(), x.data()); });
+    double *z = M.cycle(r.data());
+    if (mode == 0)
+    {
+        emu::launch(dim3(4), dim3(256), 0, [&] { k_gather(P.g, z, x_out); });
+        return 0;
+    }
+    auto zsums = [&](int kind) {
+        const MgLevel L0 = M.dev[0];
+        emu::launch(dim3(3), dim3(256), 0, [&] { k_mg_zsums(L0, z, r.data(), kind, W.ws, W.cm, &st, kc, hist); });
+    };
+    if (has_const) zsums(FIN_INIT_CENTRE);
+    zsums(FIN_INIT);
+    double *pp[2] = {p0.data(), p1.data()};
+    const long long nflat = (long long)P.g.plane * P.g.nzl;
+    for (int it = 0; it < max_it + 2 && !st.done; ++it)
+    {
+        VecSet v{z, pp[it & 1], pp[(it & 1) ^ 1], w.data(), x.data(), nullptr};
+        spmv<false, false>(P, tile, v, P.g.nzl, W, &st, kc, hist);
+        emu::launch(dim3(3), dim3(256), 0, [&] { k_mg_rupdate(nflat, r.data() + P.g.plane, w.data() + P.g.plane, &st); });
+        z = M.cycle(r.data());
+        zsums(FIN_UPDATE);
+    }
+    emu::launch(dim3(4), dim3(256), 0, [&] { k_xtail(P.g, x.data(), p0.data(), p1.data(), &st); });
+    emu::launch(dim3(4), dim3(256), 0, [&] { k_gather(P.g, x.data(), x_out); });
     *nhist = st.nhist;
     *its = st.its;
     *reason = st.reason;

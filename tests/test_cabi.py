@@ -98,6 +98,21 @@ def test_unsupported_options_fail_loudly(text):
     assert rc == _lib.ERR_UNSUPPORTED and msg
 
 
+def test_multigrid_options_use_the_pcmg_names():
+    """pc_type mg is an extension of this backend (PetIBM's shipped configs precondition with GAMG / AmgX AMG, which is
+    refused above); it takes PETSc's PCMG option names, and only the combination that is implemented."""
+    rc, o, msg = _parse("-poisson_pc_type mg")
+    assert rc == 0 and o.pc_type == _lib.PC_MG and (o.mg_levels, o.mg_smooth_its, o.mg_coarse_its) == (0, 2, 16), msg
+    rc, o, msg = _parse("-poisson_ksp_type cg\n-poisson_pc_type mg\n-poisson_pc_mg_levels 4\n-poisson_mg_levels_ksp_type chebyshev\n"
+                        "-poisson_mg_levels_ksp_max_it 3\n-poisson_mg_levels_pc_type jacobi\n-poisson_mg_coarse_ksp_max_it 24\n"
+                        "-poisson_pc_mg_cycle_type v\n")
+    assert rc == 0 and (o.pc_type, o.mg_levels, o.mg_smooth_its, o.mg_coarse_its) == (_lib.PC_MG, 4, 3, 24), msg
+    for bad in ("-poisson_mg_levels_pc_type sor", "-poisson_pc_mg_cycle_type w", "-poisson_mg_coarse_ksp_type preonly",
+                "-poisson_pc_mg_galerkin"):
+        rc, _, msg = _parse(bad)
+        assert rc == _lib.ERR_UNSUPPORTED and msg
+
+
 @pytest.mark.parametrize("text", ["-poisson_ksp_rtol abc", "-poisson_ksp_max_it", "stray -poisson_ksp_type cg"])
 def test_malformed_options(text):
     rc, _, msg = _parse(text)

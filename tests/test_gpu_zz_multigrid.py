@@ -1,0 +1,97 @@
+"""GPU checks of the geometric multigrid preconditioner (-<name>_pc_type mg; mg_kernels.cuh): the device cycle against
+the independent numpy/scipy restatement (tests/mg_reference.py), preconditioned-CG histories, and the point of it --
+the same converged solution as plain CG on the same library in a fraction of the iterations.  The same kernel sources
+run on the CPU emulation in tests/test_emulated_mg.py."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests import helpers as H
+from tests import mg_reference as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import petibm_b200
+
+    return petibm_b200
+
+
+def _solver(pb, widths, per, **opts):
+    s = pb.LinSolverB200("poisson", "None")
+    s.setOptions(pc_type="mg", **opts)
+    s.setStencil(H.grid_of(widths, per))
+    s.setNullSpace(True)
+    return s
+
+
+@pytest.mark.parametrize("shape,per", [((32, 24, 16), (0, 0, 0)), ((20, 32, 24), (1, 0, 1)), ((70, 45), (0, 0)), ((33, 40), (1, 1)),
+                                       ((31, 17, 13), (0, 0, 0))])
+def test_pcg_with_multigrid_matches_the_restatement(pb, shape, per):
+    widths = H.make_widths(shape)
+    A = H.oracle_matrix(widths, per)
+    b, xs = H.consistent_rhs(A)
+    V = R.VCycle(widths, per, 0.01)
+    nit = 6
+    xr, hr, _, _ = R.pcg(A.to_scipy(), b, V.apply, True, 0.0, 0.0, nit)
+    s = _solver(pb, widths, per, rtol=0.0, atol=0.0, max_it=nit)
+    x = np.empty_like(b)
+    with pytest.raises(pb.B200Error):
+        s.solve(x, b)                              # DIVERGED_ITS after the fixed number of iterations, like KSP
+    assert (s.getIters(), s.getReason()) == (nit, -3)
+    np.testing.assert_allclose(s.getHistory(), hr, rtol=1e-8)
+    np.testing.assert_allclose(x, xr, rtol=0, atol=1e-9 * np.abs(xr).max())
+    # to convergence, against plain CG of the same library
+    s.setOptions(rtol=1e-10, atol=1e-50, max_it=200)
+    s.solve(x, b)
+    its_mg = s.getIters()
+    assert s.getReason() == 2
+    p = pb.LinSolverB200("poisson", "None")
+    p.setOptions(rtol=1e-10, atol=1e-50, max_it=5000)
+    p.setStencil(H.grid_of(widths, per))
+    p.setNullSpace(True)
+    xp = np.empty_like(b)
+    p.solve(xp, b)
+    assert p.getReason() == 2 and its_mg <= 25 and 3 * its_mg <= p.getIters(), (its_mg, p.getIters())
+    np.testing.assert_allclose(x, xs, rtol=0, atol=1e-7 * np.abs(xs).max())
+    np.testing.assert_allclose(x, xp, rtol=0, atol=1e-7 * np.abs(xs).max())
+    hist = s.getHistory()
+    assert np.all(np.diff(np.log(hist)) < 0)
+    s.destroy(); p.destroy()
+
+
+def test_multigrid_through_the_options_file_and_on_128_cubed(pb, tmp_path):
+    cfg = tmp_path / "poisson_solver.info"
+    cfg.write_text("-poisson_ksp_type cg\n-poisson_pc_type mg\n-poisson_mg_levels_ksp_max_it 2\n-poisson_ksp_rtol 1e-8\n"
+                   "-poisson_ksp_atol 1e-50\n-poisson_ksp_max_it 100\n")
+    s = pb.LinSolverB200("poisson", str(cfg))
+    assert s.options().pc_type == 2
+    grid = pb.Grid.uniform((128, 128, 128), dt=0.01)
+    s.setStencil(grid)
+    s.setNullSpace(True)
+    rng = np.random.default_rng(3)
+    xs = rng.standard_normal(grid.size)
+    xs -= xs.mean()
+    b = s.apply(xs)
+    x = np.empty_like(b)
+    s.solve(x, b)
+    assert s.getReason() == 2 and s.getIters() <= 20, s.getIters()      # grid-independent: ~11 at 32^3 and 64^3 as well
+    res = s.apply(x) - b
+    assert np.linalg.norm(res) <= 1e-6 * np.linalg.norm(b)
+    np.testing.assert_allclose(x - x.mean(), xs, rtol=0, atol=1e-6 * np.abs(xs).max())
+    s.destroy()
+
+
+def test_multigrid_needs_the_separable_operator(pb):
+    shape, per = (9, 8, 7), (0, 0, 0)
+    A = H.oracle_matrix(H.make_widths(shape), per)
+    s = pb.LinSolverB200("poisson", "None")
+    s.setOptions(pc_type="mg")
+    s.setMatrix(H.mat_of(A))                      # no grid description: the matrix is kept as CSR
+    assert s.operator == "csr"
+    with pytest.raises(pb.B200Error) as ei:
+        s.solve(np.empty(A.shape[0]), np.ones(A.shape[0]))
+    assert ei.value.code == -3
+    s.destroy()
