@@ -1190,7 +1190,10 @@ int b200ls_set_options(b200ls_solver *h, const b200ls_options *o)
 {
     if (!h || !o) return B200LS_ERR_ARG;
     if (o->ksp_type != B200LS_KSP_CG && o->ksp_type != B200LS_KSP_BCGS) return fail(h, B200LS_ERR_UNSUPPORTED, "ksp_type %d", o->ksp_type);
-    if (o->pc_type != B200LS_PC_NONE && o->pc_type != B200LS_PC_JACOBI) return fail(h, B200LS_ERR_UNSUPPORTED, "pc_type %d", o->pc_type);
+    if (o->pc_type != B200LS_PC_NONE && o->pc_type != B200LS_PC_JACOBI && o->pc_type != B200LS_PC_MG)
+        return fail(h, B200LS_ERR_UNSUPPORTED, "pc_type %d", o->pc_type);
+    if (o->pc_type == B200LS_PC_MG && o->ksp_type != B200LS_KSP_CG) return fail(h, B200LS_ERR_UNSUPPORTED, "pc_type mg is used with ksp_type cg");
+    if (o->mg_levels < 0 || o->mg_levels > 32) return fail(h, B200LS_ERR_ARG, "pc_mg_levels %d", o->mg_levels);
     if (o->norm_type < B200LS_NORM_PRECONDITIONED || o->norm_type > B200LS_NORM_NATURAL)
         return fail(h, B200LS_ERR_UNSUPPORTED, "norm_type %d (KSP_NORM_NONE is not supported)", o->norm_type);
     if (o->max_it < 0) return fail(h, B200LS_ERR_ARG, "max_it < 0");
