@@ -197,11 +197,13 @@ class Repart:
         import torch
         import torch.distributed as dist
 
-        out = torch.empty(int(np.sum(recv_counts)), dtype=torch.float64)
         inp = torch.from_numpy(np.ascontiguousarray(send, dtype=np.float64))
-        # PetIBM's shim: MPI_Alltoallv(send, counts, displs, MPI_DOUBLE, recv, counts, displs, MPI_DOUBLE, PETSC_COMM_WORLD)
-        dist.all_to_all_single(out, inp, [int(c) for c in recv_counts], [int(c) for c in send_counts], group=group)
-        return out.numpy()
+        # the harness transport may be NCCL (one process per GPU under torchrun), which only moves device tensors; inside
+        # PetIBM this is MPI_Alltoallv(send, counts, displs, MPI_DOUBLE, recv, counts, displs, MPI_DOUBLE, PETSC_COMM_WORLD)
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        out = torch.empty(int(np.sum(recv_counts)), dtype=torch.float64, device=dev)
+        dist.all_to_all_single(out, inp.to(dev), [int(c) for c in recv_counts], [int(c) for c in send_counts], group=group)
+        return out.cpu().numpy()
 
     def box_to_slab(self, box: np.ndarray, group=None) -> np.ndarray:
         """Box-ordered local vector (PETSc ordering) -> slab-ordered local vector (natural order inside the slab)."""
