@@ -126,6 +126,8 @@ struct b200ls_solver
     MgParams mg_prm;
     bool mg_ready = false;
     int mg_built_levels = 0;
+    int64_t mg_graph_launches = 0;
+    int mg_graph = 0;        // tuning "mg_graph": replay pairs of preconditioned iterations as one CUDA graph (off until timed)
 
     // ---- vectors (solver layout)
     double *arena = nullptr;  // [mailboxes | flags | r]; exported over CUDA IPC
@@ -1221,6 +1223,7 @@ int b200ls_set_tuning(b200ls_solver *h, const char *key, int value)
     else if (k == "upd_reverse") h->upd_reverse = value;
     else if (k == "use_graph") h->use_graph = value;
     else if (k == "use_pdl") h->use_pdl = value;
+    else if (k == "mg_graph") h->mg_graph = value;
     else return fail(h, B200LS_ERR_ARG, "unknown tuning key %s", key);
     invalidate_graph(h);
     return B200LS_OK;
