@@ -123,6 +123,7 @@ struct b200ls_solver
     std::vector<MgLevel> mg_dev;
     std::vector<std::vector<double *>> mg_bufs;  // per level: 4 work vectors (+ the right-hand side of a coarse level)
     std::vector<double *> mg_axes;               // per coarse level: its six 1-D arrays
+    std::vector<int *> mg_maps;                  // per level but the coarsest: fine -> coarse index maps
     MgParams mg_prm;
     bool mg_ready = false;
     int mg_built_levels = 0;

@@ -6,7 +6,9 @@
 // is not an arbitrary sparse matrix but D (dt I) G of a stretched Cartesian grid, fully described by six 1-D arrays,
 // so the hierarchy is GEOMETRIC and matrix-free on every level:
 //
-//   coarsening    cells are merged pairwise per axis (an odd last cell stays alone), widths add up;
+//   coarsening    per axis one or two neighbouring cells form a coarse cell, widths add up; WHICH pairs are merged is
+//                 decided level by level so that the narrowest cells go first (width-equalising coarsening,
+//                 mg_schedule.h: a stretched grid loses its anisotropy on the way down, a uniform one is halved);
 //   operator      the same closed form D (dt I) G on the merged cells (rediscretisation; appendix A.1 of SURVEY.md);
 //   restriction   sum over the merged cells (the rows are volume-integrated divergences), prolongation = its
 //                 transpose (piecewise constant), so the V-cycle is symmetric;
@@ -38,7 +40,10 @@ struct MgLevel
     int px;                   // row pitch of this level's vectors
     long long plane, base;    // plane stride and offset of cell (0,0,0): index = base + i + px*j + plane*k
     int perx, pery, perz;     // periodic axes (index wrap)
-    int cx, cy, cz;           // 1: the axis is coarsened on the way to the next level (cells 2I, 2I+1 -> I)
+    // transition to the next level (null on the coarsest): m?[i] = coarse cell of fine cell i, s?[I] = first fine cell of
+    // coarse cell I (n_coarse + 1 entries); one or two fine cells per coarse cell and axis
+    const int *mx, *my, *mz;
+    const int *sx, *sy, *sz;
     const double *dx, *dy, *dz;  // cell widths
     const double *gx, *gy, *gz;  // face coefficients dt/h, n+1 entries, 0 at walls, wrap value at both ends if periodic
 };
@@ -103,8 +108,7 @@ __device__ __forceinline__ void mg_cell(const MgLevel &L, long long t, int &i, i
 // index in the NEXT level's vectors of the coarse cell that holds fine cell (i, j, k)
 __device__ __forceinline__ long long mg_coarse_index(const MgLevel &L, const MgLevel &Lc, int i, int j, int k)
 {
-    const int I = L.cx ? (i >> 1) : i, J = L.cy ? (j >> 1) : j, K = L.cz ? (k >> 1) : k;
-    return Lc.base + I + (long long)Lc.px * J + Lc.plane * K;
+    return Lc.base + L.mx[i] + (long long)Lc.px * L.my[j] + Lc.plane * L.mz[k];
 }
 
 // first Chebyshev step from a zero guess: d = (1/theta) D^-1 b   (x stays implicit zero)
@@ -178,9 +182,9 @@ __global__ void __launch_bounds__(256) k_mg_restrict(MgLevel L, MgLevel Lc, cons
     {
         int I, J, K;
         mg_cell(Lc, t, I, J, K);
-        const int i0 = L.cx ? 2 * I : I, i1 = L.cx ? min(2 * I + 1, L.nx - 1) : I;
-        const int j0 = L.cy ? 2 * J : J, j1 = L.cy ? min(2 * J + 1, L.ny - 1) : J;
-        const int k0 = L.cz ? 2 * K : K, k1 = L.cz ? min(2 * K + 1, L.nz - 1) : K;
+        const int i0 = L.sx[I], i1 = L.sx[I + 1] - 1;
+        const int j0 = L.sy[J], j1 = L.sy[J + 1] - 1;
+        const int k0 = L.sz[K], k1 = L.sz[K + 1] - 1;
         double acc = 0.0;
         for (int k = k0; k <= k1; ++k)
             for (int j = j0; j <= j1; ++j)

@@ -625,7 +625,12 @@ void mg_setup(MgEmu &M, const Problem &P, int dim, const int64_t *n, double dt, 
         MgLevel &D = M.dev[l];
         D.nx = H.n[0]; D.ny = H.n[1]; D.nz = H.n[2];
         D.perx = H.per[0]; D.pery = H.per[1]; D.perz = H.per[2];
-        D.cx = H.coarsen[0]; D.cy = H.coarsen[1]; D.cz = H.coarsen[2];
+        D.mx = D.my = D.mz = D.sx = D.sy = D.sz = nullptr;
+        if (l + 1 < nl)
+        {
+            D.mx = H.cmap[0].data(); D.my = H.cmap[1].data(); D.mz = H.cmap[2].data();
+            D.sx = H.cstart[0].data(); D.sy = H.cstart[1].data(); D.sz = H.cstart[2].data();
+        }
         size_t elems;
         if (l == 0)
         {

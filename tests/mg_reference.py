@@ -52,9 +52,25 @@ def assemble(d, per, dt, active):
     return A
 
 
-def hierarchy(widths, per, dt, max_levels=0):
-    """Levels [{d, n, A, R}]: axes with at least four cells are merged pairwise (an odd last cell stays alone); R sums the
-    merged cells (restriction), R^T is the prolongation."""
+def merge_map(d, tau):
+    """Greedy pairing from the left: cells i, i+1 form one coarse cell iff d[i] + d[i+1] <= tau."""
+    out, i, I = [], 0, 0
+    while i < len(d):
+        if i + 1 < len(d) and d[i] + d[i + 1] <= tau:
+            out += [I, I]
+            i += 2
+        else:
+            out += [I]
+            i += 1
+        I += 1
+    return np.array(out)
+
+
+def hierarchy(widths, per, dt, max_levels=0, ratio=2.0):
+    """Levels [{d, n, A, R}].  Width-equalising coarsening: on every level the smallest sum of two neighbouring widths
+    over all axes with at least four cells sets the scale; pairs whose merged width is within `ratio` of it are merged,
+    everything wider waits (a uniform grid is halved, a stretched one loses its fine band first).  R sums the merged
+    cells (restriction), R^T is the prolongation."""
     dim = len(widths)
     d = [np.asarray(w, dtype=np.float64) for w in widths] + [np.ones(1)] * (3 - dim)
     per = list(per) + [0] * (3 - len(per))
@@ -65,18 +81,12 @@ def hierarchy(widths, per, dt, max_levels=0):
         n = [len(a) for a in d]
         lev = {"d": d, "n": n, "A": assemble(d, per, dt, active), "R": None}
         levels.append(lev)
-        co = [m >= 4 for m in n]
-        if not any(co) or len(levels) >= cap:
+        cand = [q for q in range(3) if n[q] >= 4]
+        if not cand or len(levels) >= cap:
             break
-        dc, maps = [], []
-        for ax in range(3):
-            if co[ax]:
-                m = (n[ax] + 1) // 2
-                dc.append(np.array([d[ax][2 * I] + (d[ax][2 * I + 1] if 2 * I + 1 < n[ax] else 0.0) for I in range(m)]))
-                maps.append(np.arange(n[ax]) // 2)
-            else:
-                dc.append(d[ax].copy())
-                maps.append(np.arange(n[ax]))
+        tau = ratio * min(float((d[q][:-1] + d[q][1:]).min()) for q in cand)
+        maps = [merge_map(d[q], tau) if q in cand else np.arange(n[q]) for q in range(3)]
+        dc = [np.bincount(maps[q], weights=d[q]) for q in range(3)]       # widths add up
         nc = [len(a) for a in dc]
         K, J, I = np.meshgrid(maps[2], maps[1], maps[0], indexing="ij")
         coarse = (I + nc[0] * (J + nc[1] * K)).ravel()

@@ -66,6 +66,38 @@ def test_emulated_vcycle_matches_the_restatement(emu, shape, per, smooth):
     assert abs(zu @ r - u @ z) <= 1e-10 * abs(zu @ r)
 
 
+def _petibm_like_axis(n_band, n_side, ratio):
+    """Uniform fine band with geometrically stretched cells on both sides, like the axes of the shipped examples
+    (examples/ibpm/cylinder2dRe100_GPU/config.yaml: stretchRatio 1.02 over 125 cells next to a 200-cell band)."""
+    side = [{"end": -0.5, "cells": n_side, "stretchRatio": 1.0 / ratio}, {"end": 0.5, "cells": n_band, "stretchRatio": 1.0},
+            {"end": 6.0, "cells": n_side, "stretchRatio": ratio}]
+    return orc.axis_from_subdomains(-6.0, side)
+
+
+def test_stretched_grid_needs_and_gets_the_width_equalising_coarsening(emu):
+    """Aspect ratios like PetIBM's grids: merging every pair on every axis keeps the anisotropy on all levels and the
+    point smoother stalls; coarsening the narrowest cells first does not.  Checked with the restatement (both rules) and
+    with the emulated kernels (the rule that is built)."""
+    w = _petibm_like_axis(20, 14, 1.25)
+    widths = [w, w.copy()]
+    assert w.max() / w.min() > 15
+    A = H.oracle_matrix(widths, (0, 0))
+    b, xs = H.consistent_rhs(A)
+    As = A.to_scipy()
+    V = R.VCycle(widths, (0, 0), 0.01)
+    _, _, its_eq, reason = R.pcg(As, b, V.apply, True, 1e-8, 0.0, 300)
+    Vp = R.VCycle(widths, (0, 0), 0.01)
+    Vp.levels = R.hierarchy(widths, (0, 0), 0.01, ratio=1e30)      # every pair merges: plain 2:1 coarsening
+    for lev in Vp.levels:
+        dg = lev["A"].diagonal()
+        lev["dinv"] = np.where(dg != 0.0, 1.0 / np.where(dg != 0.0, dg, 1.0), 0.0)
+    _, _, its_pair, _ = R.pcg(As, b, Vp.apply, True, 1e-8, 0.0, 300)
+    assert reason == 2 and its_eq <= 22 and its_pair >= 2 * its_eq, (its_eq, its_pair)
+    x, hist, its, reason, nl = _mg(emu, widths, (0, 0), b, rtol=1e-8, max_it=60)
+    assert reason == 2 and abs(its - its_eq) <= 1 and nl == len(V.levels), (its, its_eq, nl, len(V.levels))
+    np.testing.assert_allclose(x, xs, rtol=0, atol=1e-6 * np.abs(xs).max())
+
+
 @pytest.mark.parametrize("shape,per", [((16, 12, 8), (0, 0, 0)), ((12, 16, 8), (1, 0, 1)), ((24, 20), (0, 0)), ((13, 9, 10), (0, 0, 0))])
 def test_emulated_pcg_history_and_iteration_count(emu, shape, per):
     widths = H.make_widths(shape)
