@@ -39,7 +39,7 @@ inline std::vector<double> mg_faces(const std::vector<double> &d, bool periodic,
 // of two neighbouring widths over all axes that still have at least four cells, a pair (i, i+1) is merged (greedy, left
 // to right) iff d[i] + d[i+1] <= ratio * smin.  A uniform grid is halved on every axis as usual; on a stretched grid the
 // fine band is coarsened first -- in the direction in which its cells are narrow, i.e. strongly coupled -- until the
-// widths have evened out (16 iterations on the same grid at 2.5 x the fine-level work).  The hierarchy stays a tensor
+// widths have evened out (12 iterations on the same grid at 2.5 x the fine-level work).  The hierarchy stays a tensor
 // product of 1-D grids, so every level is still described by six 1-D arrays.
 inline std::vector<MgHostLevel> mg_build_hierarchy(const int64_t n[3], const int per[3], const std::vector<double> &dx,
                                                    const std::vector<double> &dy, const std::vector<double> &dz,
@@ -112,7 +112,7 @@ struct MgParams
     int smooth_its = 2;        // Chebyshev degree before and after the coarse correction
     int coarse_its = 16;       // Chebyshev degree on the coarsest level
     double lmax = 2.0;         // Gershgorin bound of D^-1 A (rows sum to zero)
-    double smooth_ratio = 8.0; // smoothing interval [lmax / ratio, lmax]
+    double smooth_ratio = 5.0; // smoothing interval [lmax / ratio, lmax] (tuned on uniform and PetIBM-like stretched grids)
     double coarse_ratio = 40.0;
 };
 

@@ -120,7 +120,7 @@ def chebyshev(A, dinv, b, x, its, lmax, ratio):
 
 
 class VCycle:
-    def __init__(self, widths, per, dt, max_levels=0, smooth_its=2, coarse_its=16, lmax=2.0, smooth_ratio=8.0, coarse_ratio=40.0):
+    def __init__(self, widths, per, dt, max_levels=0, smooth_its=2, coarse_its=16, lmax=2.0, smooth_ratio=5.0, coarse_ratio=40.0):
         self.levels = hierarchy(widths, per, dt, max_levels)
         for lev in self.levels:
             dg = lev["A"].diagonal()

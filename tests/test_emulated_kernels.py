@@ -19,7 +19,7 @@ EMU = os.path.join(ROOT, "tests", "emu")
 LIB = os.path.join(EMU, "libb200emu.so")
 SRC = [os.path.join(EMU, f) for f in ("emu_solver.cpp", "cuda_emu.h")] + \
       [os.path.join(ROOT, "petibm_b200", "csrc", f) for f in ("kernels.cuh", "spmv2.cuh", "spmv3.cuh", "hw.cuh", "csr_kernels.cuh",
-                                                            "sep_kernels.cuh")]
+                                                            "sep_kernels.cuh", "mg_kernels.cuh", "mg_schedule.h")]
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
