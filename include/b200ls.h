@@ -237,6 +237,20 @@ int b200ls_staggered_analyze(int nfields, const int64_t *dims, const int *period
                              const int32_t *col, const double *val, double *coef, double *diag, int64_t *rem_rowptr,
                              int32_t *rem_col, double *rem_val, char *errbuf, size_t errlen);
 
+/* IBPM's modified Poisson system on a STRETCHED grid: the pressure block is D (dt I) G of the mesh -- its coefficients
+ * carry face areas, so they are not one-dimensional -- followed by the Lagrangian coupling rows/columns.  The block is
+ * checked bitwise against the closed form of b200ls_set_poisson_stencil ((w_a w_b) * (dt * (1/h)), appendix A.1 of
+ * SURVEY.md), the diagonal is taken from the matrix, everything else becomes the CSR remainder; same kernels and
+ * same bit-identical row sums as b200ls_set_staggered.  With -<name>_pc_type mg the pressure block is preconditioned by
+ * the geometric multigrid and the remaining rows by their diagonal.  B200LS_ERR_MISMATCH: the solver is untouched. */
+int b200ls_set_poisson_hybrid(b200ls_solver *h, int dim, const int64_t *n, const int *periodic, const double *dx,
+                              const double *dy, const double *dz, double dt, int64_t nrows, const int64_t *rowptr,
+                              const int32_t *col, const double *val);
+/* g: (nx+1) + (ny+1) + (nz+1) doubles (face arrays), diag: nx*ny*nz; the rest as in b200ls_staggered_analyze. */
+int b200ls_hybrid_analyze(int dim, const int64_t *n, const int *periodic, const double *dx, const double *dy, const double *dz,
+                          double dt, int64_t nrows, const int64_t *rowptr, const int32_t *col, const double *val, double *g,
+                          double *diag, int64_t *rem_rowptr, int32_t *rem_col, double *rem_val, char *errbuf, size_t errlen);
+
 /* Null space attached to the operator: has_const != 0 -> the constant vector
  * (MatNullSpaceCreate(comm, PETSC_TRUE, 0, ...), navierstokes.cpp:404-413); nvecs explicit
  * orthonormal vectors of local length nrows (ibpm.cpp:251-267). */

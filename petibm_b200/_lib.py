@@ -81,6 +81,9 @@ SIGNATURES = {
     "b200ls_staggered_coef_size": (C.c_int64, [C.c_int, _i64p]),
     "b200ls_staggered_analyze": (C.c_int, [C.c_int, _i64p, _ip, C.c_int64, _i64p, _i32p, _dp, _dp, _dp, _i64p, _i32p, _dp,
                                           C.c_char_p, C.c_size_t]),
+    "b200ls_set_poisson_hybrid": (C.c_int, [_vp, C.c_int, _i64p, _ip, _dp, _dp, _dp, C.c_double, C.c_int64, _i64p, _i32p, _dp]),
+    "b200ls_hybrid_analyze": (C.c_int, [C.c_int, _i64p, _ip, _dp, _dp, _dp, C.c_double, C.c_int64, _i64p, _i32p, _dp, _dp, _dp,
+                                       _i64p, _i32p, _dp, C.c_char_p, C.c_size_t]),
     "b200ls_set_nullspace": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
     "b200ls_apply": (C.c_int, [_vp, _vp, _vp]),
     "b200ls_solve": (C.c_int, [_vp, _vp, _vp]),

@@ -113,6 +113,7 @@ struct b200ls_solver
 
     // ---- operator: line-coefficient form of an assembled staggered-grid matrix (single GPU, sep_kernels.cuh)
     SepDev sep{};
+    bool sep_hybrid = false;   // the stencil block is the pressure operator of the mesh (b200ls_set_poisson_hybrid)
     double *d_sep_coef = nullptr, *d_sep_diag = nullptr;
     int64_t *d_rem_rowptr = nullptr;
     int32_t *d_rem_col = nullptr;
@@ -253,6 +254,7 @@ void free_vectors(b200ls_solver *h)
     fr(h->d_col);
     fr(h->d_val);
     fr(h->d_nullvecs);
+    h->sep_hybrid = false;
     fr(h->d_sep_coef);
     fr(h->d_sep_diag);
     fr(h->d_rem_rowptr);

@@ -262,7 +262,7 @@ PetscErrorCode LinSolverB200::setMatrix(const Mat &A)
         //    (cartesianmesh.cpp:251-273: one point fewer than cells along the field's own direction unless periodic)
         //    or the pressure block followed by IBPM's Lagrangian force rows (ibpm.cpp:164-194).  The structure is read
         //    out of A and verified against every entry by b200ls_set_staggered.
-        bool staggered = false;
+        bool staggered = false, hybrid = false;
         if (haveGrid)
         {
             const int64_t n3[3] = {gn[0], gn[1], gdim == 3 ? gn[2] : 1};
@@ -284,12 +284,19 @@ PetscErrorCode LinSolverB200::setMatrix(const Mat &A)
             if (velOk && (int64_t)nloc == velTotal)
                 rc = b200ls_set_staggered(handle, (int)gdim, vel, gper, nloc, rowptr.data(), col.data(), val.data());
             if (rc == B200LS_ERR_MISMATCH && (int64_t)nloc > pN)
+            {
+                // IBPM: the pressure operator of the mesh (stretched grid: coefficients with face areas) + coupling rows
+                rc = b200ls_set_poisson_hybrid(handle, (int)gdim, gn, gper, gdL[0].data(), gdL[1].data(),
+                                               gdim == 3 ? gdL[2].data() : nullptr, gdt, nloc, rowptr.data(), col.data(), val.data());
+                if (rc == B200LS_OK) hybrid = true;
+            }
+            if (rc == B200LS_ERR_MISMATCH && (int64_t)nloc > pN)
                 rc = b200ls_set_staggered(handle, 1, n3, gper, nloc, rowptr.data(), col.data(), val.data());
             if (rc == B200LS_OK) staggered = true;
             else if (rc != B200LS_ERR_MISMATCH) B200CHK(handle, rc);
         }
         if (staggered)
-            opKind = "staggered";
+            opKind = hybrid ? "hybrid" : "staggered";
         else
         {
             // 3. verified fallback: the assembled operator itself, still on the GPU (BN order > 1, anything else)

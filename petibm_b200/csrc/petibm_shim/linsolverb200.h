@@ -50,8 +50,8 @@ public:
     PetscErrorCode getIters(PetscInt &iters) override;
     PetscErrorCode getResidual(PetscReal &res) override;
 
-    /** "stencil" (matrix-free separable pressure operator verified against A), "staggered" (line-coefficient form
-     *  read out of A: velocity system, IBPM modified Poisson) or "csr". */
+    /** "stencil" (matrix-free separable pressure operator verified against A), "hybrid" (that operator followed by
+     *  IBPM's coupling rows), "staggered" (line-coefficient form read out of A: velocity system) or "csr". */
     const std::string &getOperatorKind() const { return opKind; }
 
 protected:

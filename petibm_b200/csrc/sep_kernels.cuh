@@ -5,7 +5,8 @@
 // navierstokes.cpp:342-344 / createlaplacian.cpp:134-159; or the pressure block of IBPM's modified Poisson
 // system, ibpm.cpp:100-203), each a 5-/7-point stencil whose off-diagonal coefficient in direction d depends
 // only on the index along d (two 1-D arrays per field and direction), the diagonal as a vector, and a CSR
-// remainder for everything behind the stencil blocks (IBPM's Lagrangian coupling).  A row costs
+// remainder for everything behind the stencil blocks (IBPM's Lagrangian coupling); on a stretched grid the pressure
+// block of IBPM's system carries face areas on top of the 1-D face arrays (SepField::w).  A row costs
 // 8 (x) + 8 (diag) + 8 (y) bytes of HBM traffic instead of ~100 for the assembled CSR row; the terms are added
 // in ascending column order without FMA contraction, so the result is bit-identical to MatMult_SeqAIJ on the
 // assembled matrix (the remainder columns all lie behind the stencil columns of their row).
@@ -26,6 +27,10 @@ struct SepField
     long long off;             // first row of the field in the packed vector
     const double *cm[3];       // coefficient of the minus neighbour in direction d at index s (0: no entry)
     const double *cp[3];       // plus neighbour
+    // non-null: the block is the pressure operator D (dt I) G of a stretched grid (IBPM's modified Poisson system): the
+    // coefficient in direction d is (product of the two OTHER cell widths) * cm/cp, with cm/cp the face arrays dt/h --
+    // the grouping of the assembled matrix (createdivergence.cpp:142,146,150)
+    const double *w[3];
 };
 
 struct SepDev
@@ -58,9 +63,20 @@ __device__ __forceinline__ double sep_row(const SepDev &A, long long i, Fetch fe
         const int i2 = (int)(row1 / n1);
         const int i1 = (int)(row1 - (long long)i2 * n1);
         const long long s1 = n0, s2 = (long long)n0 * n1;
-        const double cxm = f.cm[0][i0], cxp = f.cp[0][i0];
-        const double cym = f.cm[1][i1], cyp = f.cp[1][i1];
-        const double czm = f.cm[2][i2], czp = f.cp[2][i2];
+        double cxm = f.cm[0][i0], cxp = f.cp[0][i0];
+        double cym = f.cm[1][i1], cyp = f.cp[1][i1];
+        double czm = f.cm[2][i2], czp = f.cp[2][i2];
+        if (f.w[0])
+        {
+            const double dxi = f.w[0][i0], dyj = f.w[1][i1], dzk = f.w[2][i2];
+            const double ayz = __dmul_rn(dyj, dzk), axz = __dmul_rn(dxi, dzk), axy = __dmul_rn(dxi, dyj);
+            cxm = __dmul_rn(ayz, cxm);
+            cxp = __dmul_rn(ayz, cxp);
+            cym = __dmul_rn(axz, cym);
+            cyp = __dmul_rn(axz, cyp);
+            czm = __dmul_rn(axy, czm);
+            czp = __dmul_rn(axy, czp);
+        }
         const bool xlo = f.per0 && i0 == 0, xhi = f.per0 && i0 == n0 - 1;
         const bool ylo = f.per1 && i1 == 0, yhi = f.per1 && i1 == n1 - 1;
         const bool zlo = f.per2 && i2 == 0, zhi = f.per2 && i2 == n2 - 1;
@@ -161,6 +177,54 @@ __global__ void __launch_bounds__(256) k_sep_bcgs_spmv2(SepDev A, const double *
         acc[2] = fma(si, si, acc[2]);
     }
     csr_reduce_finalize<3>(acc, FIN_BCGS_OMEGA, ws, st, kc, hist);
+}
+
+// ---- preconditioned CG with an explicit z0 = M^-1 r (pc_type mg on the hybrid operator: multigrid on the pressure block,
+// diagonal scaling on the rows behind it).  k_sep_cg_spmv is used unchanged with r := z0 and JACOBI = false; the update
+// kernel of the CSR path is split into k_mg_rupdate (r -= a w), the preconditioner, and these sums.
+
+// the rows behind the stencil block: z0 = D^-1 r
+__global__ void __launch_bounds__(256) k_sep_tail_pc(long long nsep, long long nrows, const double *r, const double *dinv,
+                                                     double *z0, const DevState *st)
+{
+    if (st->done) return;
+    for (long long i = nsep + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nrows; i += (long long)gridDim.x * blockDim.x)
+        z0[i] = __dmul_rn(r[i], dinv[i]);
+}
+
+// the six sums of k_csr_cg_update for z0 given as a vector
+template <int NULLMODE>
+__global__ void __launch_bounds__(256) k_sep_zsums(long long n, const double *z0v, const double *r, const double *nv, int fin_kind,
+                                                   ReduceWs ws, DevState *st, SolveConsts kc, double *hist)
+{
+    if (st->done) return;
+    const double c = st->c;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    {
+        const double z0 = z0v[i], rn = r[i];
+        if (NULLMODE == 2)
+        {
+            const double nvi = nv[i];
+            acc[0] = fma(z0, nvi, acc[0]);
+            acc[1] = fma(z0, z0, acc[1]);
+            acc[2] = fma(z0, rn, acc[2]);
+            acc[3] = fma(nvi, rn, acc[3]);
+            acc[4] = fma(nvi, nvi, acc[4]);
+            acc[5] = fma(rn, rn, acc[5]);
+        }
+        else
+        {
+            const double d0 = z0 - c;
+            acc[0] += z0;
+            acc[1] += d0;
+            acc[2] = fma(d0, d0, acc[2]);
+            acc[3] = fma(d0, rn, acc[3]);
+            acc[4] += rn;
+            acc[5] = fma(rn, rn, acc[5]);
+        }
+    }
+    csr_reduce_finalize<6>(acc, fin_kind, ws, st, kc, hist);
 }
 
 }  // namespace b200

@@ -108,7 +108,7 @@ class LinSolverB200(LinSolverBase):
         self._procs = None     # DMDA process grid, if the caller knows it (setProcessGrid)
         self._repart = None    # box <-> slab exchange plan when the vectors arrive as DMDA boxes
         self._staggered = True # setMatrix may use the line-coefficient form for velocity / IBPM matrices
-        self.operator = None   # "stencil" | "staggered" | "csr" after setMatrix
+        self.operator = None   # "stencil" | "hybrid" | "staggered" | "csr" after setMatrix
         if device is None:
             device = comm.device if comm is not None else 0
         _lib.check(self._L.b200ls_create(C.byref(self._h), int(device)))
@@ -264,7 +264,30 @@ class LinSolverB200(LinSolverBase):
             out.append([n])
         return out, per
 
+    def _try_hybrid(self, A: Mat) -> bool:
+        """IBPM's modified Poisson system: the pressure operator of the mesh (stretched grid: coefficients with face areas)
+        followed by the Lagrangian coupling (b200ls_set_poisson_hybrid)."""
+        g = self._grid
+        if A.nrows <= g.size:
+            return False
+        n = (C.c_int64 * 3)(*(list(g.n) + [1] * (3 - g.dim)))
+        per = (C.c_int * 3)(*[int(bool(p)) for p in g.periodic][:3])
+        w = [np.ascontiguousarray(a, dtype=np.float64) for a in g.widths]
+        dz = w[2].ctypes.data_as(_lib._dp) if g.dim == 3 else None
+        rc = self._L.b200ls_set_poisson_hybrid(self._h, g.dim, n, per, w[0].ctypes.data_as(_lib._dp), w[1].ctypes.data_as(_lib._dp),
+                                               dz, float(g.dt), A.nrows, A.indptr.ctypes.data_as(_lib._i64p),
+                                               A.indices.ctypes.data_as(_lib._i32p), A.data.ctypes.data_as(_lib._dp))
+        if rc == _lib.OK:
+            self.operator = "hybrid"
+            self.nlocal = A.nrows
+            return True
+        if rc != _lib.ERR_MISMATCH:
+            _lib.check(rc, self._h)
+        return False
+
     def _try_staggered(self, A: Mat) -> bool:
+        if self._try_hybrid(A):
+            return True
         layouts, per = self._staggered_layouts(A.nrows)
         for dims in layouts:
             d = np.ascontiguousarray(dims, dtype=np.int64).reshape(-1)

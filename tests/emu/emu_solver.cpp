@@ -460,13 +460,12 @@ EMU_API int emu_csr_solve(int64_t n, const int64_t *rowptr, const int32_t *col, 
 
 // ---- line-coefficient operator (sep_kernels.cuh): same Krylov drivers as emu_csr_solve with the row product swapped.
 // The structure comes from b200ls_staggered_analyze (host code of libb200ls.so), passed in as plain arrays.
-EMU_API int emu_sep_solve(int nfields, const int64_t *dims, const int *periodic, int64_t n, const double *coef, const double *diag,
-                          const int64_t *rem_rowptr, const int32_t *rem_col, const double *rem_val, const double *dinv_in,
-                          int mode /* 0 apply, 1 cg, 2 bcgs */, int jacobi, int has_const, const double *nullvec, double rtol,
-                          double atol, int max_it, const double *b, double *x_out, double *hist, int hist_cap, int *nhist,
-                          int *its, int *reason)
+}  // extern "C"
+
+namespace {
+SepDev make_sep(int nfields, const int64_t *dims, const int *periodic, const double *widths, int64_t n, const double *coef,
+                const double *diag, const int64_t *rem_rowptr, const int32_t *rem_col, const double *rem_val)
 {
-    Ws W;
     SepDev A{};
     A.nf = nfields;
     A.nrows = n;
@@ -479,11 +478,24 @@ EMU_API int emu_sep_solve(int nfields, const int64_t *dims, const int *periodic,
         F.per0 = periodic[0] && F.n0 >= 3; F.per1 = periodic[1] && F.n1 >= 3; F.per2 = periodic[2] && F.n2 >= 3;
         F.off = off;
         off += (long long)F.n0 * F.n1 * F.n2;
+        long long wpos = 0;
         for (int d = 0; d < 3; ++d)
         {
-            F.cm[d] = coef + cpos;
-            F.cp[d] = coef + cpos + dims[3 * f + d];
-            cpos += 2 * dims[3 * f + d];
+            if (widths)
+            {
+                F.w[d] = widths + wpos;
+                F.cm[d] = coef + cpos;
+                F.cp[d] = coef + cpos + 1;
+                wpos += dims[3 * f + d];
+                cpos += dims[3 * f + d] + 1;
+            }
+            else
+            {
+                F.w[d] = nullptr;
+                F.cm[d] = coef + cpos;
+                F.cp[d] = coef + cpos + dims[3 * f + d];
+                cpos += 2 * dims[3 * f + d];
+            }
         }
     }
     A.nsep = off;
@@ -493,6 +505,22 @@ EMU_API int emu_sep_solve(int nfields, const int64_t *dims, const int *periodic,
         A.rem_col = rem_col;
         A.rem_val = rem_val;
     }
+    return A;
+}
+}  // namespace
+
+extern "C" {
+
+// widths != nullptr: "hybrid" form (b200ls_set_poisson_hybrid) -- one field, coef = face arrays gx (n0+1) | gy | gz,
+// widths = dx | dy | dz, coefficient = (product of the two other widths) * g
+EMU_API int emu_sep_solve(int nfields, const int64_t *dims, const int *periodic, const double *widths, int64_t n, const double *coef, const double *diag,
+                          const int64_t *rem_rowptr, const int32_t *rem_col, const double *rem_val, const double *dinv_in,
+                          int mode /* 0 apply, 1 cg, 2 bcgs */, int jacobi, int has_const, const double *nullvec, double rtol,
+                          double atol, int max_it, const double *b, double *x_out, double *hist, int hist_cap, int *nhist,
+                          int *its, int *reason)
+{
+    Ws W;
+    const SepDev A = make_sep(nfields, dims, periodic, widths, n, coef, diag, rem_rowptr, rem_col, rem_val);
     const int blocks = 3;
     if (mode == 0)
     {
@@ -707,6 +735,104 @@ EMU_API int emu_mg(int dim, const int64_t *n, const int *per, const double *dx, 
     }
     emu::launch(dim3(4), dim3(256), 0, [&] { k_xtail(P.g, x.data(), p0.data(), p1.data(), &st); });
     emu::launch(dim3(4), dim3(256), 0, [&] { k_gather(P.g, x.data(), x_out); });
+    *nhist = st.nhist;
+    *its = st.its;
+    *reason = st.reason;
+    return st.done ? 0 : 1;
+}
+
+// KSPSolve_CG on the hybrid operator preconditioned with diag(V-cycle on the pressure block, 1/diag behind it): mirrors
+// sep_pcg_mg of mg_solver.inc.  widths = dx | dy | dz, coef = gx | gy | gz of the pressure grid.
+EMU_API int emu_hybrid_mg_pcg(int dim, const int64_t *n3, const int *periodic, const double *widths, double dt, int64_t n,
+                              const double *coef, const double *diag, const int64_t *rem_rowptr, const int32_t *rem_col,
+                              const double *rem_val, const double *dinv, int has_const, const double *nullvec, double rtol,
+                              double atol, int max_it, int smooth_its, int coarse_its, const double *b, double *x_out, double *hist,
+                              int hist_cap, int *nhist, int *its, int *reason)
+{
+    Ws W;
+    const SepDev A = make_sep(1, n3, periodic, widths, n, coef, diag, rem_rowptr, rem_col, rem_val);
+    // hierarchy of the pressure grid; level 0 in the compact layout of the system's first nsep rows
+    MgEmu M;
+    {
+        std::vector<double> dx(widths, widths + n3[0]), dy(widths + n3[0], widths + n3[0] + n3[1]),
+            dz(widths + n3[0] + n3[1], widths + n3[0] + n3[1] + n3[2]);
+        std::vector<double> gx(coef, coef + n3[0] + 1), gy(coef + n3[0] + 1, coef + n3[0] + n3[1] + 2),
+            gz(coef + n3[0] + n3[1] + 2, coef + n3[0] + n3[1] + n3[2] + 3);
+        M.host = mg_build_hierarchy(n3, periodic, dx, dy, dz, gx, gy, gz, dt, 0);
+        const size_t nl = M.host.size();
+        M.dev.resize(nl);
+        M.axes.resize(nl);
+        M.bufs.resize(nl);
+        for (size_t l = 0; l < nl; ++l)
+        {
+            const MgHostLevel &H = M.host[l];
+            MgLevel &D = M.dev[l];
+            D.nx = H.n[0]; D.ny = H.n[1]; D.nz = H.n[2];
+            D.perx = H.per[0]; D.pery = H.per[1]; D.perz = H.per[2];
+            D.px = D.nx; D.plane = (long long)D.nx * D.ny; D.base = 0;
+            D.mx = D.my = D.mz = D.sx = D.sy = D.sz = nullptr;
+            if (l + 1 < nl)
+            {
+                D.mx = H.cmap[0].data(); D.my = H.cmap[1].data(); D.mz = H.cmap[2].data();
+                D.sx = H.cstart[0].data(); D.sy = H.cstart[1].data(); D.sz = H.cstart[2].data();
+            }
+            size_t off[6];
+            const std::vector<double> *parts[6] = {&H.d[0], &H.d[1], &H.d[2], &H.g[0], &H.g[1], &H.g[2]};
+            for (int q = 0; q < 6; ++q)
+            {
+                off[q] = M.axes[l].size();
+                M.axes[l].insert(M.axes[l].end(), parts[q]->begin(), parts[q]->end());
+            }
+            const double *base = M.axes[l].data();
+            D.dx = base + off[0]; D.dy = base + off[1]; D.dz = base + off[2];
+            D.gx = base + off[3]; D.gy = base + off[4]; D.gz = base + off[5];
+            M.bufs[l].assign(5, std::vector<double>(l == 0 ? (size_t)n : (size_t)H.cells(), 0.0));
+        }
+        M.prm.smooth_its = smooth_its;
+        M.prm.coarse_its = coarse_its;
+    }
+    SolveConsts kc{};
+    kc.rtol = rtol; kc.atol = atol; kc.divtol = 1e4; kc.nglobal = (double)n;
+    kc.max_it = max_it; kc.norm_type = 1; kc.has_const = has_const; kc.hist_cap = hist_cap;
+    DevState st{};
+    M.st = &st;
+    emu::launch(dim3(1), dim3(32), 0, [&] { k_state_reset(&st); });
+    std::vector<double> r(b, b + n), p0((size_t)n, 0.0), p1((size_t)n, 0.0), w((size_t)n, 0.0), x((size_t)n, 0.0);
+    const int blocks = 3;
+    const int nm = nullvec ? 2 : (has_const ? 1 : 0);
+    const long long nsep = A.nsep;
+    double *z = nullptr;
+    auto precondition = [&] {
+        z = M.cycle(r.data());
+        if (n > nsep) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_tail_pc(nsep, n, r.data(), dinv, z, &st); });
+    };
+    auto sums = [&](int kind) {
+        if (nm == 2) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_zsums<2>(n, z, r.data(), nullvec, kind, W.ws, &st, kc, hist); });
+        else if (nm == 1) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_zsums<1>(n, z, r.data(), nullvec, kind, W.ws, &st, kc, hist); });
+        else emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_zsums<0>(n, z, r.data(), nullvec, kind, W.ws, &st, kc, hist); });
+    };
+    precondition();
+    if (nm == 2) sums(FIN_CSR_INIT);
+    else
+    {
+        if (nm == 1) sums(FIN_INIT_CENTRE);
+        sums(FIN_INIT);
+    }
+    double *pp[2] = {p0.data(), p1.data()};
+    for (int it = 0; it < max_it + 2 && !st.done; ++it)
+    {
+        CsrVecs v{z, pp[it & 1], pp[(it & 1) ^ 1], w.data(), x.data(), nullptr, nullvec};
+        if (nm == 2) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_cg_spmv<false, 2>(A, v, W.ws, &st, kc, hist); });
+        else if (nm == 1) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_cg_spmv<false, 1>(A, v, W.ws, &st, kc, hist); });
+        else emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_cg_spmv<false, 0>(A, v, W.ws, &st, kc, hist); });
+        emu::launch(dim3(blocks), dim3(256), 0, [&] { k_mg_rupdate(n, r.data(), w.data(), &st); });
+        precondition();
+        sums(nm == 2 ? FIN_CSR_UPDATE : FIN_UPDATE);
+    }
+    GridDev g1{};
+    g1.nx = (int)n; g1.ny = 1; g1.nzl = 1; g1.px = (int)n; g1.plane = 0;
+    emu::launch(dim3(1), dim3(256), 0, [&] { k_xtail(g1, x.data(), p0.data(), p1.data(), &st); });
+    memcpy(x_out, x.data(), sizeof(double) * (size_t)n);
     *nhist = st.nhist;
     *its = st.its;
     *reason = st.reason;

@@ -128,3 +128,70 @@ def box_local_system(A, b, dim, n, procs, rank):
         cols_p[a:e] = cols_p[a:e][o]
         vals[a:e] = vals[a:e][o]
     return Mat(indptr, cols_p.astype(np.int32), vals, total), np.ascontiguousarray(b[rows]), plan
+
+
+def ibpm_system(widths, dt=0.01, nb=24, radius=0.3, centre=None):
+    """Test-side assembly of IBPM's modified Poisson system [D;E] BN [G,-H] (applications/ibpm/ibpm.cpp:164-194) on a
+    (stretched) grid with non-periodic walls: D and G from the oracle's literal assembly (createdivergence.cpp:140-223,
+    creategradient.cpp:70-128), E a regularised-delta interpolation of each velocity component onto nb Lagrangian points
+    on a circle (createdelta.cpp:32-164 in spirit: a 4 x 4(x 4) patch of the Roma kernel), H = W E^T with
+    W = diag(1 / (face area * face spacing)) so that the product is symmetric like PetIBM's, BN = dt I, and both
+    MatMatMult calls through the oracle's restatement (operand and accumulation order of navierstokes.cpp:351-356).
+    Returns (M as scipy CSR with sorted rows, pN, null vector: constant on the pressure block, zero on the forces)."""
+    import scipy.sparse as sp
+
+    dim = len(widths)
+    per = [0] * dim
+    D = orc.assemble_divergence(widths, per + [0] * (3 - dim))
+    G = orc.assemble_gradient(widths, per + [0] * (3 - dim))
+    Ds, Gs = D.to_scipy().tocsc(), G.to_scipy().tocsr()
+    UN, pN = Gs.shape
+    n = [len(w) for w in widths]
+    edges = [np.concatenate([[0.0], np.cumsum(w)]) for w in widths]
+    cen = [0.5 * (e[:-1] + e[1:]) for e in edges]
+    if centre is None:
+        centre = [0.5 * e[-1] for e in edges]
+    hmin = min(float(np.min(w)) for w in widths)
+
+    def roma(r):
+        r = np.abs(r) / hmin
+        return np.where(r <= 0.5, (1 + np.sqrt(np.maximum(1 - 3 * r * r, 0))) / 3,
+                        np.where(r <= 1.5, (5 - 3 * r - np.sqrt(np.maximum(1 - 3 * (1 - r) ** 2, 0))) / 6, 0.0)) / hmin
+
+    th = np.linspace(0.0, 2 * np.pi, nb, endpoint=False)
+    pts = np.zeros((nb, dim))
+    pts[:, 0] = centre[0] + radius * np.cos(th)
+    pts[:, 1] = centre[1] + radius * np.sin(th)
+    if dim == 3:
+        pts[:, 2] = centre[2] + 0.2 * radius * np.sin(3 * th)
+    rows, cols, vals = [], [], []
+    off = 0
+    for f in range(dim):
+        coords = [edges[d][1:-1] if d == f else cen[d] for d in range(dim)]     # field f sits on its own faces
+        nf = [len(c) for c in coords]
+        for p in range(nb):
+            i0 = [int(np.searchsorted(coords[d], pts[p, d])) for d in range(dim)]
+            rng_ = [range(max(i0[d] - 2, 0), min(i0[d] + 2, nf[d])) for d in range(dim)]
+            for idx in np.ndindex(*[len(r) for r in rng_]):
+                ii = [rng_[d][idx[d]] for d in range(dim)]
+                wgt = float(np.prod([roma(coords[d][ii[d]] - pts[p, d]) * hmin for d in range(dim)]))
+                if wgt > 0.0:
+                    lin = ii[0] + nf[0] * (ii[1] + (nf[1] * ii[2] if dim == 3 else 0))
+                    rows.append(f * nb + p); cols.append(off + lin); vals.append(wgt)
+        off += int(np.prod(nf))
+    assert off == UN
+    E = sp.csr_matrix((vals, (rows, cols)), shape=(dim * nb, UN))
+    area = np.abs(Ds).max(axis=0).toarray().ravel()
+    invh = np.abs(Gs).max(axis=1).toarray().ravel()
+    W = sp.diags(invh / area)
+    H = (W @ E.T).tocsr()
+    DE = sp.vstack([Ds.tocsr(), E]).tocsr(); DE.sort_indices()
+    GH = sp.hstack([Gs, -H]).tocsr(); GH.sort_indices()
+    BNGH = GH.copy(); BNGH.data = dt * BNGH.data                      # BN = dt I (createbn.cpp:49-53): MatMatMult(BN, GH)
+    A1 = orc.Csr.from_arrays(DE.shape[0], DE.shape[1], DE.indptr, DE.indices, DE.data)
+    A2 = orc.Csr.from_arrays(BNGH.shape[0], BNGH.shape[1], BNGH.indptr, BNGH.indices, BNGH.data)
+    M = orc.matmatmult(A1, A2).to_scipy().tocsr()
+    M.sort_indices()
+    nv = np.zeros(M.shape[0])
+    nv[:pN] = 1.0 / np.sqrt(pN)
+    return M, pN, nv

@@ -138,16 +138,18 @@ class VCycle:
         return chebyshev(lev["A"], lev["dinv"], b, x, self.smooth_its, self.lmax, self.smooth_ratio)
 
 
-def pcg(A, b, M, const_nullspace=True, rtol=0.0, atol=0.0, max_it=50):
-    """KSPSolve_CG semantics (zero guess, left PC, preconditioned norm, MatNullSpaceRemove after PCApply,
-    KSPConvergedDefault) with z = M(r).  Returns (x, history, its, reason)."""
+def pcg(A, b, M, const_nullspace=True, rtol=0.0, atol=0.0, max_it=50, nullvec=None):
+    """KSPSolve_CG semantics (zero guess, left PC, preconditioned norm, MatNullSpaceRemove after PCApply -- the constant
+    or one explicit orthonormal vector --, KSPConvergedDefault) with z = M(r).  Returns (x, history, its, reason)."""
     n = b.size
     x = np.zeros(n)
     r = b.copy()
 
     def pc(v):
         z = M(v)
-        if const_nullspace:
+        if nullvec is not None:
+            z = z + (-(z @ nullvec)) * nullvec
+        elif const_nullspace:
             z = z + z.sum() / (-1.0 * n)
         return z
 

@@ -45,7 +45,7 @@ def emu():
     L.emu_set_schedule.argtypes = [C.c_uint64]
     L.emu_csr_solve.argtypes = [C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32), _dp, C.c_int, C.c_int, C.c_int, _dp,
                                 C.c_double, C.c_double, C.c_int, _dp, _dp, _dp, C.c_int, _ip, _ip, _ip]
-    L.emu_sep_solve.argtypes = [C.c_int, C.POINTER(C.c_int64), _ip, C.c_int64, _dp, _dp, C.POINTER(C.c_int64),
+    L.emu_sep_solve.argtypes = [C.c_int, C.POINTER(C.c_int64), _ip, _dp, C.c_int64, _dp, _dp, C.POINTER(C.c_int64),
                                 C.POINTER(C.c_int32), _dp, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_double, C.c_double, C.c_int,
                                 _dp, _dp, _dp, C.c_int, _ip, _ip, _ip]
     return L
@@ -277,16 +277,27 @@ def test_emulated_csr_paths(emu, pc):
     np.testing.assert_allclose(x, refm.x, rtol=0, atol=1e-9 * np.abs(refm.x).max())
 
 
-def _sep_solve(L, dims, per, M, b, mode="apply", pc="none", has_const=False, nullvec=None, rtol=0.0, atol=0.0, max_it=20):
+def _sep_solve(L, dims, per, M, b, mode="apply", pc="none", has_const=False, nullvec=None, rtol=0.0, atol=0.0, max_it=20,
+               hybrid_widths=None, dt=0.01):
     """The line-coefficient operator (sep_kernels.cuh) on the emulation; the structure is read out of M by the host
-    code of libb200ls.so (b200ls_staggered_analyze), exactly as b200ls_set_staggered does before uploading it."""
-    from petibm_b200.staggered import analyze
+    code of libb200ls.so (b200ls_staggered_analyze), exactly as b200ls_set_staggered does before uploading it.
+    hybrid_widths: the pressure operator of that grid + remainder instead (b200ls_hybrid_analyze / _set_poisson_hybrid)."""
+    from petibm_b200.staggered import analyze, analyze_hybrid
 
     M = M.tocsr(); M.sort_indices()
-    st = analyze(dims, per, M.indptr, M.indices, M.data)
+    wp = None
+    if hybrid_widths is not None:
+        st = analyze_hybrid(hybrid_widths, per, dt, M.indptr, M.indices, M.data)
+        w3 = [np.asarray(a, dtype=np.float64) for a in hybrid_widths] + [np.ones(1)] * (3 - len(hybrid_widths))
+        dims = [[a.size for a in w3]]
+        coef = np.ascontiguousarray(np.concatenate(st["g"]))
+        wpack = np.ascontiguousarray(np.concatenate(w3))
+        wp = wpack.ctypes.data_as(_dp)
+    else:
+        st = analyze(dims, per, M.indptr, M.indices, M.data)
+        coef = np.ascontiguousarray(np.concatenate([np.concatenate(ax) for f in st["coef"] for ax in f]))
     d = np.ascontiguousarray(dims, dtype=np.int64).reshape(-1)
     p3 = (C.c_int * 3)(*([int(v) for v in per] + [0] * 3)[:3])
-    coef = np.ascontiguousarray(np.concatenate([np.concatenate(ax) for f in st["coef"] for ax in f]))
     diag = np.ascontiguousarray(st["diag"])
     rp, rc, rv = st["rem"]
     rc = np.ascontiguousarray(rc if rc.size else np.zeros(1, dtype=np.int32)); rv = np.ascontiguousarray(rv if rv.size else np.zeros(1))
@@ -296,7 +307,7 @@ def _sep_solve(L, dims, per, M, b, mode="apply", pc="none", has_const=False, nul
     x = np.empty_like(b); hist = np.zeros(max_it + 2)
     nh, its, reason = C.c_int(0), C.c_int(0), C.c_int(0)
     nvp = None if nullvec is None else np.ascontiguousarray(nullvec, dtype=np.float64).ctypes.data_as(_dp)
-    rcode = L.emu_sep_solve(len(dims), d.ctypes.data_as(C.POINTER(C.c_int64)), p3, M.shape[0], coef.ctypes.data_as(_dp),
+    rcode = L.emu_sep_solve(len(dims), d.ctypes.data_as(C.POINTER(C.c_int64)), p3, wp, M.shape[0], coef.ctypes.data_as(_dp),
                             diag.ctypes.data_as(_dp), rp.ctypes.data_as(C.POINTER(C.c_int64)),
                             rc.ctypes.data_as(C.POINTER(C.c_int32)), rv.ctypes.data_as(_dp), dinv.ctypes.data_as(_dp),
                             {"apply": 0, "cg": 1, "bcgs": 2}[mode], int(pc == "jacobi"), int(has_const), nvp, rtol, atol, max_it,
@@ -372,3 +383,32 @@ def test_emulated_line_coefficient_krylov_paths(emu, pc):
     assert (its, reason) == (ic, rc) and np.array_equal(hist, hc) and np.array_equal(x, xc)
     np.testing.assert_allclose(hist, refm.history, rtol=1e-10)
     np.testing.assert_allclose(x, refm.x, rtol=0, atol=1e-9 * np.abs(refm.x).max())
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_emulated_hybrid_operator_on_a_stretched_ibpm_system(emu, dim):
+    """IBPM's modified Poisson system [D;E] BN [G,-H] on a stretched grid (tests/helpers.ibpm_system): the pressure block
+    is rebuilt from the 1-D arrays with its face areas, the coupling comes from the remainder -- SpMV bit-identical to
+    the oracle's MatMult on the assembled matrix, CG with the explicit null-space vector equal to the CSR kernels bit for
+    bit (and to the oracle like they are)."""
+    sub = [{"end": 0.6, "cells": 5 if dim == 3 else 8, "stretchRatio": 1.0 / 1.25}, {"end": 1.4, "cells": 8 if dim == 3 else 14, "stretchRatio": 1.0},
+           {"end": 2.0, "cells": 5 if dim == 3 else 8, "stretchRatio": 1.25}]
+    w = orc.axis_from_subdomains(0.0, sub)
+    widths = [w.copy() for _ in range(dim)]
+    M, pN, nv = H.ibpm_system(widths, dt=0.01, nb=10)
+    Mo = orc.Csr.from_arrays(M.shape[0], M.shape[1], M.indptr, M.indices, M.data)
+    rng = np.random.default_rng(12)
+    xs = rng.standard_normal(M.shape[0]); xs -= (xs @ nv) * nv
+    y, _, _, _ = _sep_solve(emu, None, (0,) * dim, M, xs, mode="apply", hybrid_widths=widths)
+    assert np.array_equal(y, Mo.spmv(xs))
+    bm = Mo.spmv(xs)
+    for pc in ("none", "jacobi"):
+        ref = orc.ksp_solve(Mo, bm, pc_type=pc, rtol=0, atol=0, max_it=15, nullvecs=nv)
+        xc, hc, ic, rc = _csr_solve(emu, M, bm, pc=pc, nullvec=nv, max_it=15)
+        x, hist, its, reason = _sep_solve(emu, None, (0,) * dim, M, bm, mode="cg", pc=pc, nullvec=nv, max_it=15, hybrid_widths=widths)
+        assert (its, reason) == (ic, rc) and np.array_equal(hist, hc) and np.array_equal(x, xc)
+        # against the oracle: 1e-10 while the recurrence is insensitive to the summation order (the assembled matrix is
+        # symmetric only up to rounding, and CG amplifies that from iteration to iteration), 1e-6 over the whole window
+        np.testing.assert_allclose(hist[:8], ref.history[:8], rtol=1e-10)
+        np.testing.assert_allclose(hist, ref.history, rtol=1e-6)
+        np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-6 * np.abs(ref.x).max())

@@ -157,3 +157,54 @@ def test_an_explicit_zero_is_harmless():
     Z.data[(Z.indices == 17) & (np.repeat(np.arange(Z.shape[0]), np.diff(Z.indptr)) == 2)] = 0.0   # stored, but zero
     st = analyze(dims, p, Z.indptr, Z.indices, Z.data)
     assert same_matrix(A, rebuild(dims, p, st, A.shape[0]))
+
+
+def _stretched_axis(n_side, n_band, ratio):
+    sub = [{"end": 0.6, "cells": n_side, "stretchRatio": 1.0 / ratio}, {"end": 1.4, "cells": n_band, "stretchRatio": 1.0},
+           {"end": 2.0, "cells": n_side, "stretchRatio": ratio}]
+    return orc.axis_from_subdomains(0.0, sub)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_ibpm_system_on_a_stretched_grid_is_pressure_operator_plus_remainder(dim):
+    """[D;E] BN [G,-H] assembled through the oracle's MatMatMult restatement (tests/helpers.ibpm_system): the pressure
+    block is D (dt I) G of the mesh bit for bit, so b200ls_hybrid_analyze accepts it; its coefficients carry face areas,
+    so the line-coefficient analysis does not (that is why the hybrid form exists)."""
+    from petibm_b200.staggered import analyze_hybrid
+
+    w = _stretched_axis(5, 8, 1.3) if dim == 3 else _stretched_axis(8, 14, 1.2)
+    widths = [w.copy() for _ in range(dim)]
+    M, pN, nv = H.ibpm_system(widths, dt=0.01, nb=10)
+    assert abs(M @ nv).max() < 1e-15 and abs(M - M.T).max() < 1e-14 * abs(M).max()
+    st = analyze_hybrid(widths, (0,) * dim, 0.01, M.indptr, M.indices, M.data)
+    assert st["nsep"] == pN and np.array_equal(st["diag"], M.diagonal()[:pN])
+    rp, rc, rv = st["rem"]
+    assert rc.size > 0 and np.all(rc[: rp[pN]] >= pN) and np.array_equal(np.diff(rp)[pN:], np.diff(M.indptr)[pN:])
+    # rebuild: closed-form stencil block (area * g) + stored diagonal + remainder == M, bitwise
+    n3 = [w.size] * dim + [1] * (3 - dim)
+    d3 = widths + [np.ones(1)] * (3 - dim)
+    rows, cols, vals = [np.arange(pN)], [np.arange(pN)], [st["diag"]]
+    l = np.arange(pN)
+    idx = (l % n3[0], (l // n3[0]) % n3[1], l // (n3[0] * n3[1]))
+    stride = (1, n3[0], n3[0] * n3[1])
+    for d in range(3):
+        a, b = (1 if d == 0 else 0), (1 if d == 2 else 2)
+        area = d3[a][idx[a]] * d3[b][idx[b]]
+        for gsel, step in ((0, -1), (1, +1)):
+            c = area * st["g"][d][idx[d] + gsel]
+            keep = c != 0.0
+            rows.append(l[keep]); cols.append(l[keep] + step * stride[d]); vals.append(c[keep])
+    rr = np.repeat(np.arange(M.shape[0]), np.diff(rp))
+    rows.append(rr); cols.append(rc.astype(np.int64)); vals.append(rv)
+    B = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=M.shape)
+    B.sort_indices()
+    assert same_matrix(M, B)
+    with pytest.raises(B200Error):
+        analyze([n3], (0, 0, 0), M.indptr, M.indices, M.data)          # not a line-coefficient stencil
+    # a changed pressure entry or a wrong time step is refused
+    Bad = M.copy()
+    Bad.data[Bad.indptr[5]] = np.nextafter(Bad.data[Bad.indptr[5]], 0.0)
+    with pytest.raises(B200Error):
+        analyze_hybrid(widths, (0,) * dim, 0.01, Bad.indptr, Bad.indices, Bad.data)
+    with pytest.raises(B200Error):
+        analyze_hybrid(widths, (0,) * dim, 0.02, M.indptr, M.indices, M.data)
