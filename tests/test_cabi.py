@@ -113,6 +113,13 @@ def test_multigrid_options_use_the_pcmg_names():
         assert rc == _lib.ERR_UNSUPPORTED and msg
 
 
+def test_example_option_files_parse():
+    for name, prefix, want in (("poisson_solver.info", "poisson_", (_lib.KSP_CG, _lib.PC_MG)),
+                               ("velocity_solver.info", "velocity_", (_lib.KSP_BCGS, _lib.PC_JACOBI))):
+        rc, o, msg = _parse(open(os.path.join(ROOT, "examples", "config", name)).read(), prefix)
+        assert rc == 0 and (o.ksp_type, o.pc_type) == want and o.atol == 1e-6 and o.rtol == 0.0, msg
+
+
 @pytest.mark.parametrize("text", ["-poisson_ksp_rtol abc", "-poisson_ksp_max_it", "stray -poisson_ksp_type cg"])
 def test_malformed_options(text):
     rc, _, msg = _parse(text)

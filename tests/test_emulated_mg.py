@@ -66,6 +66,20 @@ def test_emulated_vcycle_matches_the_restatement(emu, shape, per, smooth):
     assert abs(zu @ r - u @ z) <= 1e-10 * abs(zu @ r)
 
 
+def test_emulated_vcycle_with_a_level_cap(emu):
+    """-pc_mg_levels: the hierarchy stops early and the (now larger) last level gets the long Chebyshev polynomial."""
+    shape, per = (16, 12, 8), (0, 0, 0)
+    widths = H.make_widths(shape)
+    r = np.random.default_rng(9).standard_normal(int(np.prod(shape)))
+    r -= r.mean()
+    for cap in (1, 2):
+        V = R.VCycle(widths, per, 0.01, max_levels=cap, coarse_its=9)
+        z, _, _, _, nl = _mg(emu, widths, per, r, mode="apply", levels=cap, coarse=9)
+        assert nl == cap == len(V.levels)
+        zr = V.apply(r)
+        np.testing.assert_allclose(z, zr, rtol=0, atol=1e-11 * np.abs(zr).max())
+
+
 def _petibm_like_axis(n_band, n_side, ratio):
     """Uniform fine band with geometrically stretched cells on both sides, like the axes of the shipped examples
     (examples/ibpm/cylinder2dRe100_GPU/config.yaml: stretchRatio 1.02 over 125 cells next to a 200-cell band)."""
