@@ -445,7 +445,7 @@ EMU_API int emu_csr_solve(int64_t n, const int64_t *rowptr, const int32_t *col, 
             if (jacobi) { if (nm == 2) EMU_CS(true, 2); else if (nm == 1) EMU_CS(true, 1); else EMU_CS(true, 0); }
             else { if (nm == 2) EMU_CS(false, 2); else if (nm == 1) EMU_CS(false, 1); else EMU_CS(false, 0); }
 #undef EMU_CS
-            upd(false, nm == 2 ? FIN_CSR_UPDATE : FIN_UPDATE);
+            upd(false, nm == 2 ? (int)FIN_CSR_UPDATE : (int)FIN_UPDATE);
         }
         GridDev g1{};
         g1.nx = (int)n; g1.ny = 1; g1.nzl = 1; g1.px = (int)n; g1.plane = 0;
@@ -574,7 +574,7 @@ EMU_API int emu_sep_solve(int nfields, const int64_t *dims, const int *periodic,
             if (jacobi) { if (nm == 2) EMU_CS(true, 2); else if (nm == 1) EMU_CS(true, 1); else EMU_CS(true, 0); }
             else { if (nm == 2) EMU_CS(false, 2); else if (nm == 1) EMU_CS(false, 1); else EMU_CS(false, 0); }
 #undef EMU_CS
-            upd(false, nm == 2 ? FIN_CSR_UPDATE : FIN_UPDATE);
+            upd(false, nm == 2 ? (int)FIN_CSR_UPDATE : (int)FIN_UPDATE);
         }
         GridDev g1{};
         g1.nx = (int)n; g1.ny = 1; g1.nzl = 1; g1.px = (int)n; g1.plane = 0;
@@ -827,7 +827,7 @@ EMU_API int emu_hybrid_mg_pcg(int dim, const int64_t *n3, const int *periodic, c
         else emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_cg_spmv<false, 0>(A, v, W.ws, &st, kc, hist); });
         emu::launch(dim3(blocks), dim3(256), 0, [&] { k_mg_rupdate(n, r.data(), w.data(), &st); });
         precondition();
-        sums(nm == 2 ? FIN_CSR_UPDATE : FIN_UPDATE);
+        sums(nm == 2 ? (int)FIN_CSR_UPDATE : (int)FIN_UPDATE);
     }
     GridDev g1{};
     g1.nx = (int)n; g1.ny = 1; g1.nzl = 1; g1.px = (int)n; g1.plane = 0;
