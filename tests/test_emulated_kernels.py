@@ -412,3 +412,49 @@ def test_emulated_hybrid_operator_on_a_stretched_ibpm_system(emu, dim):
         np.testing.assert_allclose(hist[:8], ref.history[:8], rtol=1e-10)
         np.testing.assert_allclose(hist, ref.history, rtol=1e-6)
         np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-6 * np.abs(ref.x).max())
+
+
+def test_emulated_line_coefficient_spmv_on_random_stencil_blocks(emu):
+    """Random combinations the structured tests do not reach: one to three blocks, extents down to one cell, periodic
+    axes with three cells (every neighbour wraps somewhere), a random remainder behind the blocks.  y = A x must equal the
+    oracle's MatMult_SeqAIJ restatement bit for bit (same row sums in the same order)."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(77)
+    for case in range(14):
+        nf = int(rng.integers(1, 4))
+        per = [bool(rng.integers(0, 2)) for _ in range(3)]
+        dims = [[int(rng.integers(3 if per[d] else 1, 7)) for d in range(3)] for _ in range(nf)]
+        nextra = int(rng.integers(0, 5))
+        rows, cols, vals = [], [], []
+        off = 0
+        for n in dims:
+            n0, n1, n2 = n
+            size = n0 * n1 * n2
+            stride = (1, n0, n0 * n1)
+            l = np.arange(size)
+            idx = (l % n0, (l // n0) % n1, l // (n0 * n1))
+            rows.append(off + l); cols.append(off + l); vals.append(rng.uniform(5.0, 9.0, size))
+            for d in range(3):
+                if n[d] == 1:
+                    continue
+                cm, cp = rng.uniform(-1.0, -0.1, n[d]), rng.uniform(-1.0, -0.1, n[d])
+                for coef, step in ((cm, -1), (cp, +1)):
+                    nb = idx[d] + step
+                    ok = (nb >= 0) & (nb < n[d])
+                    if per[d]:
+                        nb, ok = nb % n[d], np.ones_like(ok)
+                    rows.append(off + l[ok]); cols.append(off + l[ok] + (nb[ok] - idx[d][ok]) * stride[d]); vals.append(coef[idx[d]][ok])
+            off += size
+        nrows = off + nextra
+        if nextra:
+            k = 3 * nextra
+            rr = np.concatenate([rng.integers(0, nrows, k), np.arange(off, nrows)])
+            cc = np.concatenate([rng.integers(off, nrows, k), np.arange(off, nrows)])
+            rows.append(rr); cols.append(cc); vals.append(rng.uniform(0.1, 1.0, rr.size))
+        M = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nrows, nrows))
+        M.sum_duplicates(); M.sort_indices()
+        Mo = orc.Csr.from_arrays(nrows, nrows, M.indptr, M.indices, M.data)
+        x = rng.standard_normal(nrows)
+        y, _, _, _ = _sep_solve(emu, dims, per, M, x, mode="apply")
+        assert np.array_equal(y, Mo.spmv(x)), (case, dims, per, nextra)

@@ -202,3 +202,23 @@ def test_emulated_block_preconditioner_on_the_ibpm_system(emu, dim):
     jac = orc.ksp_solve(Mo, b, pc_type="jacobi", rtol=1e-9, atol=1e-50, max_it=5000, nullvecs=nv)
     assert reason == 2 and jac.reason == 2 and 3 * its <= jac.its, (its, jac.its)
     np.testing.assert_allclose(x, xs, rtol=0, atol=1e-6 * np.abs(xs).max())
+
+
+def test_emulated_mg_edge_cases(emu):
+    """Zero and NaN right-hand sides end like KSP ends them (KSPConvergedDefault: converged at iteration 0 with a zero
+    residual; KSP_DIVERGED_NANORINF), and an already tiny grid (one level) still works."""
+    shape, per = (12, 8, 8), (0, 0, 0)
+    widths = H.make_widths(shape)
+    n = int(np.prod(shape))
+    x, hist, its, reason, _ = _mg(emu, widths, per, np.zeros(n), rtol=1e-8, atol=1e-50, max_it=10)
+    assert (its, reason) == (0, 3) and hist.size == 1 and hist[0] == 0.0 and not np.any(x)
+    b = np.ones(n); b[5] = np.nan
+    x, hist, its, reason, _ = _mg(emu, widths, per, b, rtol=1e-8, max_it=10)
+    assert reason == -9 and its == 0
+    # one level only: the "coarse" polynomial is the whole preconditioner
+    tiny = H.make_widths((3, 3, 3))
+    A = H.oracle_matrix(tiny, (0, 0, 0))
+    b, xs = H.consistent_rhs(A)
+    x, hist, its, reason, nl = _mg(emu, tiny, (0, 0, 0), b, rtol=1e-10, max_it=60)
+    assert nl == 1 and reason == 2
+    np.testing.assert_allclose(x, xs, rtol=0, atol=1e-8 * np.abs(xs).max())
