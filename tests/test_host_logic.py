@@ -61,3 +61,18 @@ def test_mat_wrapper_keeps_nullspace_and_types():
     M = pb.Mat.from_scipy(A).setNullSpace(True)
     assert M.nrows == 20 and M.indptr.dtype == np.int64 and M.indices.dtype == np.int32 and M.data.dtype == np.float64
     assert M.null_has_const and M.null_vecs is None
+
+
+def test_vcycle_schedule_invariants_for_every_degree(tmp_path):
+    """tests/cpp/mg_schedule_check.cpp: the shared V-cycle schedule (petibm_b200/csrc/mg_schedule.h) never lets a kernel
+    write a buffer it reads, reads only what was written, and issues (levels - 1) * (2 m + 1) + m_coarse launches, for
+    1..6 levels x smoothing degree 1..6 x coarse degree 1..6."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "mg_schedule_check")
+    res = subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "petibm_b200", "csrc"),
+                          os.path.join(root, "tests", "cpp", "mg_schedule_check.cpp"), "-o", exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 0 and "216 combinations, 0 bad" in run.stdout, run.stdout + run.stderr
