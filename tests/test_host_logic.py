@@ -1,5 +1,7 @@
 """Host-side logic of the plugin mirror that needs no GPU: grid description from the YAML settings, DMDA slab
 ownership, factory dispatch (linsolver.cpp:57-91)."""
+import os
+
 import numpy as np
 import pytest
 
