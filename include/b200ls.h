@@ -31,6 +31,9 @@
  *   b200ls_axis_from_subdomains           parser::parseSubDomains/parseOneSubDomain
  *                                         src/parser/parser.cpp:297-356, misc::stretchGrid
  *                                         include/petibm/misc.h:148-163
+ *   b200ls_divergence / _gradient / _project   MatMult(D, ...), MatMult(G / BNG, ...), VecAXPY around the solve
+ *                                         navierstokes.cpp:442,540-551,583-615; createdivergence.cpp:140-223,
+ *                                         creategradient.cpp:70-128
  *   b200ls_repart_*                       the DMDA ownership the Vecs/Mat rows arrive in
  *                                         src/mesh/cartesianmesh.cpp:500-538,709-721 (DMDACreate3d,
  *                                         AOApplicationToPetsc) -> slab partition of the solver
@@ -272,6 +275,22 @@ int b200ls_get_residual(const b200ls_solver *h, double *rnorm);
 int b200ls_get_reason(const b200ls_solver *h, int *reason);
 /* Copies min(cap, n) entries of the residual-norm history (entry 0 = initial) and sets *n. */
 int b200ls_get_history(const b200ls_solver *h, double *buf, int cap, int *n);
+
+/* ---- the operators on either side of the pressure solve, matrix-free (single GPU) ----
+ * With these, b and x of b200ls_solve_device never leave the device: rhs2 = D u* (MatMult(D, UGlobal, rhs2),
+ * navierstokes.cpp:540-551) -> solve -> u -= (BN G) dP, p += dP (navierstokes.cpp:583-615) is a chain of launches on the
+ * solver's stream.  D (createdivergence.cpp:140-223) and G (creategradient.cpp:70-128) of the mesh given to
+ * b200ls_set_poisson_stencil; velocities are PetIBM's packed vector [u | v | w] (cartesianmesh.cpp:251-273: one point
+ * fewer than cells along the field's own direction unless periodic), pressures the cell vector of the solve.  Bit-identical
+ * to MatMult on the assembled matrices (ascending column order, no FMA).  The boundary terms (DCorrection, bc1) are the
+ * application's MatShells and stay with the caller.  *_device: device pointers, asynchronous on b200ls_stream(h). */
+int b200ls_velocity_size(b200ls_solver *h, int64_t *nvel, int64_t *npressure);
+int b200ls_divergence_device(b200ls_solver *h, const double *u_dev, double *out_dev);               /* out = D u */
+int b200ls_gradient_device(b200ls_solver *h, const double *p_dev, double *out_dev, int with_bn);   /* out = G p or (BN G) p */
+int b200ls_project_device(b200ls_solver *h, double *u_dev, double *p_dev, const double *dp_dev);   /* u -= BNG dp; p += dp (p may be null) */
+int b200ls_divergence(b200ls_solver *h, const double *u_host, double *out_host);
+int b200ls_gradient(b200ls_solver *h, const double *p_host, double *out_host, int with_bn);
+int b200ls_project(b200ls_solver *h, double *u_host, double *p_host, const double *dp_host);
 
 /* ---- measurement hooks (bench.py) ----
  * Device time of the last solve (solve_ms: scatter of b .. gather of x; loop_ms: the iteration loop

@@ -92,6 +92,13 @@ SIGNATURES = {
     "b200ls_get_residual": (C.c_int, [_vp, _dp]),
     "b200ls_get_reason": (C.c_int, [_vp, _ip]),
     "b200ls_get_history": (C.c_int, [_vp, _dp, C.c_int, _ip]),
+    "b200ls_velocity_size": (C.c_int, [_vp, _i64p, _i64p]),
+    "b200ls_divergence_device": (C.c_int, [_vp, _vp, _vp]),
+    "b200ls_gradient_device": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "b200ls_project_device": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "b200ls_divergence": (C.c_int, [_vp, _vp, _vp]),
+    "b200ls_gradient": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "b200ls_project": (C.c_int, [_vp, _vp, _vp, _vp]),
     "b200ls_get_timing": (C.c_int, [_vp, _dp, _dp, _i64p]),
     "b200ls_get_e2e_ms": (C.c_int, [_vp, _dp]),
     "b200ls_set_profile": (C.c_int, [_vp, C.c_int]),

@@ -27,6 +27,7 @@
 #include "sep_kernels.cuh"
 #include "mg_kernels.cuh"
 #include "mg_schedule.h"
+#include "ops_kernels.cuh"
 
 using namespace b200;
 
@@ -1863,3 +1864,5 @@ int b200ls_get_trace(b200ls_solver *h, unsigned long long *buf, int capacity, in
 void *b200ls_stream(b200ls_solver *h) { return h ? (void *)h->stream : nullptr; }
 
 }  // extern "C"
+
+#include "ops_solver.inc"

@@ -398,6 +398,72 @@ class LinSolverB200(LinSolverBase):
         _lib.check(self._L.b200ls_apply(self._h, C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data)), self._h)
         return y
 
+    # ---- the operators on either side of the pressure solve (extension beyond LinSolverBase):
+    # matrix-free D, G and BN G of the mesh given to setStencil / recognised by setMatrix, bit-identical to MatMult on the
+    # assembled matrices (navierstokes.cpp:442, 540-551, 583-615).  numpy arrays or CUDA float64 torch tensors.
+    def velocitySize(self):
+        nv, npr = C.c_int64(0), C.c_int64(0)
+        _lib.check(self._L.b200ls_velocity_size(self._h, C.byref(nv), C.byref(npr)), self._h)
+        return nv.value, npr.value
+
+    @staticmethod
+    def _dev(t, n):
+        import torch
+
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() == n):
+            raise ValueError("device vectors must be contiguous CUDA float64 tensors of the operator's size")
+        return C.c_void_p(t.data_ptr())
+
+    def divergence(self, u, out=None):
+        """out = D u   (MatMult(D, UGlobal, rhs2), navierstokes.cpp:548)."""
+        nv, npr = self.velocitySize()
+        if _is_torch_cuda(u):
+            import torch
+
+            out = torch.empty(npr, dtype=torch.float64, device=u.device) if out is None else out
+            torch.cuda.current_stream(u.device).synchronize()
+            _lib.check(self._L.b200ls_divergence_device(self._h, self._dev(u, nv), self._dev(out, npr)), self._h)
+            return out
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        out = np.empty(npr)
+        assert u.size == nv
+        _lib.check(self._L.b200ls_divergence(self._h, C.c_void_p(u.ctypes.data), C.c_void_p(out.ctypes.data)), self._h)
+        return out
+
+    def gradient(self, p, with_bn=False, out=None):
+        """out = G p, or (BN G) p with BN = dt I   (navierstokes.cpp:442, 595)."""
+        nv, npr = self.velocitySize()
+        if _is_torch_cuda(p):
+            import torch
+
+            out = torch.empty(nv, dtype=torch.float64, device=p.device) if out is None else out
+            torch.cuda.current_stream(p.device).synchronize()
+            _lib.check(self._L.b200ls_gradient_device(self._h, self._dev(p, npr), self._dev(out, nv), int(bool(with_bn))), self._h)
+            return out
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        out = np.empty(nv)
+        assert p.size == npr
+        _lib.check(self._L.b200ls_gradient(self._h, C.c_void_p(p.ctypes.data), C.c_void_p(out.ctypes.data), int(bool(with_bn))),
+                   self._h)
+        return out
+
+    def project(self, u, p, dp):
+        """u <- u - (BN G) dp ; p <- p + dp, in place   (navierstokes.cpp:583-615)."""
+        nv, npr = self.velocitySize()
+        if _is_torch_cuda(u):
+            import torch
+
+            torch.cuda.current_stream(u.device).synchronize()
+            _lib.check(self._L.b200ls_project_device(self._h, self._dev(u, nv), self._dev(p, npr), self._dev(dp, npr)), self._h)
+            return u, p
+        for a, m in ((u, nv), (p, npr)):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.size == m):
+                raise ValueError("u and p are updated in place: contiguous float64 numpy arrays of the operator's sizes")
+        dp = np.ascontiguousarray(dp, dtype=np.float64)
+        _lib.check(self._L.b200ls_project(self._h, C.c_void_p(u.ctypes.data), C.c_void_p(p.ctypes.data),
+                                          C.c_void_p(dp.ctypes.data)), self._h)
+        return u, p
+
     def getIters(self) -> int:
         v = C.c_int(0)
         _lib.check(self._L.b200ls_get_iters(self._h, C.byref(v)), self._h)

@@ -13,6 +13,7 @@
 #include "sep_kernels.cuh"
 #include "mg_kernels.cuh"
 #include "mg_schedule.h"
+#include "ops_kernels.cuh"
 
 using namespace b200;
 
@@ -840,3 +841,30 @@ EMU_API int emu_hybrid_mg_pcg(int dim, const int64_t *n3, const int *periodic, c
 }
 
 }  // extern "C"
+
+// ---- matrix-free staggered-grid operators (ops_kernels.cuh).  mode 0: out = D u;  1: out = G p;  2: out = (BN G) p;
+// 3: projection u -= (BN G) dp (io = u, in = dp), p += dp (io2 = p)
+extern "C" EMU_API int emu_stag_ops(int mode, int dim, const int64_t *n, const int *per, const double *dx, const double *dy,
+                                    const double *dz, double dt, const double *in, double *io, double *io2)
+{
+    Problem P;
+    build(P, dim, n, per, dx, dy, dz, dt);
+    StagGrid s{};
+    s.nx = P.g.nx; s.ny = P.g.ny; s.nz = P.g.nzl; s.dim = dim;
+    s.perx = P.per[0]; s.pery = P.per[1]; s.perz = dim == 3 ? P.per[2] : 0;
+    s.nu = s.nx - (s.perx ? 0 : 1); s.nv = s.ny - (s.pery ? 0 : 1); s.nw = dim == 3 ? s.nz - (s.perz ? 0 : 1) : 0;
+    s.offv = (long long)s.nu * s.ny * s.nz;
+    s.offw = s.offv + (long long)s.nx * s.nv * s.nz;
+    s.dx = P.g.dx; s.dy = P.g.dy; s.dz = P.g.dz; s.gx = P.g.gx; s.gy = P.g.gy; s.gz = P.g.gz;
+    const long long np = (long long)s.nx * s.ny * s.nz;
+    if (mode == 0) emu::launch(dim3(3), dim3(256), 0, [&] { k_divergence(s, in, io); });
+    else if (mode == 1) emu::launch(dim3(3), dim3(256), 0, [&] { k_gradient<0>(s, in, io); });
+    else if (mode == 2) emu::launch(dim3(3), dim3(256), 0, [&] { k_gradient<1>(s, in, io); });
+    else
+    {
+        emu::launch(dim3(3), dim3(256), 0, [&] { k_gradient<2>(s, in, io); });
+        emu::launch(dim3(3), dim3(256), 0, [&] { k_axpy_one(np, io2, in); });
+    }
+    return 0;
+}
+

@@ -19,7 +19,8 @@ EMU = os.path.join(ROOT, "tests", "emu")
 LIB = os.path.join(EMU, "libb200emu.so")
 SRC = [os.path.join(EMU, f) for f in ("emu_solver.cpp", "cuda_emu.h")] + \
       [os.path.join(ROOT, "petibm_b200", "csrc", f) for f in ("kernels.cuh", "spmv2.cuh", "spmv3.cuh", "hw.cuh", "csr_kernels.cuh",
-                                                            "sep_kernels.cuh", "mg_kernels.cuh", "mg_schedule.h")]
+                                                            "sep_kernels.cuh", "mg_kernels.cuh", "mg_schedule.h",
+                                                            "ops_kernels.cuh")]
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -458,3 +459,41 @@ def test_emulated_line_coefficient_spmv_on_random_stencil_blocks(emu):
         x = rng.standard_normal(nrows)
         y, _, _, _ = _sep_solve(emu, dims, per, M, x, mode="apply")
         assert np.array_equal(y, Mo.spmv(x)), (case, dims, per, nextra)
+
+
+@pytest.mark.parametrize("shape,per", [((9, 7), (0, 0)), ((8, 6), (1, 0)), ((7, 6, 5), (0, 0, 0)), ((6, 5, 7), (1, 0, 1)),
+                                       ((5, 5, 5), (1, 1, 1)), ((12, 3, 4), (0, 1, 0))])
+def test_emulated_divergence_gradient_projection_are_the_assembled_products(emu, shape, per):
+    """The operators on either side of the pressure solve (ops_kernels.cuh; navierstokes.cpp:540-551, 583-615, 442):
+    rhs2 = D u, G p, (BN G) dp and the projection u -= BNG dp, p += dp are bit-identical to MatMult on the oracle's
+    assembled D, G and MatMatMult(BN, G), and chaining them gives D (BN G) = the Poisson operator of the solve."""
+    emu.emu_stag_ops.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int64), _ip, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp]
+    widths = H.make_widths(shape)
+    dim, n, p, w, dz = _grid_args(widths, per)
+    per3 = list(per) + [0] * (3 - dim)
+    D = orc.assemble_divergence(widths, per3)
+    G = orc.assemble_gradient(widths, per3)
+    BNG = orc.matmatmult(orc.bnhead_order1(G.shape[0], 0.01), G)
+    UN, pN = G.shape
+    rng = np.random.default_rng(11)
+
+    def run(mode, vin, io, io2=None):
+        vin = np.ascontiguousarray(vin); io = np.ascontiguousarray(io)
+        emu.emu_stag_ops(mode, dim, n, p, w[0].ctypes.data_as(_dp), w[1].ctypes.data_as(_dp), dz, 0.01, vin.ctypes.data_as(_dp),
+                         io.ctypes.data_as(_dp), None if io2 is None else io2.ctypes.data_as(_dp))
+        return io
+
+    u = rng.standard_normal(UN)
+    assert np.array_equal(run(0, u, np.empty(pN)), D.spmv(u))
+    pr = rng.standard_normal(pN)
+    assert np.array_equal(run(1, pr, np.empty(UN)), G.spmv(pr))
+    assert np.array_equal(run(2, pr, np.empty(UN)), BNG.spmv(pr))
+    # projection: u <- u + (-1.0) * (BNG dp), p <- p + 1.0 * dp   (VecAXPY semantics)
+    dp = rng.standard_normal(pN)
+    u2, p2 = u.copy(), pr.copy()
+    run(3, dp, u2, p2)
+    assert np.array_equal(u2, u + (-1.0) * BNG.spmv(dp)) and np.array_equal(p2, pr + 1.0 * dp)
+    # D (BN G) p is the operator the solver applies (its own bit-exact SpMV is checked elsewhere): same to rounding
+    A = H.oracle_matrix(widths, per)
+    lhs = run(0, run(2, pr, np.empty(UN)), np.empty(pN))
+    np.testing.assert_allclose(lhs, A.spmv(pr), rtol=0, atol=1e-12 * np.abs(lhs).max())
