@@ -14,11 +14,11 @@ run() { # name timeout command...
   tail -n 6 "gpurun_out/r02_$name.log" | tee -a gpurun_out/r02_summary.log
 }
 # 1. the validated suite first (must stay green), then the new device tests one file at a time
-run pytest_validated 900 python -m pytest tests -m gpu -q -x --deselect tests/test_zzz_gpu_boxes.py --deselect tests/test_zzz_gpu_staggered.py --deselect tests/test_zzz_gpu_multigrid.py --deselect tests/test_zzz_gpu_ops.py
-run pytest_boxes 300 python -m pytest tests/test_zzz_gpu_boxes.py -m gpu -q
-run pytest_staggered 300 python -m pytest tests/test_zzz_gpu_staggered.py -m gpu -q
-run pytest_multigrid 600 python -m pytest tests/test_zzz_gpu_multigrid.py -m gpu -q
-run pytest_ops 300 python -m pytest tests/test_zzz_gpu_ops.py -m gpu -q
+run pytest_validated 900 python -m pytest tests -m gpu -q -x --deselect tests/test_zzz_gpu_1_boxes.py --deselect tests/test_zzz_gpu_2_staggered.py --deselect tests/test_zzz_gpu_4_multigrid.py --deselect tests/test_zzz_gpu_3_ops.py
+run pytest_boxes 300 python -m pytest tests/test_zzz_gpu_1_boxes.py -m gpu -q
+run pytest_staggered 300 python -m pytest tests/test_zzz_gpu_2_staggered.py -m gpu -q
+run pytest_multigrid 600 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m gpu -q
+run pytest_ops 300 python -m pytest tests/test_zzz_gpu_3_ops.py -m gpu -q
 # 2. round-2 kernel candidates against the default: 256^3 and the 8-GPU slab
 run tune_256 600 python scripts/tune_k1.py --tiles 10 18 30 31 32 33
 run tune_slab 300 python scripts/tune_k1.py --size 256 256 32 --tiles 10 13 18 30 31 32 33

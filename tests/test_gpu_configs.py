@@ -125,7 +125,7 @@ def test_c3_ibpm_sized_modified_poisson(pb):
     s = pb.LinSolverB200("poisson", "None")
     s.setOptions(pc_type="jacobi", rtol=0.0, atol=0.0, max_it=40)
     s.setGrid(pb.Grid(widths, (False, False, False), 0.01))   # the grid is known, the matrix is NOT its stencil
-    s.setStaggered(False)                                      # plain CSR here; line-coefficient form: test_zzz_gpu_staggered.py
+    s.setStaggered(False)                                      # plain CSR here; line-coefficient form: test_zzz_gpu_2_staggered.py
     s.setMatrix(pb.Mat.from_scipy(M).setNullSpace(False, nv))
     assert s.operator == "csr" and s.nlocal == pN + nf
     ref = orc.ksp_solve(Mo, b, pc_type="jacobi", rtol=0.0, atol=0.0, max_it=40, nullvecs=nv)
