@@ -109,13 +109,10 @@ def test_a_matrix_without_the_structure_keeps_the_csr_operator(pb):
 
 
 @pytest.mark.parametrize("dim", [2, 3])
-def test_hybrid_operator_and_block_multigrid_on_a_stretched_ibpm_system(pb, dim):
+def test_hybrid_operator_on_a_stretched_ibpm_system(pb, dim):
     """[D;E] BN [G,-H] assembled like PetIBM does (tests/helpers.ibpm_system) on a stretched grid: setMatrix recognises the
-    pressure operator of the mesh plus a remainder ("hybrid"), SpMV and CG are those of the CSR kernels bit for bit, and
-    -poisson_pc_type mg (V-cycle on the pressure block, diagonal on the force rows) converges to the same solution in a
-    fraction of the iterations."""
-    from tests import mg_reference as R
-
+    pressure operator of the mesh plus a remainder ("hybrid"), SpMV and CG are those of the CSR kernels bit for bit
+    (the multigrid block preconditioner on this operator: tests/test_zzz_gpu_4_multigrid.py)."""
     n_side, n_band = (6, 10) if dim == 3 else (12, 24)
     sub = [{"end": 0.6, "cells": n_side, "stretchRatio": 1.0 / 1.2}, {"end": 1.4, "cells": n_band, "stretchRatio": 1.0},
            {"end": 2.0, "cells": n_side, "stretchRatio": 1.2}]
@@ -140,25 +137,4 @@ def test_hybrid_operator_and_block_multigrid_on_a_stretched_ibpm_system(pb, dim)
     assert np.array_equal(s.getHistory(), c.getHistory()) and np.array_equal(x, xc)
     ref = orc.ksp_solve(Mo, b, pc_type="jacobi", rtol=0.0, atol=0.0, max_it=nit, nullvecs=nv)
     np.testing.assert_allclose(s.getHistory()[:8], ref.history[:8], rtol=1e-10)
-    # multigrid on the pressure block + diagonal on the force rows, against the numpy restatement and against Jacobi CG
-    V = R.VCycle(widths, (0,) * dim, 0.01)
-    dg = M.diagonal()
-
-    def block_pc(v):
-        z = np.empty_like(v)
-        z[:pN] = V.apply(v[:pN])
-        z[pN:] = v[pN:] / dg[pN:]
-        return z
-
-    xr, hr, _, _ = R.pcg(M, b, block_pc, False, 0.0, 0.0, 6, nullvec=nv)
-    s.setOptions(pc_type="mg", rtol=0.0, atol=0.0, max_it=6)
-    with pytest.raises(pb.B200Error):
-        s.solve(x, b)
-    np.testing.assert_allclose(s.getHistory(), hr, rtol=1e-8)
-    s.setOptions(rtol=1e-9, atol=1e-50, max_it=500)
-    s.solve(x, b)
-    c.setOptions(rtol=1e-9, atol=1e-50, max_it=5000)
-    c.solve(xc, b)
-    assert s.getReason() == c.getReason() == 2 and 3 * s.getIters() <= c.getIters(), (s.getIters(), c.getIters())
-    np.testing.assert_allclose(x, xs, rtol=0, atol=1e-6 * np.abs(xs).max())
     s.destroy(); c.destroy()

@@ -41,14 +41,14 @@ def test_operators_are_the_assembled_products(pb, shape, per):
 
 
 def test_device_resident_projection_step(pb):
-    """One fractional-step projection with everything on the device: rhs2 = D u*, CG (multigrid-preconditioned) for dP,
-    u = u* - BNG dP.  The projected field is divergence-free to the tolerance of the solve."""
+    """One fractional-step projection with everything on the device: rhs2 = D u*, CG for dP, u = u* - BNG dP.  The
+    projected field is divergence-free to the tolerance of the solve."""
     import torch
 
     shape, per = (48, 40, 32), (0, 0, 0)
     widths = H.make_widths(shape)
     s = pb.LinSolverB200("poisson", "None")
-    s.setOptions(pc_type="mg", rtol=1e-10, atol=1e-50, max_it=200)
+    s.setOptions(pc_type="jacobi", rtol=1e-10, atol=1e-50, max_it=5000)
     s.setStencil(H.grid_of(widths, per))
     s.setNullSpace(True)
     nv, npr = s.velocitySize()

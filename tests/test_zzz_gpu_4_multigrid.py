@@ -115,3 +115,48 @@ def test_multigrid_needs_the_separable_operator(pb):
         s.solve(np.empty(A.shape[0]), np.ones(A.shape[0]))
     assert ei.value.code == -3
     s.destroy()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_block_multigrid_on_a_stretched_ibpm_system(pb, dim):
+    """[D;E] BN [G,-H] on a stretched grid in hybrid form (tests/test_zzz_gpu_2_staggered.py) with -poisson_pc_type mg:
+    V-cycle on the pressure block, diagonal on the force rows, the explicit null-space vector of ibpm.cpp:251-267 --
+    histories of the numpy restatement, same solution as Jacobi CG in a fraction of the iterations."""
+    n_side, n_band = (6, 10) if dim == 3 else (12, 24)
+    sub = [{"end": 0.6, "cells": n_side, "stretchRatio": 1.0 / 1.2}, {"end": 1.4, "cells": n_band, "stretchRatio": 1.0},
+           {"end": 2.0, "cells": n_side, "stretchRatio": 1.2}]
+    w = orc.axis_from_subdomains(0.0, sub)
+    widths = [w.copy() for _ in range(dim)]
+    M, pN, nv = H.ibpm_system(widths, dt=0.01, nb=14)
+    Mo = orc.Csr.from_arrays(M.shape[0], M.shape[1], M.indptr, M.indices, M.data)
+    rng = np.random.default_rng(4)
+    xs = rng.standard_normal(M.shape[0]); xs -= (xs @ nv) * nv
+    b = Mo.spmv(xs)
+    V = R.VCycle(widths, (0,) * dim, 0.01)
+    dg = M.diagonal()
+
+    def block_pc(v):
+        z = np.empty_like(v)
+        z[:pN] = V.apply(v[:pN])
+        z[pN:] = v[pN:] / dg[pN:]
+        return z
+
+    xr, hr, _, _ = R.pcg(M, b, block_pc, False, 0.0, 0.0, 6, nullvec=nv)
+    s = pb.LinSolverB200("poisson", "None")
+    s.setOptions(pc_type="mg", rtol=0.0, atol=0.0, max_it=6)
+    s.setGrid(pb.Grid(widths, (False, False, False), 0.01))
+    s.setMatrix(pb.Mat.from_scipy(M).setNullSpace(False, nv))
+    assert s.operator == "hybrid"
+    x = np.empty_like(b)
+    with pytest.raises(pb.B200Error):
+        s.solve(x, b)
+    np.testing.assert_allclose(s.getHistory(), hr, rtol=1e-8)
+    s.setOptions(rtol=1e-9, atol=1e-50, max_it=500)
+    s.solve(x, b)
+    its_mg = s.getIters()
+    s.setOptions(pc_type="jacobi", max_it=5000)
+    xj = np.empty_like(b)
+    s.solve(xj, b)
+    assert s.getReason() == 2 and 3 * its_mg <= s.getIters(), (its_mg, s.getIters())
+    np.testing.assert_allclose(x, xs, rtol=0, atol=1e-6 * np.abs(xs).max())
+    s.destroy()
