@@ -26,7 +26,6 @@
 #include "csr_kernels.cuh"
 #include "sep_kernels.cuh"
 #include "mg_kernels.cuh"
-#include "mg_schedule.h"
 #include "ops_kernels.cuh"
 
 using namespace b200;
@@ -130,6 +129,12 @@ struct b200ls_solver
     bool mg_ready = false;
     int mg_built_levels = 0;
     int64_t mg_graph_launches = 0;
+    int mg_tail = 0;         // tuning "mg_tail": the coarse levels of the cycle as one launch (k_mg_tail; off until timed)
+    MgOp *mg_tail_ops = nullptr;
+    MgLevel *mg_tail_levels = nullptr;
+    int mg_tail_nops = 0;
+    int mg_tail_degrees[2] = {0, 0};
+    double *mg_tail_result = nullptr;
     int mg_graph = 0;        // tuning "mg_graph": replay pairs of preconditioned iterations as one CUDA graph (off until timed)
 
     // ---- vectors (solver layout)
@@ -1228,6 +1233,7 @@ int b200ls_set_tuning(b200ls_solver *h, const char *key, int value)
     else if (k == "use_graph") h->use_graph = value;
     else if (k == "use_pdl") h->use_pdl = value;
     else if (k == "mg_graph") h->mg_graph = value;
+    else if (k == "mg_tail") h->mg_tail = value;
     else return fail(h, B200LS_ERR_ARG, "unknown tuning key %s", key);
     invalidate_graph(h);
     return B200LS_OK;

@@ -31,6 +31,7 @@
 #include <stdint.h>
 
 #include "kernels.cuh"
+#include "mg_schedule.h"
 
 namespace b200 {
 
@@ -111,13 +112,15 @@ __device__ __forceinline__ long long mg_coarse_index(const MgLevel &L, const MgL
     return Lc.base + L.mx[i] + (long long)Lc.px * L.my[j] + Lc.plane * L.mz[k];
 }
 
+// ---- bodies: (t0, stride) = the calling thread's first cell and the number of cooperating threads, so that the same
+// code runs as a grid-stride kernel of its own or as one step of the single-CTA tail below
+
 // first Chebyshev step from a zero guess: d = (1/theta) D^-1 b   (x stays implicit zero)
-__global__ void __launch_bounds__(256) k_mg_cheb_first(MgLevel L, const double *b, double *dout, double inv_theta,
-                                                       const DevState *st)
+__device__ __forceinline__ void mg_first_body(const MgLevel &L, const double *b, double *dout, double inv_theta, long long t0,
+                                              long long stride)
 {
-    if (st->done) return;
     const long long n = (long long)L.nx * L.ny * L.nz;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+    for (long long t = t0; t < n; t += stride)
     {
         int i, j, k;
         mg_cell(L, t, i, j, k);
@@ -132,13 +135,12 @@ __global__ void __launch_bounds__(256) k_mg_cheb_first(MgLevel L, const double *
 // XZERO / DZERO: x / d is implicitly zero (not read).  PROLONG: the coarse-grid correction e_c of the next level is
 // added on the fly (piecewise-constant prolongation folded into the first post-smoothing step).
 template <bool XZERO, bool DZERO, bool PROLONG, bool LAST>
-__global__ void __launch_bounds__(256) k_mg_cheb_step(MgLevel L, MgLevel Lc, const double *b, const double *xin,
-                                                      const double *din, const double *ec, double *xout, double *dout,
-                                                      double c1, double c2, const DevState *st)
+__device__ __forceinline__ void mg_step_body(const MgLevel &L, const MgLevel &Lc, const double *b, const double *xin,
+                                             const double *din, const double *ec, double *xout, double *dout, double c1, double c2,
+                                             long long t0, long long stride)
 {
-    if (st->done) return;
     const long long n = (long long)L.nx * L.ny * L.nz;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+    for (long long t = t0; t < n; t += stride)
     {
         int i, j, k;
         mg_cell(L, t, i, j, k);
@@ -173,12 +175,11 @@ __global__ void __launch_bounds__(256) k_mg_cheb_step(MgLevel L, MgLevel Lc, con
 // residual + restriction: v = x + d is materialised (xsum), b_c(I,J,K) = sum over the merged fine cells of (b - A v).
 // One thread per COARSE cell.
 template <bool XZERO>
-__global__ void __launch_bounds__(256) k_mg_restrict(MgLevel L, MgLevel Lc, const double *b, const double *xin, const double *din,
-                                                     double *xsum, double *bc, const DevState *st)
+__device__ __forceinline__ void mg_restrict_body(const MgLevel &L, const MgLevel &Lc, const double *b, const double *xin,
+                                                 const double *din, double *xsum, double *bc, long long t0, long long stride)
 {
-    if (st->done) return;
     const long long nc = (long long)Lc.nx * Lc.ny * Lc.nz;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nc; t += (long long)gridDim.x * blockDim.x)
+    for (long long t = t0; t < nc; t += stride)
     {
         int I, J, K;
         mg_cell(Lc, t, I, J, K);
@@ -196,6 +197,78 @@ __global__ void __launch_bounds__(256) k_mg_restrict(MgLevel L, MgLevel Lc, cons
                     acc += b[r.j[3]] - mg_apply(r, val);
                 }
         bc[Lc.base + I + (long long)Lc.px * J + Lc.plane * K] = acc;
+    }
+}
+
+// ---- one kernel per step (levels with enough cells to fill the machine)
+__global__ void __launch_bounds__(256) k_mg_cheb_first(MgLevel L, const double *b, double *dout, double inv_theta,
+                                                       const DevState *st)
+{
+    if (st->done) return;
+    mg_first_body(L, b, dout, inv_theta, blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+
+template <bool XZERO, bool DZERO, bool PROLONG, bool LAST>
+__global__ void __launch_bounds__(256) k_mg_cheb_step(MgLevel L, MgLevel Lc, const double *b, const double *xin,
+                                                      const double *din, const double *ec, double *xout, double *dout,
+                                                      double c1, double c2, const DevState *st)
+{
+    if (st->done) return;
+    mg_step_body<XZERO, DZERO, PROLONG, LAST>(L, Lc, b, xin, din, ec, xout, dout, c1, c2,
+                                              blockIdx.x * (long long)blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+
+template <bool XZERO>
+__global__ void __launch_bounds__(256) k_mg_restrict(MgLevel L, MgLevel Lc, const double *b, const double *xin, const double *din,
+                                                     double *xsum, double *bc, const DevState *st)
+{
+    if (st->done) return;
+    mg_restrict_body<XZERO>(L, Lc, b, xin, din, xsum, bc, blockIdx.x * (long long)blockDim.x + threadIdx.x,
+                            (long long)gridDim.x * blockDim.x);
+}
+
+// ---- the coarse tail of the cycle as ONE launch.  Below a few thousand cells every step above is a launch that costs
+// more than its work (a V(2,2) cycle on 256^3 has ~36 of them under 16^3).  The steps of the levels >= tail_level are
+// recorded once, in schedule order (mg_schedule.h: the recording launcher), and interpreted here by a single CTA with a
+// block barrier between steps; the bodies are the ones above, so the numbers are the same bit for bit.
+__global__ void __launch_bounds__(512) k_mg_tail(const MgLevel *levels, const MgOp *ops, int nops, const DevState *st)
+{
+    if (st->done) return;
+    const long long t0 = threadIdx.x, stride = blockDim.x;
+    for (int q = 0; q < nops; ++q)
+    {
+        const MgOp op = ops[q];
+        const MgLevel &L = levels[op.l];
+        if (op.kind == 0) mg_first_body(L, op.b, op.dout, op.c2, t0, stride);
+        else if (op.kind == 2)
+        {
+            const MgLevel &Lc = levels[op.l + 1];
+            if (op.xzero) mg_restrict_body<true>(L, Lc, op.b, op.xin, op.din, op.xout, op.dout, t0, stride);
+            else mg_restrict_body<false>(L, Lc, op.b, op.xin, op.din, op.xout, op.dout, t0, stride);
+        }
+        else
+        {
+            const MgLevel &Lc = levels[op.prolong ? op.l + 1 : op.l];
+#define B200_MG_TAIL(XZ, DZ, PR, LA) \
+    mg_step_body<XZ, DZ, PR, LA>(L, Lc, op.b, op.xin, op.din, op.ec, op.xout, op.dout, op.c1, op.c2, t0, stride)
+            if (op.prolong)
+            {
+                if (op.last) B200_MG_TAIL(false, true, true, true);
+                else B200_MG_TAIL(false, true, true, false);
+            }
+            else if (op.xzero)
+            {
+                if (op.last) B200_MG_TAIL(true, false, false, true);
+                else B200_MG_TAIL(true, false, false, false);
+            }
+            else
+            {
+                if (op.last) B200_MG_TAIL(false, false, false, true);
+                else B200_MG_TAIL(false, false, false, false);
+            }
+#undef B200_MG_TAIL
+        }
+        __syncthreads();  // the next step reads what this one wrote (global memory, same block)
     }
 }
 

@@ -112,6 +112,7 @@ struct MgParams
     int smooth_its = 2;        // Chebyshev degree before and after the coarse correction
     int coarse_its = 16;       // Chebyshev degree on the coarsest level
     double lmax = 2.0;         // Gershgorin bound of D^-1 A (rows sum to zero)
+    int tail_level = -1;       // >= 1: levels from here down run as ONE launch (Launcher::tail), see k_mg_tail
     double smooth_ratio = 5.0; // smoothing interval [lmax / ratio, lmax] (tuned on uniform and PetIBM-like stretched grids)
     double coarse_ratio = 40.0;
 };
@@ -139,10 +140,50 @@ struct MgCheb
     }
 };
 
+// One recorded step of the cycle (k_mg_tail interprets a list of these in a single CTA)
+struct MgOp
+{
+    int kind;                  // 0 first, 1 step, 2 restrict
+    int l;                     // level
+    int xzero, dzero, prolong, last;
+    const double *b, *xin, *din, *ec;
+    double *xout, *dout;       // restrict: xout = xsum, dout = coarse right-hand side
+    double c1, c2;             // first: c2 = 1/theta
+};
+
+// launcher that writes the steps down instead of running them
+struct MgProgramRecorder
+{
+    std::vector<MgOp> ops;
+    void first(int l, const double *b, double *dout, double inv_theta)
+    {
+        ops.push_back(MgOp{0, l, 1, 0, 0, 0, b, nullptr, nullptr, nullptr, nullptr, dout, 0.0, inv_theta});
+    }
+    void step(int l, bool xzero, bool dzero, bool prolong, bool last, const double *b, const double *xin, const double *din,
+              const double *ec, double *xout, double *dout, double c1, double c2)
+    {
+        ops.push_back(MgOp{1, l, xzero, dzero, prolong, last, b, xin, din, ec, xout, dout, c1, c2});
+    }
+    void restrict(int l, bool xzero, const double *b, const double *xin, const double *din, double *xsum, double *bc)
+    {
+        ops.push_back(MgOp{2, l, xzero, 0, 0, 0, b, xin, din, nullptr, xsum, bc, 0.0, 0.0});
+    }
+    double *tail() { return nullptr; }
+};
+
+// the level from which the rest of the cycle is small enough for one CTA (or -1)
+inline int mg_tail_level(const std::vector<MgHostLevel> &lv, int64_t max_cells)
+{
+    for (size_t l = 1; l < lv.size(); ++l)
+        if (lv[l].cells() <= max_cells) return (int)l;
+    return -1;
+}
+
 // One V-cycle on level l for the right-hand side b; returns the buffer that holds the result.
 //   work[l][0..3]: four work vectors of level l;  rhs[l]: right-hand side of level l (l > 0).
 // Launcher: first(l, b, dout, inv_theta); step(l, xzero, dzero, prolong, last, b, xin, din, ec, xout, dout, c1, c2);
-//           restrict(l, xzero, b, xin, din, xsum, b_coarse)
+//           restrict(l, xzero, b, xin, din, xsum, b_coarse); tail(): runs the recorded steps of the levels >= prm.tail_level
+//           on rhs[tail_level] and returns that level's result buffer
 template <class Launcher>
 double *mg_cycle(int l, int nlevels, const double *b, double *const (*work)[4], double *const *rhs, const MgParams &prm,
                  Launcher &L)
@@ -173,7 +214,7 @@ double *mg_cycle(int l, int nlevels, const double *b, double *const (*work)[4], 
     // ---- residual of x + d, restricted; x + d is materialised
     double *xs = pick(x, d, nullptr);
     L.restrict(l, x == nullptr, b, x, d, xs, rhs[l + 1]);
-    const double *ec = mg_cycle(l + 1, nlevels, rhs[l + 1], work, rhs, prm, L);
+    const double *ec = (l + 1 == prm.tail_level) ? L.tail() : mg_cycle(l + 1, nlevels, rhs[l + 1], work, rhs, prm, L);
     // ---- post-smoothing: deg updates starting from xs + P e_c (prolongation folded into the first step)
     MgCheb cp(prm.lmax, prm.smooth_ratio);
     {

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--pcs", nargs="+", default=["none", "jacobi", "mg"])
     ap.add_argument("--smooth", type=int, default=2)
     ap.add_argument("--mg-graph", type=int, default=0, help="replay pairs of multigrid-preconditioned iterations as a CUDA graph")
+    ap.add_argument("--mg-tail", type=int, default=0, help="coarse levels of the cycle as one launch (k_mg_tail)")
     args = ap.parse_args()
     n = tuple(args.size)
     rng = np.random.default_rng(20240521)
@@ -39,6 +40,7 @@ def main():
         s = pb.LinSolverB200("poisson", "None")
         s.setOptions(pc_type=pc, rtol=args.rtol, atol=1e-50, max_it=20000, mg_smooth_its=args.smooth)
         s.setTuning("mg_graph", args.mg_graph)
+        s.setTuning("mg_tail", args.mg_tail)
         s.setStencil(grid)
         s.setNullSpace(True)
         if b is None:
@@ -52,7 +54,7 @@ def main():
         err = float(np.abs((x - x.mean()) - xs).max() / np.abs(xs).max())
         print(json.dumps({"size": list(n), "stretched": args.stretched, "pc": pc, "rtol": args.rtol, "iterations": s.getIters(),
                           "reason": s.getReason(), "solve_ms": round(best["solve_ms"], 3), "launches": best["launches"],
-                          "max_rel_error": err, "mg_graph": args.mg_graph}), flush=True)
+                          "max_rel_error": err, "mg_graph": args.mg_graph, "mg_tail": args.mg_tail}), flush=True)
         s.destroy()
 
 

@@ -56,6 +56,22 @@ struct Recorder
         wr(xout, l);
         if (!last) wr(dout, l);
     }
+    // the recorded tail of the cycle, replayed through the same checks (what k_mg_tail does in one launch)
+    std::vector<MgOp> tail_ops;
+    double *tail_result = nullptr;
+    int tail_launches = 0;
+    double *tail()
+    {
+        const int before = launches;
+        for (const MgOp &op : tail_ops)
+        {
+            if (op.kind == 0) first(op.l, op.b, op.dout, op.c2);
+            else if (op.kind == 1) step(op.l, op.xzero, op.dzero, op.prolong, op.last, op.b, op.xin, op.din, op.ec, op.xout, op.dout, op.c1, op.c2);
+            else restrict(op.l, op.xzero, op.b, op.xin, op.din, op.xout, op.dout);
+        }
+        tail_launches += launches - before;
+        return tail_result;
+    }
     void restrict(int l, bool xzero, const double *b, const double *xin, const double *din, double *xsum, double *bc)
     {
         ++launches;
@@ -105,6 +121,24 @@ int main()
                 {
                     std::fprintf(stderr, "nl %d sm %d co %d: %d launches, expected %d\n", nl, sm, co, R.launches, want);
                     ok = false;
+                }
+                // with the coarse levels recorded and replayed as a tail (every possible tail level): same launches in the
+                // same order, same result buffer
+                for (int tl = 1; tl < nl && ok; ++tl)
+                {
+                    MgProgramRecorder rec;
+                    MgParams p0 = prm;
+                    p0.tail_level = -1;
+                    double *tres = mg_cycle(tl, nl, rhs[tl], work, rhs, p0, rec);
+                    Recorder RT;
+                    RT.level_of = R.level_of;
+                    RT.version[b0] = 1;
+                    RT.tail_ops = rec.ops;
+                    RT.tail_result = tres;
+                    MgParams p1 = prm;
+                    p1.tail_level = tl;
+                    double *zt = mg_cycle(0, nl, b0, work, rhs, p1, RT);
+                    ok = ok && zt == z && RT.errors == 0 && RT.launches == want && (int)rec.ops.size() == RT.tail_launches;
                 }
                 // the schedule is the same in every cycle: a second cycle returns the same buffer
                 Recorder R2 = R;

@@ -12,7 +12,6 @@
 #include "csr_kernels.cuh"
 #include "sep_kernels.cuh"
 #include "mg_kernels.cuh"
-#include "mg_schedule.h"
 #include "ops_kernels.cuh"
 
 using namespace b200;
@@ -623,17 +622,44 @@ struct MgEmu
         if (xzero) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_mg_restrict<true>(L, Lc, b, xin, din, xsum, bc, st); });
         else emu::launch(dim3(blocks), dim3(256), 0, [&] { k_mg_restrict<false>(L, Lc, b, xin, din, xsum, bc, st); });
     }
-    double *cycle(const double *r)
+    std::vector<MgOp> tail_ops;
+    double *tail_result = nullptr;
+    double *tail()
     {
-        const int nl = (int)dev.size();
+        const MgLevel *lv = dev.data();
+        const MgOp *ops = tail_ops.data();
+        const int nops = (int)tail_ops.size();
+        emu::launch(dim3(1), dim3(512), 0, [&] { k_mg_tail(lv, ops, nops, st); });
+        return tail_result;
+    }
+    void pointers(double *(*work)[4], double **rhs)
+    {
+        for (size_t l = 0; l < dev.size(); ++l)
+        {
+            for (int q = 0; q < 4; ++q) work[l][q] = bufs[l][(size_t)q].data();
+            rhs[l] = l > 0 ? bufs[l][4].data() : nullptr;
+        }
+    }
+    // tail_cells > 0: the levels with at most that many cells run as one launch (record_mg_tail of mg_solver.inc)
+    void record_tail(int64_t tail_cells)
+    {
+        prm.tail_level = -1;
+        const int tl = tail_cells > 0 ? mg_tail_level(host, tail_cells) : -1;
+        if (tl < 1) return;
         double *work[32][4];
         double *rhs[32];
-        for (int l = 0; l < nl; ++l)
-        {
-            for (int q = 0; q < 4; ++q) work[l][q] = bufs[(size_t)l][(size_t)q].data();
-            rhs[l] = l > 0 ? bufs[(size_t)l][4].data() : nullptr;
-        }
-        return mg_cycle(0, nl, r, work, rhs, prm, *this);
+        pointers(work, rhs);
+        MgProgramRecorder rec;
+        tail_result = mg_cycle(tl, (int)dev.size(), rhs[tl], work, rhs, prm, rec);
+        tail_ops = rec.ops;
+        prm.tail_level = tl;
+    }
+    double *cycle(const double *r)
+    {
+        double *work[32][4];
+        double *rhs[32];
+        pointers(work, rhs);
+        return mg_cycle(0, (int)dev.size(), r, work, rhs, prm, *this);
     }
 };
 
@@ -694,7 +720,7 @@ extern "C" {
 // mode 0: x_out = M^-1 b (one V-cycle);  mode 1: KSPSolve_CG preconditioned with the V-cycle (solve_stencil_pcg_mg)
 EMU_API int emu_mg(int dim, const int64_t *n, const int *per, const double *dx, const double *dy, const double *dz, double dt,
                    int mode, int has_const, double rtol, double atol, int max_it, int max_levels, int smooth_its, int coarse_its,
-                   int tile, const double *b, double *x_out, double *hist, int hist_cap, int *nhist, int *its, int *reason,
+                   int tile, int tail_cells, const double *b, double *x_out, double *hist, int hist_cap, int *nhist, int *its, int *reason,
                    int *nlevels)
 {
     Problem P;
@@ -702,6 +728,7 @@ EMU_API int emu_mg(int dim, const int64_t *n, const int *per, const double *dx, 
     Ws W;
     MgEmu M;
     mg_setup(M, P, dim, n, dt, max_levels, smooth_its, coarse_its);
+    M.record_tail(tail_cells);
     *nlevels = (int)M.dev.size();
     const size_t ve = P.vec_elems;
     std::vector<double> r(ve, 0.0), p0(ve, 0.0), p1(ve, 0.0), w(ve, 0.0), x(ve, 0.0);

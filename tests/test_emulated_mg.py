@@ -14,16 +14,18 @@ from tests import mg_reference as R
 from tests.test_emulated_kernels import emu, _grid_args, _cg, _dp, _ip  # noqa: F401  (emu is a fixture)
 
 
-def _mg(L, widths, per, b, mode="pcg", has_const=True, rtol=0.0, atol=0.0, max_it=20, levels=0, smooth=2, coarse=16, tile=10):
+def _mg(L, widths, per, b, mode="pcg", has_const=True, rtol=0.0, atol=0.0, max_it=20, levels=0, smooth=2, coarse=16, tile=10,
+        tail_cells=0):
     dim, n, p, w, dz = _grid_args(widths, per)
     L.emu_mg.argtypes = [C.c_int, C.POINTER(C.c_int64), _ip, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double,
-                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _ip, _ip, _ip, _ip]
+                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _ip, _ip, _ip, _ip]
     b = np.ascontiguousarray(b, dtype=np.float64)
     x = np.empty_like(b)
     hist = np.zeros(max_it + 2)
     nh, its, reason, nl = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
     rc = L.emu_mg(dim, n, p, w[0].ctypes.data_as(_dp), w[1].ctypes.data_as(_dp), dz, 0.01, {"apply": 0, "pcg": 1}[mode],
-                  int(has_const), rtol, atol, max_it, levels, smooth, coarse, tile, b.ctypes.data_as(_dp), x.ctypes.data_as(_dp),
+                  int(has_const), rtol, atol, max_it, levels, smooth, coarse, tile, int(tail_cells), b.ctypes.data_as(_dp),
+                  x.ctypes.data_as(_dp),
                   hist.ctypes.data_as(_dp), hist.size, C.byref(nh), C.byref(its), C.byref(reason), C.byref(nl))
     assert rc == 0
     return x, hist[: nh.value].copy(), its.value, reason.value, nl.value
@@ -222,3 +224,22 @@ def test_emulated_mg_edge_cases(emu):
     x, hist, its, reason, nl = _mg(emu, tiny, (0, 0, 0), b, rtol=1e-10, max_it=60)
     assert nl == 1 and reason == 2
     np.testing.assert_allclose(x, xs, rtol=0, atol=1e-8 * np.abs(xs).max())
+
+
+@pytest.mark.parametrize("shape,per", [((16, 12, 8), (0, 0, 0)), ((12, 16, 8), (1, 0, 1)), ((24, 20), (0, 0))])
+@pytest.mark.parametrize("smooth", [1, 2, 3])
+def test_emulated_single_cta_tail_gives_the_same_numbers(emu, shape, per, smooth):
+    """Tuning "mg_tail": the coarse levels of the cycle interpreted by ONE CTA (k_mg_tail) from the recorded schedule --
+    same bodies, same order, so z = M^-1 r and the PCG history are identical bit for bit to the launch-per-step cycle."""
+    widths = H.make_widths(shape)
+    r = np.random.default_rng(5).standard_normal(int(np.prod(shape)))
+    r -= r.mean()
+    z0, _, _, _, nl = _mg(emu, widths, per, r, mode="apply", smooth=smooth, coarse=7)
+    for cells in (2000, 200, 30):                      # tail starts at different levels
+        z1, _, _, _, _ = _mg(emu, widths, per, r, mode="apply", smooth=smooth, coarse=7, tail_cells=cells)
+        assert np.array_equal(z0, z1), cells
+    A = H.oracle_matrix(widths, per)
+    b, _ = H.consistent_rhs(A)
+    x0, h0, i0, r0, _ = _mg(emu, widths, per, b, rtol=1e-9, max_it=40, smooth=smooth)
+    x1, h1, i1, r1, _ = _mg(emu, widths, per, b, rtol=1e-9, max_it=40, smooth=smooth, tail_cells=200)
+    assert (i0, r0) == (i1, r1) and np.array_equal(h0, h1) and np.array_equal(x0, x1)
