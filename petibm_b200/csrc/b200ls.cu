@@ -129,6 +129,7 @@ struct b200ls_solver
     bool mg_ready = false;
     int mg_built_levels = 0;
     int64_t mg_graph_launches = 0;
+    int mg_fuse = 0;         // tuning "mg_fuse": r -= a w and the six sums ride on the first / last fine-level step of the cycle
     int mg_tail = 0;         // tuning "mg_tail": the coarse levels of the cycle as one launch (k_mg_tail; off until timed)
     MgOp *mg_tail_ops = nullptr;
     MgLevel *mg_tail_levels = nullptr;
@@ -1234,6 +1235,7 @@ int b200ls_set_tuning(b200ls_solver *h, const char *key, int value)
     else if (k == "use_pdl") h->use_pdl = value;
     else if (k == "mg_graph") h->mg_graph = value;
     else if (k == "mg_tail") h->mg_tail = value;
+    else if (k == "mg_fuse") h->mg_fuse = value;
     else return fail(h, B200LS_ERR_ARG, "unknown tuning key %s", key);
     invalidate_graph(h);
     return B200LS_OK;

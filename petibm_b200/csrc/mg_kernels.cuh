@@ -134,10 +134,15 @@ __device__ __forceinline__ void mg_first_body(const MgLevel &L, const double *b,
 //   x' = v + d'     when LAST (nothing follows).
 // XZERO / DZERO: x / d is implicitly zero (not read).  PROLONG: the coarse-grid correction e_c of the next level is
 // added on the fly (piecewise-constant prolongation folded into the first post-smoothing step).
-template <bool XZERO, bool DZERO, bool PROLONG, bool LAST>
+struct MgNoHook
+{
+    __device__ __forceinline__ void operator()(long long, double) const {}
+};
+
+template <bool XZERO, bool DZERO, bool PROLONG, bool LAST, class Hook = MgNoHook>
 __device__ __forceinline__ void mg_step_body(const MgLevel &L, const MgLevel &Lc, const double *b, const double *xin,
                                              const double *din, const double *ec, double *xout, double *dout, double c1, double c2,
-                                             long long t0, long long stride)
+                                             long long t0, long long stride, Hook hook = Hook())
 {
     const long long n = (long long)L.nx * L.ny * L.nz;
     for (long long t = t0; t < n; t += stride)
@@ -167,8 +172,10 @@ __device__ __forceinline__ void mg_step_body(const MgLevel &L, const MgLevel &Lc
         const double res = b[r.j[3]] - mg_apply(r, val);
         const double dold = DZERO ? 0.0 : din[r.j[3]];
         const double dnew = r.c[3] != 0.0 ? c1 * dold + c2 * (res / r.c[3]) : 0.0;
-        xout[r.j[3]] = LAST ? vc + dnew : vc;
+        const double xnew = LAST ? vc + dnew : vc;
+        xout[r.j[3]] = xnew;
         if (!LAST) dout[r.j[3]] = dnew;
+        hook(r.j[3], xnew);
     }
 }
 
@@ -270,6 +277,50 @@ __global__ void __launch_bounds__(512) k_mg_tail(const MgLevel *levels, const Mg
         }
         __syncthreads();  // the next step reads what this one wrote (global memory, same block)
     }
+}
+
+// ---- tuning "mg_fuse": the two CG passes around the cycle folded into its first and last fine-level steps
+// first step + residual update: r <- r - a w (VecAXPY(R, -a, W)), d = (1/theta) D^-1 r      (k_mg_rupdate + k_mg_cheb_first)
+__global__ void __launch_bounds__(256) k_mg_first_rupd(MgLevel L, double *r, const double *w, double *dout, double inv_theta,
+                                                       const DevState *st)
+{
+    if (st->done) return;
+    const double ma = -st->a;
+    const long long n = (long long)L.nx * L.ny * L.nz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+    {
+        int i, j, k;
+        mg_cell(L, t, i, j, k);
+        const MgRow row = mg_row(L, i, j, k);
+        const double rn = __dadd_rn(r[row.j[3]], __dmul_rn(ma, w[row.j[3]]));
+        r[row.j[3]] = rn;
+        dout[row.j[3]] = row.c[3] != 0.0 ? inv_theta * (rn / row.c[3]) : 0.0;
+    }
+}
+
+// last step + the six sums of k_mg_zsums for the z it produces (b is the residual r)      (last step + k_mg_zsums)
+template <bool PROLONG>
+__global__ void __launch_bounds__(256) k_mg_last_sums(MgLevel L, MgLevel Lc, const double *b, const double *xin, const double *din,
+                                                      const double *ec, double *xout, double c1, double c2, int fin_kind,
+                                                      ReduceWs ws, CommDev cm, DevState *st, SolveConsts kc, double *hist)
+{
+    if (st->done) return;
+    const double c = st->c;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    auto hook = [&](long long idx, double z0) {
+        const double rn = b[idx];
+        const double d0 = z0 - c;
+        acc[0] += z0;
+        acc[1] += d0;
+        acc[2] = fma(d0, d0, acc[2]);
+        acc[3] = fma(d0, rn, acc[3]);
+        acc[4] += rn;
+        acc[5] = fma(rn, rn, acc[5]);
+    };
+    const long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    if (PROLONG) mg_step_body<false, true, true, true>(L, Lc, b, xin, din, ec, xout, nullptr, c1, c2, t0, stride, hook);
+    else mg_step_body<false, false, false, true>(L, Lc, b, xin, din, ec, xout, nullptr, c1, c2, t0, stride, hook);
+    grid_reduce_finalize<6>(acc, fin_kind, ws, cm, st, kc, hist, false);
 }
 
 // PCG with an explicit z = M^-1 r: the residual update on its own (the sums need z, which the cycle produces next)

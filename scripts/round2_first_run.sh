@@ -30,6 +30,7 @@ run tts_256 600 python scripts/tts_bench.py --size 256 256 256 --pcs jacobi mg
 run tts_128_graph 300 python scripts/tts_bench.py --size 128 128 128 --pcs mg --mg-graph 1
 run tts_128_tail 300 python scripts/tts_bench.py --size 128 128 128 --pcs mg --mg-tail 1
 run tts_256_tail 300 python scripts/tts_bench.py --size 256 256 256 --pcs mg --mg-tail 1
+run tts_256_tail_fuse 300 python scripts/tts_bench.py --size 256 256 256 --pcs mg --mg-tail 1 --mg-fuse 1
 run tts_2d_tail_graph 300 python scripts/tts_bench.py --size 448 448 --pcs mg --mg-tail 1 --mg-graph 1
 run tts_2d_graph 300 python scripts/tts_bench.py --size 448 448 --pcs mg --mg-graph 1
 run tts_2d 300 python scripts/tts_bench.py --size 448 448 --pcs jacobi mg

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--smooth", type=int, default=2)
     ap.add_argument("--mg-graph", type=int, default=0, help="replay pairs of multigrid-preconditioned iterations as a CUDA graph")
     ap.add_argument("--mg-tail", type=int, default=0, help="coarse levels of the cycle as one launch (k_mg_tail)")
+    ap.add_argument("--mg-fuse", type=int, default=0, help="residual update and reduction folded into the cycle's first/last step")
     args = ap.parse_args()
     n = tuple(args.size)
     rng = np.random.default_rng(20240521)
@@ -41,6 +42,7 @@ def main():
         s.setOptions(pc_type=pc, rtol=args.rtol, atol=1e-50, max_it=20000, mg_smooth_its=args.smooth)
         s.setTuning("mg_graph", args.mg_graph)
         s.setTuning("mg_tail", args.mg_tail)
+        s.setTuning("mg_fuse", args.mg_fuse)
         s.setStencil(grid)
         s.setNullSpace(True)
         if b is None:
@@ -54,7 +56,7 @@ def main():
         err = float(np.abs((x - x.mean()) - xs).max() / np.abs(xs).max())
         print(json.dumps({"size": list(n), "stretched": args.stretched, "pc": pc, "rtol": args.rtol, "iterations": s.getIters(),
                           "reason": s.getReason(), "solve_ms": round(best["solve_ms"], 3), "launches": best["launches"],
-                          "max_rel_error": err, "mg_graph": args.mg_graph, "mg_tail": args.mg_tail}), flush=True)
+                          "max_rel_error": err, "mg_graph": args.mg_graph, "mg_tail": args.mg_tail, "mg_fuse": args.mg_fuse}), flush=True)
         s.destroy()
 
 

@@ -601,15 +601,32 @@ struct MgEmu
     MgParams prm;
     DevState *st = nullptr;
     int blocks = 3;
+    // "mg_fuse" (see MgCudaLauncher)
+    bool fuse_rupdate = false, sums_done = false;
+    int fuse_sums_kind = -1;
+    double *fuse_r = nullptr;
+    const double *fuse_w = nullptr;
+    Ws *fuse_W = nullptr;
+    SolveConsts fuse_kc{};
+    double *fuse_hist = nullptr;
     void first(int l, const double *b, double *dout, double inv_theta)
     {
         const MgLevel L = dev[(size_t)l];
-        emu::launch(dim3(blocks), dim3(256), 0, [&] { k_mg_cheb_first(L, b, dout, inv_theta, st); });
+        if (l == 0 && fuse_rupdate) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_mg_first_rupd(L, fuse_r, fuse_w, dout, inv_theta, st); });
+        else emu::launch(dim3(blocks), dim3(256), 0, [&] { k_mg_cheb_first(L, b, dout, inv_theta, st); });
     }
     void step(int l, bool xzero, bool, bool prolong, bool last, const double *b, const double *xin, const double *din,
               const double *ec, double *xout, double *dout, double c1, double c2)
     {
         const MgLevel L = dev[(size_t)l], Lc = dev[(size_t)std::min<int>(l + 1, (int)dev.size() - 1)];
+        if (l == 0 && last && !xzero && fuse_sums_kind >= 0)
+        {
+            const int kind = fuse_sums_kind;
+            if (prolong) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_mg_last_sums<true>(L, Lc, b, xin, din, ec, xout, c1, c2, kind, fuse_W->ws, fuse_W->cm, st, fuse_kc, fuse_hist); });
+            else emu::launch(dim3(blocks), dim3(256), 0, [&] { k_mg_last_sums<false>(L, Lc, b, xin, din, ec, xout, c1, c2, kind, fuse_W->ws, fuse_W->cm, st, fuse_kc, fuse_hist); });
+            sums_done = true;
+            return;
+        }
 #define EMU_MG(XZ, DZ, PR, LA) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_mg_cheb_step<XZ, DZ, PR, LA>(L, Lc, b, xin, din, ec, xout, dout, c1, c2, st); })
         if (prolong) { if (last) EMU_MG(false, true, true, true); else EMU_MG(false, true, true, false); }
         else if (xzero) { if (last) EMU_MG(true, false, false, true); else EMU_MG(true, false, false, false); }
@@ -720,7 +737,7 @@ extern "C" {
 // mode 0: x_out = M^-1 b (one V-cycle);  mode 1: KSPSolve_CG preconditioned with the V-cycle (solve_stencil_pcg_mg)
 EMU_API int emu_mg(int dim, const int64_t *n, const int *per, const double *dx, const double *dy, const double *dz, double dt,
                    int mode, int has_const, double rtol, double atol, int max_it, int max_levels, int smooth_its, int coarse_its,
-                   int tile, int tail_cells, const double *b, double *x_out, double *hist, int hist_cap, int *nhist, int *its, int *reason,
+                   int tile, int tail_cells, int fuse, const double *b, double *x_out, double *hist, int hist_cap, int *nhist, int *its, int *reason,
                    int *nlevels)
 {
     Problem P;
@@ -757,6 +774,15 @@ EMU_API int emu_mg(int dim, const int64_t *n, const int *per, const double *dx, 
     {
         VecSet v{z, pp[it & 1], pp[(it & 1) ^ 1], w.data(), x.data(), nullptr};
         spmv<false, false>(P, tile, v, P.g.nzl, W, &st, kc, hist);
+        if (fuse)
+        {
+            M.fuse_rupdate = true; M.fuse_sums_kind = FIN_UPDATE; M.sums_done = false;
+            M.fuse_r = r.data(); M.fuse_w = w.data(); M.fuse_W = &W; M.fuse_kc = kc; M.fuse_hist = hist;
+            z = M.cycle(r.data());
+            M.fuse_rupdate = false; M.fuse_sums_kind = -1;
+            if (!M.sums_done) zsums(FIN_UPDATE);
+            continue;
+        }
         emu::launch(dim3(3), dim3(256), 0, [&] { k_mg_rupdate(nflat, r.data() + P.g.plane, w.data() + P.g.plane, &st); });
         z = M.cycle(r.data());
         zsums(FIN_UPDATE);

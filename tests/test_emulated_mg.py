@@ -15,16 +15,16 @@ from tests.test_emulated_kernels import emu, _grid_args, _cg, _dp, _ip  # noqa: 
 
 
 def _mg(L, widths, per, b, mode="pcg", has_const=True, rtol=0.0, atol=0.0, max_it=20, levels=0, smooth=2, coarse=16, tile=10,
-        tail_cells=0):
+        tail_cells=0, fuse=0):
     dim, n, p, w, dz = _grid_args(widths, per)
     L.emu_mg.argtypes = [C.c_int, C.POINTER(C.c_int64), _ip, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double,
-                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _ip, _ip, _ip, _ip]
+                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _ip, _ip, _ip, _ip]
     b = np.ascontiguousarray(b, dtype=np.float64)
     x = np.empty_like(b)
     hist = np.zeros(max_it + 2)
     nh, its, reason, nl = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
     rc = L.emu_mg(dim, n, p, w[0].ctypes.data_as(_dp), w[1].ctypes.data_as(_dp), dz, 0.01, {"apply": 0, "pcg": 1}[mode],
-                  int(has_const), rtol, atol, max_it, levels, smooth, coarse, tile, int(tail_cells), b.ctypes.data_as(_dp),
+                  int(has_const), rtol, atol, max_it, levels, smooth, coarse, tile, int(tail_cells), int(fuse), b.ctypes.data_as(_dp),
                   x.ctypes.data_as(_dp),
                   hist.ctypes.data_as(_dp), hist.size, C.byref(nh), C.byref(its), C.byref(reason), C.byref(nl))
     assert rc == 0
@@ -226,8 +226,7 @@ def test_emulated_mg_edge_cases(emu):
     np.testing.assert_allclose(x, xs, rtol=0, atol=1e-8 * np.abs(xs).max())
 
 
-@pytest.mark.parametrize("shape,per", [((16, 12, 8), (0, 0, 0)), ((12, 16, 8), (1, 0, 1)), ((24, 20), (0, 0))])
-@pytest.mark.parametrize("smooth", [1, 2, 3])
+@pytest.mark.parametrize("shape,per,smooth", [((16, 12, 8), (0, 0, 0), 2), ((12, 16, 8), (1, 0, 1), 1), ((24, 20), (0, 0), 3)])
 def test_emulated_single_cta_tail_gives_the_same_numbers(emu, shape, per, smooth):
     """Tuning "mg_tail": the coarse levels of the cycle interpreted by ONE CTA (k_mg_tail) from the recorded schedule --
     same bodies, same order, so z = M^-1 r and the PCG history are identical bit for bit to the launch-per-step cycle."""
@@ -243,3 +242,18 @@ def test_emulated_single_cta_tail_gives_the_same_numbers(emu, shape, per, smooth
     x0, h0, i0, r0, _ = _mg(emu, widths, per, b, rtol=1e-9, max_it=40, smooth=smooth)
     x1, h1, i1, r1, _ = _mg(emu, widths, per, b, rtol=1e-9, max_it=40, smooth=smooth, tail_cells=200)
     assert (i0, r0) == (i1, r1) and np.array_equal(h0, h1) and np.array_equal(x0, x1)
+
+
+@pytest.mark.parametrize("shape,per,smooth", [((16, 12, 8), (0, 0, 0), 1), ((12, 16, 8), (1, 0, 1), 2), ((24, 20), (0, 0), 3),
+                                              ((3, 3, 3), (0, 0, 0), 1), ((3, 3, 3), (0, 0, 0), 2)])
+def test_emulated_fused_first_and_last_steps_give_the_same_numbers(emu, shape, per, smooth):
+    """Tuning "mg_fuse": r <- r - a w inside the first fine-level step and the six sums inside the last one (24 + 16 B/row
+    and two launches less per iteration) -- same arithmetic, same thread-to-cell mapping, so the PCG history and the
+    solution are identical bit for bit; a single-level hierarchy falls back to the separate kernels where it has to."""
+    widths = H.make_widths(shape)
+    A = H.oracle_matrix(widths, per)
+    b, _ = H.consistent_rhs(A)
+    x0, h0, i0, r0, _ = _mg(emu, widths, per, b, rtol=1e-9, max_it=40, smooth=smooth, coarse=smooth + 1)
+    for tail in (0, 200):
+        x1, h1, i1, r1, _ = _mg(emu, widths, per, b, rtol=1e-9, max_it=40, smooth=smooth, coarse=smooth + 1, fuse=1, tail_cells=tail)
+        assert (i0, r0) == (i1, r1) and np.array_equal(h0, h1) and np.array_equal(x0, x1)
