@@ -126,7 +126,8 @@ int check_rows(int nfields, const Field *F, const int *periodic, const double *c
                         return mismatch(errbuf, errlen, "row %lld: entry in column %lld is outside the 7-point pattern", (long long)row, (long long)c);
                     }
                     if (std::memcmp(&val[q], &eval[e], sizeof(double)) != 0)
-                        return mismatch(errbuf, errlen, "row %lld, column %lld: %.17g is not the line coefficient %.17g", (long long)row, (long long)c, val[q], eval[e]);
+                        return mismatch(errbuf, errlen, "row %lld, column %lld: %.17g is not the %s %.17g", (long long)row, (long long)c, val[q],
+                                        area ? "closed-form coefficient (face area * dt/h)" : "line coefficient", eval[e]);
                     seen[e] = true;
                 }
                 else
