@@ -1167,6 +1167,10 @@ int b200ls_create(b200ls_solver **out, int device)
     }
     if (const char *e = getenv("B200LS_TILE")) h->tile = atoi(e);
     if (const char *e = getenv("B200LS_KZ_CHUNK")) h->kz_chunk = atoi(e);
+    // experiment switches of the multigrid path (same as b200ls_set_tuning): lets the whole device test-suite run with them
+    if (const char *e = getenv("B200LS_MG_GRAPH")) h->mg_graph = atoi(e);
+    if (const char *e = getenv("B200LS_MG_TAIL")) h->mg_tail = atoi(e);
+    if (const char *e = getenv("B200LS_MG_FUSE")) h->mg_fuse = atoi(e);
     build_commdev(h);
     *out = h;
     return B200LS_OK;
