@@ -23,6 +23,7 @@
 #include "kernels.cuh"
 #include "spmv2.cuh"
 #include "spmv3.cuh"
+#include "update_fly.cuh"
 #include "csr_kernels.cuh"
 #include "sep_kernels.cuh"
 #include "mg_kernels.cuh"
@@ -177,7 +178,7 @@ struct b200ls_solver
     int kz_chunk = 0;        // 0 = auto
     int upd_blocks = 0;      // 0 = auto
     int tile = -1;           // K1 tile variant (-1: cost model picks 10 or 18; 10+: k_spmv2; <10: k_spmv)
-    int upd_variant = 0;     // 0: flat k_update2, 1: first-generation k_update
+    int upd_variant = 0;     // 0: flat k_update2, 1: first-generation k_update, 2: k_update2f (Jacobi diagonal on the fly)
     int upd_reverse = 1;     // k_update2 walks the owned range top-down (L2 reuse of what k_spmv2 wrote last)
     int use_graph = 1;
     int use_pdl = 1;
@@ -593,6 +594,20 @@ void launch_update_t(b200ls_solver *h, int fin_kind, bool push)
     const int blocks = upd_grid_blocks(h);
     if (h->upd_variant == 1)
         k_update<JAC, INIT, 4><<<blocks, 256, 0, h->stream>>>(h->g, v, fin_kind, h->ws, cm, h->d_state, kc, h->d_hist);
+    else if (JAC && h->upd_variant == 2)
+    {
+        // round-2 candidate: 1/diag rebuilt from the 1-D arrays instead of streamed (update_fly.cuh)
+        const bool padded = h->g.px != h->g.nx;
+        const bool psh = cm.r_ghost_dn || cm.r_ghost_up;
+#define B200_UPDF(PAD, PSH)                                                                                        \
+    launch_k(h, h->in_loop && pdl_on(h), k_update2f<INIT, PAD, PSH, 4>, dim3(blocks), dim3(256), 0, h->g, v, fin_kind, \
+             h->ws, cm, h->d_state, kc, h->d_hist)
+        if (padded && psh) B200_UPDF(true, true);
+        else if (padded) B200_UPDF(true, false);
+        else if (psh) B200_UPDF(false, true);
+        else B200_UPDF(false, false);
+#undef B200_UPDF
+    }
     else
     {
         const bool padded = h->g.px != h->g.nx;
@@ -1167,6 +1182,7 @@ int b200ls_create(b200ls_solver **out, int device)
     }
     if (const char *e = getenv("B200LS_TILE")) h->tile = atoi(e);
     if (const char *e = getenv("B200LS_KZ_CHUNK")) h->kz_chunk = atoi(e);
+    if (const char *e = getenv("B200LS_UPD_VARIANT")) h->upd_variant = atoi(e);
     // experiment switches of the multigrid path (same as b200ls_set_tuning): lets the whole device test-suite run with them
     if (const char *e = getenv("B200LS_MG_GRAPH")) h->mg_graph = atoi(e);
     if (const char *e = getenv("B200LS_MG_TAIL")) h->mg_tail = atoi(e);

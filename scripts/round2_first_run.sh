@@ -28,6 +28,9 @@ run tune_256 600 python scripts/tune_k1.py --tiles 10 18 30 31 32 33
 run tune_slab 300 python scripts/tune_k1.py --size 256 256 32 --tiles 10 13 18 30 31 32 33
 run parity_tile30 300 env B200LS_TILE=30 python -m pytest tests/test_gpu_parity.py -m gpu -q -x
 run parity_tile32 300 env B200LS_TILE=32 python -m pytest tests/test_gpu_parity.py -m gpu -q -x
+run parity_jacobi_fly 300 env B200LS_UPD_VARIANT=2 python -m pytest tests/test_gpu_parity.py -m gpu -q -x
+run bench_jacobi 300 python bench.py --pc jacobi --no-cpu-baseline
+run bench_jacobi_fly 300 env B200LS_UPD_VARIANT=2 python bench.py --pc jacobi --no-cpu-baseline
 # 3. time to solution: none / jacobi / mg
 run tts_128 300 python scripts/tts_bench.py --size 128 128 128
 run tts_256 600 python scripts/tts_bench.py --size 256 256 256 --pcs jacobi mg

@@ -9,6 +9,7 @@
 
 #include "spmv2.cuh"
 #include "spmv3.cuh"
+#include "update_fly.cuh"
 #include "csr_kernels.cuh"
 #include "sep_kernels.cuh"
 #include "mg_kernels.cuh"
@@ -151,11 +152,21 @@ void spmv(const Problem &P, int tile, const VecSet &v, int kz, Ws &W, DevState *
     else launch_spmv<8, 4, 3, JAC, APPLY>(P, v, kz, W, st, kc, hist);
 }
 
+int g_upd_fly = 0;  // emu_set_update_variant: 1 = k_update2f (Jacobi diagonal rebuilt on the fly)
+
 template <bool JAC, bool INIT>
 void update(const Problem &P, const UpdVecs &v, int fin_kind, int blocks, Ws &W, DevState *st, const SolveConsts &kc,
             double *hist)
 {
     const GridDev &g = P.g;
+    if (JAC && g_upd_fly)
+    {
+        if (g.px != g.nx)
+            emu::launch(dim3(blocks), dim3(256), 0, [&] { k_update2f<INIT, true, false, 4>(g, v, fin_kind, W.ws, W.cm, st, kc, hist); });
+        else
+            emu::launch(dim3(blocks), dim3(256), 0, [&] { k_update2f<INIT, false, false, 4>(g, v, fin_kind, W.ws, W.cm, st, kc, hist); });
+        return;
+    }
     if (g.px != g.nx)
         emu::launch(dim3(blocks), dim3(256), 0, [&] { k_update2<JAC, INIT, true, false, 4>(g, v, fin_kind, W.ws, W.cm, st, kc, hist); });
     else
@@ -167,6 +178,8 @@ void update(const Problem &P, const UpdVecs &v, int fin_kind, int blocks, Ws &W,
 #define EMU_API __attribute__((visibility("default")))
 
 extern "C" {
+
+EMU_API void emu_set_update_variant(int fly) { g_upd_fly = fly; }
 
 // seed != 0: shuffled fiber order + random preemption at shared-memory accesses; 0: deterministic round-robin
 EMU_API void emu_set_schedule(unsigned long long seed)

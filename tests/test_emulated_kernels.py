@@ -20,7 +20,7 @@ LIB = os.path.join(EMU, "libb200emu.so")
 SRC = [os.path.join(EMU, f) for f in ("emu_solver.cpp", "cuda_emu.h")] + \
       [os.path.join(ROOT, "petibm_b200", "csrc", f) for f in ("kernels.cuh", "spmv2.cuh", "spmv3.cuh", "hw.cuh", "csr_kernels.cuh",
                                                             "sep_kernels.cuh", "mg_kernels.cuh", "mg_schedule.h",
-                                                            "ops_kernels.cuh")]
+                                                            "ops_kernels.cuh", "update_fly.cuh")]
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -497,3 +497,22 @@ def test_emulated_divergence_gradient_projection_are_the_assembled_products(emu,
     A = H.oracle_matrix(widths, per)
     lhs = run(0, run(2, pr, np.empty(UN)), np.empty(pN))
     np.testing.assert_allclose(lhs, A.spmv(pr), rtol=0, atol=1e-12 * np.abs(lhs).max())
+
+
+@pytest.mark.parametrize("shape,per", [((24, 10, 9), (0, 0, 0)), ((67, 9, 6), (1, 1, 0)), ((16, 12, 10), (0, 0, 1)), ((33, 21), (1, 0))])
+def test_emulated_jacobi_diagonal_on_the_fly_is_bit_identical(emu, shape, per):
+    """k_update2f (tuning upd_variant = 2, a round-2 candidate): 1/diag rebuilt from the 1-D arrays inside the update
+    kernel instead of streamed from HBM.  Same accumulation order as k_jacobi_setup, so history and solution are equal to
+    the stored-reciprocal path bit for bit (padded rows, periodic wrap rows, 2-D included)."""
+    widths = H.make_widths(shape)
+    A = H.oracle_matrix(widths, per)
+    b, _ = H.consistent_rhs(A)
+    emu.emu_set_update_variant.argtypes = [C.c_int]
+    try:
+        emu.emu_set_update_variant(0)
+        x0, h0, i0, r0, n0 = _cg(emu, widths, per, b, pc="jacobi", max_it=12)
+        emu.emu_set_update_variant(1)
+        x1, h1, i1, r1, n1 = _cg(emu, widths, per, b, pc="jacobi", max_it=12)
+    finally:
+        emu.emu_set_update_variant(0)
+    assert (i0, r0) == (i1, r1) and np.array_equal(h0, h1) and np.array_equal(x0, x1)
