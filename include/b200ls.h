@@ -65,8 +65,10 @@ extern "C" {
 /* ---- enums (values follow PETSc's option strings) ---- */
 #define B200LS_KSP_CG 0
 #define B200LS_KSP_BCGS 1
+#define B200LS_KSP_PREONLY 2 /* with B200LS_PC_LU: direct solve of a small assembled system (decoupled IBPM forces system) */
 #define B200LS_PC_NONE 0
 #define B200LS_PC_JACOBI 1
+#define B200LS_PC_LU 3 /* dense LU of a matrix with at most 4096 rows; only with B200LS_KSP_PREONLY */
 #define B200LS_PC_MG 2 /* geometric multigrid on the separable pressure operator (extension, single GPU) */
 #define B200LS_NORM_NONE 0
 #define B200LS_NORM_PRECONDITIONED 1
@@ -76,12 +78,14 @@ extern "C" {
 /* KSPConvergedReason values reported by b200ls_get_reason (same numbers as PETSc) */
 #define B200LS_CONVERGED_RTOL 2
 #define B200LS_CONVERGED_ATOL 3
+#define B200LS_CONVERGED_ITS 4
 #define B200LS_DIVERGED_ITS (-3)
 #define B200LS_DIVERGED_DTOL (-4)
 #define B200LS_DIVERGED_BREAKDOWN (-5)
 #define B200LS_DIVERGED_INDEFINITE_PC (-8)
 #define B200LS_DIVERGED_NANORINF (-9)
 #define B200LS_DIVERGED_INDEFINITE_MAT (-10)
+#define B200LS_DIVERGED_PC_FAILED (-11)
 
 /* halo / reduction transports for the multi-GPU path */
 #define B200LS_REDUCE_P2P 0  /* in-kernel all-reduce through peer-mapped mailboxes (NVLink) */

@@ -13,8 +13,8 @@ LIB_PATH = os.path.join(HERE, "libb200ls.so")
 
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NCCL, ERR_DIVERGED, ERR_MISMATCH, ERR_PARSE = -1, -2, -3, -4, -5, -6, -7
-KSP_CG, KSP_BCGS = 0, 1
-PC_NONE, PC_JACOBI, PC_MG = 0, 1, 2
+KSP_CG, KSP_BCGS, KSP_PREONLY = 0, 1, 2
+PC_NONE, PC_JACOBI, PC_MG, PC_LU = 0, 1, 2, 3
 NORM_NONE, NORM_PRECONDITIONED, NORM_UNPRECONDITIONED, NORM_NATURAL = 0, 1, 2, 3
 REDUCE_P2P, REDUCE_NCCL = 0, 1
 HALO_STORE, HALO_MEMCPY = 0, 1

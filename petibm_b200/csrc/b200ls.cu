@@ -28,6 +28,7 @@
 #include "sep_kernels.cuh"
 #include "mg_kernels.cuh"
 #include "ops_kernels.cuh"
+#include "dense_kernels.cuh"
 
 using namespace b200;
 
@@ -138,6 +139,11 @@ struct b200ls_solver
     int mg_tail_degrees[2] = {0, 0};
     double *mg_tail_result = nullptr;
     int mg_graph = 0;        // tuning "mg_graph": replay pairs of preconditioned iterations as one CUDA graph (off until timed)
+
+    // ---- direct solve of a small assembled system (preonly + lu; dense_kernels.cuh)
+    double *d_dense = nullptr;   // n x n factors
+    int *d_dense_info = nullptr;
+    bool dense_ready = false;
 
     // ---- vectors (solver layout)
     double *arena = nullptr;  // [mailboxes | flags | r]; exported over CUDA IPC
@@ -263,6 +269,9 @@ void free_vectors(b200ls_solver *h)
     fr(h->d_val);
     fr(h->d_nullvecs);
     h->sep_hybrid = false;
+    fr(h->d_dense);
+    fr(h->d_dense_info);
+    h->dense_ready = false;
     fr(h->d_sep_coef);
     fr(h->d_sep_diag);
     fr(h->d_rem_rowptr);
@@ -908,6 +917,7 @@ int solve_stencil_cg(b200ls_solver *h, const double *b_dev, double *x_dev)
 #include "csr_solver.inc"
 #include "sep_solver.inc"
 #include "mg_solver.inc"
+#include "dense_solver.inc"
 
 // ------------------------------------------------------------------------------------------
 // C ABI
@@ -1081,7 +1091,8 @@ int b200ls_parse_options(const char *text, const char *prefix, b200ls_options *o
             if (!need()) return B200LS_ERR_PARSE;
             if (val == "cg") opts->ksp_type = B200LS_KSP_CG;
             else if (val == "bcgs") opts->ksp_type = B200LS_KSP_BCGS;
-            else { set_err(errbuf, errlen, "-%sksp_type %s is not implemented by the B200 backend (cg, bcgs)", prefix, val.c_str()); return B200LS_ERR_UNSUPPORTED; }
+            else if (val == "preonly") opts->ksp_type = B200LS_KSP_PREONLY;
+            else { set_err(errbuf, errlen, "-%sksp_type %s is not implemented by the B200 backend (cg, bcgs, preonly)", prefix, val.c_str()); return B200LS_ERR_UNSUPPORTED; }
         }
         else if (key == "pc_type")
         {
@@ -1089,7 +1100,8 @@ int b200ls_parse_options(const char *text, const char *prefix, b200ls_options *o
             if (val == "none") opts->pc_type = B200LS_PC_NONE;
             else if (val == "jacobi") opts->pc_type = B200LS_PC_JACOBI;
             else if (val == "mg") opts->pc_type = B200LS_PC_MG;
-            else { set_err(errbuf, errlen, "-%spc_type %s is not implemented by the B200 backend (none, jacobi, mg)", prefix, val.c_str()); return B200LS_ERR_UNSUPPORTED; }
+            else if (val == "lu" || val == "cholesky") opts->pc_type = B200LS_PC_LU;
+            else { set_err(errbuf, errlen, "-%spc_type %s is not implemented by the B200 backend (none, jacobi, mg, lu)", prefix, val.c_str()); return B200LS_ERR_UNSUPPORTED; }
         }
         // geometric multigrid (extension; PETSc's PCMG option names, only the combination that is implemented)
         else if (key == "pc_mg_levels") { if (!num(d)) return B200LS_ERR_PARSE; opts->mg_levels = (int)d; }
@@ -1109,6 +1121,12 @@ int b200ls_parse_options(const char *text, const char *prefix, b200ls_options *o
         {
             if (!need()) return B200LS_ERR_PARSE;
             if (val != "v") { set_err(errbuf, errlen, "-%spc_mg_cycle_type %s unsupported (v)", prefix, val.c_str()); return B200LS_ERR_UNSUPPORTED; }
+        }
+        else if (key == "pc_factor_mat_solver_type")
+        {
+            // which package factorises (superlu_dist, mumps, petsc) is PETSc's business: here the direct solve is the
+            // dense factorisation of dense_kernels.cuh
+            if (!need()) return B200LS_ERR_PARSE;
         }
         else if (key == "pc_jacobi_type")
         {
@@ -1147,6 +1165,11 @@ int b200ls_parse_options(const char *text, const char *prefix, b200ls_options *o
             set_err(errbuf, errlen, "option %s is not implemented by the B200 backend; no silent fallback", name.c_str());
             return B200LS_ERR_UNSUPPORTED;
         }
+    }
+    if ((opts->ksp_type == B200LS_KSP_PREONLY) != (opts->pc_type == B200LS_PC_LU))
+    {
+        set_err(errbuf, errlen, "-%sksp_type preonly and -%spc_type lu are only implemented together (direct solve)", prefix, prefix);
+        return B200LS_ERR_UNSUPPORTED;
     }
     return B200LS_OK;
 }
@@ -1221,9 +1244,12 @@ const char *b200ls_last_error(const b200ls_solver *h) { return h ? h->err.c_str(
 int b200ls_set_options(b200ls_solver *h, const b200ls_options *o)
 {
     if (!h || !o) return B200LS_ERR_ARG;
-    if (o->ksp_type != B200LS_KSP_CG && o->ksp_type != B200LS_KSP_BCGS) return fail(h, B200LS_ERR_UNSUPPORTED, "ksp_type %d", o->ksp_type);
-    if (o->pc_type != B200LS_PC_NONE && o->pc_type != B200LS_PC_JACOBI && o->pc_type != B200LS_PC_MG)
+    if (o->ksp_type != B200LS_KSP_CG && o->ksp_type != B200LS_KSP_BCGS && o->ksp_type != B200LS_KSP_PREONLY)
+        return fail(h, B200LS_ERR_UNSUPPORTED, "ksp_type %d", o->ksp_type);
+    if (o->pc_type != B200LS_PC_NONE && o->pc_type != B200LS_PC_JACOBI && o->pc_type != B200LS_PC_MG && o->pc_type != B200LS_PC_LU)
         return fail(h, B200LS_ERR_UNSUPPORTED, "pc_type %d", o->pc_type);
+    if ((o->ksp_type == B200LS_KSP_PREONLY) != (o->pc_type == B200LS_PC_LU))
+        return fail(h, B200LS_ERR_UNSUPPORTED, "ksp_type preonly and pc_type lu are only implemented together (direct solve)");
     if (o->pc_type == B200LS_PC_MG && o->ksp_type != B200LS_KSP_CG) return fail(h, B200LS_ERR_UNSUPPORTED, "pc_type mg is used with ksp_type cg");
     if (o->mg_levels < 0 || o->mg_levels > 32) return fail(h, B200LS_ERR_ARG, "pc_mg_levels %d", o->mg_levels);
     if (o->norm_type < B200LS_NORM_PRECONDITIONED || o->norm_type > B200LS_NORM_NATURAL)
@@ -1693,7 +1719,9 @@ int b200ls_solve_device(b200ls_solver *h, const double *b_dev, double *x_dev)
     if (!h || !b_dev || !x_dev) return B200LS_ERR_ARG;
     cudaSetDevice(h->device);
     int rc;
-    if (h->op == OP_STENCIL)
+    if (h->opt.ksp_type == B200LS_KSP_PREONLY)
+        rc = dense_solve(h, b_dev, x_dev);
+    else if (h->op == OP_STENCIL)
     {
         if (h->opt.ksp_type != B200LS_KSP_CG)
             return fail(h, B200LS_ERR_UNSUPPORTED, "the separable stencil operator is solved with cg; bcgs needs the CSR operator");

@@ -153,7 +153,8 @@ class LinSolverB200(LinSolverBase):
 
     def setOptions(self, **kw):
         o = self.options()
-        names = {"cg": _lib.KSP_CG, "bcgs": _lib.KSP_BCGS, "none": _lib.PC_NONE, "jacobi": _lib.PC_JACOBI, "mg": _lib.PC_MG,
+        names = {"cg": _lib.KSP_CG, "bcgs": _lib.KSP_BCGS, "preonly": _lib.KSP_PREONLY, "none": _lib.PC_NONE,
+                 "jacobi": _lib.PC_JACOBI, "mg": _lib.PC_MG, "lu": _lib.PC_LU,
                  "preconditioned": _lib.NORM_PRECONDITIONED, "unpreconditioned": _lib.NORM_UNPRECONDITIONED,
                  "natural": _lib.NORM_NATURAL}
         for k, v in kw.items():

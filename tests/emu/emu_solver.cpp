@@ -14,6 +14,7 @@
 #include "sep_kernels.cuh"
 #include "mg_kernels.cuh"
 #include "ops_kernels.cuh"
+#include "dense_kernels.cuh"
 
 using namespace b200;
 
@@ -931,6 +932,20 @@ extern "C" EMU_API int emu_stag_ops(int mode, int dim, const int64_t *n, const i
         emu::launch(dim3(3), dim3(256), 0, [&] { k_gradient<2>(s, in, io); });
         emu::launch(dim3(3), dim3(256), 0, [&] { k_axpy_one(np, io2, in); });
     }
+    return 0;
+}
+
+// ---- direct solve of a small assembled system (dense_kernels.cuh): factorise, then nrhs solves with the same factors
+extern "C" EMU_API int emu_dense_solve(int64_t n, const int64_t *rowptr, const int32_t *col, const double *val, int nrhs,
+                                       const double *b, double *x, int threads)
+{
+    std::vector<double> a((size_t)n * (size_t)n, 0.0);
+    int info = -1;
+    emu::launch(dim3(2), dim3(256), 0, [&] { k_dense_fill(n, rowptr, col, val, a.data()); });
+    emu::launch(dim3(1), dim3(threads), 0, [&] { k_dense_lu((int)n, a.data(), &info); });
+    if (info != 0) return info;
+    for (int q = 0; q < nrhs; ++q)
+        emu::launch(dim3(1), dim3(threads), 0, [&] { k_dense_solve((int)n, a.data(), b + (size_t)q * n, x + (size_t)q * n); });
     return 0;
 }
 

@@ -30,7 +30,7 @@ class _Opts:
         self.mg_levels, self.mg_smooth_its, self.mg_coarse_its = 0, 2, 16
 
 
-_NAMES = {"cg": 0, "bcgs": 1, "none": 0, "jacobi": 1, "mg": 2, "preconditioned": 1, "unpreconditioned": 2, "natural": 3}
+_NAMES = {"cg": 0, "bcgs": 1, "preonly": 2, "none": 0, "jacobi": 1, "mg": 2, "lu": 3, "preconditioned": 1, "unpreconditioned": 2, "natural": 3}
 
 
 def make_module(emu):
@@ -146,9 +146,20 @@ def make_module(emu):
         # ---- KSPSolve
         def solve(self, x, b):
             o, g = self._o, self._grid
-            pc = {0: "none", 1: "jacobi", 2: "mg"}[o.pc_type]
+            pc = {0: "none", 1: "jacobi", 2: "mg", 3: "lu"}[o.pc_type]
             has_const, nv = self._null
             kw = dict(rtol=o.rtol, atol=o.atol, max_it=o.max_it)
+            if (o.ksp_type == 2) != (pc == "lu"):
+                raise B200Error(-3, "ksp_type preonly and pc_type lu are only implemented together")
+            if o.ksp_type == 2:
+                if self.operator != "csr":
+                    raise B200Error(-3, "the direct solve works on a small assembled matrix kept as CSR")
+                rc, X = K._dense_solve(emu, self._M, b)
+                x[...] = X[0]
+                self._res = (np.zeros(0), 1 if rc == 0 else 0, 4 if rc == 0 else -11)
+                if rc != 0:
+                    raise B200Error(-5, "diverged: KSPConvergedReason -11")
+                return x
             if self.operator == "stencil":
                 per = [int(p) for p in g.periodic][: g.dim]
                 if o.ksp_type != 0:
@@ -192,7 +203,7 @@ def make_module(emu):
             return self._res[2]
 
         def getResidual(self):
-            return float(self._res[0][-1])
+            return float(self._res[0][-1]) if self._res[0].size else 0.0
 
         # ---- operators around the solve
         def velocitySize(self):

@@ -20,7 +20,7 @@ LIB = os.path.join(EMU, "libb200emu.so")
 SRC = [os.path.join(EMU, f) for f in ("emu_solver.cpp", "cuda_emu.h")] + \
       [os.path.join(ROOT, "petibm_b200", "csrc", f) for f in ("kernels.cuh", "spmv2.cuh", "spmv3.cuh", "hw.cuh", "csr_kernels.cuh",
                                                             "sep_kernels.cuh", "mg_kernels.cuh", "mg_schedule.h",
-                                                            "ops_kernels.cuh", "update_fly.cuh")]
+                                                            "ops_kernels.cuh", "update_fly.cuh", "dense_kernels.cuh")]
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -516,3 +516,47 @@ def test_emulated_jacobi_diagonal_on_the_fly_is_bit_identical(emu, shape, per):
     finally:
         emu.emu_set_update_variant(0)
     assert (i0, r0) == (i1, r1) and np.array_equal(h0, h1) and np.array_equal(x0, x1)
+
+
+def _forces_system(n_side=8, n_band=14, nb=20, dt=0.01):
+    """E BN H of the decoupled IBPM (decoupledibpm.cpp:149-216) for a circle of nb Lagrangian points on a stretched 2-D grid:
+    the force block of tests/helpers.ibpm_system with the sign PetIBM solves (symmetric positive definite up to rounding)."""
+    sub = [{"end": 0.6, "cells": n_side, "stretchRatio": 1.0 / 1.2}, {"end": 1.4, "cells": n_band, "stretchRatio": 1.0},
+           {"end": 2.0, "cells": n_side, "stretchRatio": 1.2}]
+    w = orc.axis_from_subdomains(0.0, sub)
+    M, pN, _ = H.ibpm_system([w, w.copy()], dt=dt, nb=nb)
+    F = (-M[pN:, pN:]).tocsr()
+    F.sort_indices()
+    return F
+
+
+def _dense_solve(L, F, B, threads=128):
+    L.emu_dense_solve.argtypes = [C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32), _dp, C.c_int, _dp, _dp, C.c_int]
+    rp = np.ascontiguousarray(F.indptr, dtype=np.int64); col = np.ascontiguousarray(F.indices, dtype=np.int32)
+    val = np.ascontiguousarray(F.data, dtype=np.float64)
+    B = np.ascontiguousarray(np.atleast_2d(B), dtype=np.float64)
+    X = np.empty_like(B)
+    rc = L.emu_dense_solve(F.shape[0], rp.ctypes.data_as(C.POINTER(C.c_int64)), col.ctypes.data_as(C.POINTER(C.c_int32)),
+                           val.ctypes.data_as(_dp), B.shape[0], B.ctypes.data_as(_dp), X.ctypes.data_as(_dp), threads)
+    return rc, X
+
+
+def test_emulated_direct_solve_of_the_forces_system(emu):
+    """-forces_ksp_type preonly -forces_pc_type lu (every shipped decoupled-IBPM case): dense LU by one thread block,
+    checked against numpy's LAPACK solve; a singular matrix is reported, not solved."""
+    F = _forces_system()
+    n = F.shape[0]
+    assert abs(F - F.T).max() < 1e-12 * abs(F).max() and np.linalg.eigvalsh(F.toarray()).min() > 0
+    rng = np.random.default_rng(3)
+    B = rng.standard_normal((3, n))
+    for threads in (128, 96):
+        rc, X = _dense_solve(emu, F, B, threads)
+        assert rc == 0
+        ref = np.linalg.solve(F.toarray(), B.T).T
+        np.testing.assert_allclose(X, ref, rtol=0, atol=1e-11 * np.abs(ref).max())
+        assert np.abs(F @ X.T - B.T).max() <= 1e-12 * np.abs(B).max() * np.linalg.cond(F.toarray())
+    import scipy.sparse as sp
+
+    S = sp.csr_matrix(np.array([[1.0, 2.0, 0.0], [2.0, 4.0, 0.0], [0.0, 0.0, 1.0]]))
+    rc, _ = _dense_solve(emu, S, np.ones(3), 32)
+    assert rc == 2                                  # zero pivot in column 1 (1-based: 2): KSP_DIVERGED_PC_FAILED on the device path

@@ -8,6 +8,7 @@ from tests import emu_backend
 from tests import test_zzz_gpu_2_staggered as T2
 from tests import test_zzz_gpu_3_ops as T3
 from tests import test_zzz_gpu_4_multigrid as T4
+from tests import test_zzz_gpu_5_direct as T5
 from tests.test_emulated_kernels import emu  # noqa: F401  (fixture)
 
 
@@ -52,3 +53,7 @@ def test_multigrid_needs_the_stencil_body(pbe):
 @pytest.mark.parametrize("dim", [2, 3])
 def test_block_multigrid_body(pbe, dim):
     T4.test_block_multigrid_on_a_stretched_ibpm_system(pbe, dim)
+
+
+def test_direct_solve_body(pbe, tmp_path):
+    T5.test_forces_system_direct_solve(pbe, tmp_path)
