@@ -14,12 +14,12 @@ run() { # name timeout command...
   tail -n 6 "gpurun_out/r02_$name.log" | tee -a gpurun_out/r02_summary.log
 }
 # 1. the validated suite first (must stay green), then the new device tests one file at a time
-run pytest_validated 900 python -m pytest tests -m gpu -q -x --deselect tests/test_zzz_gpu_1_boxes.py --deselect tests/test_zzz_gpu_2_staggered.py --deselect tests/test_zzz_gpu_4_multigrid.py --deselect tests/test_zzz_gpu_3_ops.py --deselect tests/test_zzz_gpu_5_direct.py
+run pytest_validated 900 python -m pytest tests -m gpu -q -x --deselect tests/test_zzz_gpu_1_boxes.py --deselect tests/test_zzz_gpu_2_staggered.py --deselect tests/test_zzz_gpu_4_multigrid.py --deselect tests/test_zzz_gpu_3_ops.py --deselect tests/test_zzz_gpu_3_direct.py
 run pytest_boxes 300 python -m pytest tests/test_zzz_gpu_1_boxes.py -m gpu -q
 run pytest_staggered 300 python -m pytest tests/test_zzz_gpu_2_staggered.py -m gpu -q
 run pytest_multigrid 600 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m gpu -q
 run pytest_ops 300 python -m pytest tests/test_zzz_gpu_3_ops.py -m gpu -q
-run pytest_direct 300 python -m pytest tests/test_zzz_gpu_5_direct.py -m gpu -q
+run pytest_direct 300 python -m pytest tests/test_zzz_gpu_3_direct.py -m gpu -q
 # the optional multigrid paths through the same tests (environment switches read by b200ls_create)
 run pytest_multigrid_tail 600 env B200LS_MG_TAIL=1 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m gpu -q
 run pytest_multigrid_fuse 600 env B200LS_MG_FUSE=1 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m gpu -q

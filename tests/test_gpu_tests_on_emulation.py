@@ -8,7 +8,7 @@ from tests import emu_backend
 from tests import test_zzz_gpu_2_staggered as T2
 from tests import test_zzz_gpu_3_ops as T3
 from tests import test_zzz_gpu_4_multigrid as T4
-from tests import test_zzz_gpu_5_direct as T5
+from tests import test_zzz_gpu_3_direct as T5
 from tests.test_emulated_kernels import emu  # noqa: F401  (fixture)
 
 
