@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(256) k_dense_fill(int64_t n, const int64_t *ro
         for (int64_t q = rowptr[i]; q < rowptr[i + 1]; ++q) a[i * n + col[q]] = val[q];
 }
 
-// in-place LU (unit lower L below the diagonal, U on and above), one thread block; *info = 0 or 1 + index of a zero pivot
+// in-place LU (unit lower L below the diagonal, U on and above), one thread block of a multiple of 32 threads;
+// *info = 0 or 1 + index of a zero pivot
 __global__ void __launch_bounds__(1024) k_dense_lu(int n, double *a, int *info)
 {
     __shared__ double s_pivot;
@@ -40,11 +41,12 @@ __global__ void __launch_bounds__(1024) k_dense_lu(int n, double *a, int *info)
         }
         for (int i = k + 1 + tid; i < n; i += nt) a[(size_t)i * n + k] = a[(size_t)i * n + k] / pivot;
         __syncthreads();
-        const int m = n - k - 1;
-        for (long long e = tid; e < (long long)m * m; e += nt)
+        // trailing update: a warp walks along a row (coalesced in j), the warps share out the rows
+        const int tx = tid & 31, ty = tid >> 5, nty = nt >> 5;
+        for (int i = k + 1 + ty; i < n; i += nty)
         {
-            const int i = k + 1 + (int)(e / m), j = k + 1 + (int)(e % m);
-            a[(size_t)i * n + j] = a[(size_t)i * n + j] - a[(size_t)i * n + k] * a[(size_t)k * n + j];
+            const double lik = a[(size_t)i * n + k];
+            for (int j = k + 1 + tx; j < n; j += 32) a[(size_t)i * n + j] = a[(size_t)i * n + j] - lik * a[(size_t)k * n + j];
         }
         __syncthreads();
     }
