@@ -16,14 +16,14 @@ run() { # name timeout command...
 # 1. the validated suite first (must stay green), then the new device tests one file at a time
 run pytest_validated 900 python -m pytest tests -m gpu -q -x --deselect tests/test_zzz_gpu_1_boxes.py --deselect tests/test_zzz_gpu_2_staggered.py --deselect tests/test_zzz_gpu_4_multigrid.py --deselect tests/test_zzz_gpu_3_ops.py --deselect tests/test_zzz_gpu_3_direct.py
 run pytest_boxes 300 python -m pytest tests/test_zzz_gpu_1_boxes.py -m gpu -q
-run pytest_staggered 300 python -m pytest tests/test_zzz_gpu_2_staggered.py -m gpu -q
-run pytest_multigrid 600 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m gpu -q
-run pytest_ops 300 python -m pytest tests/test_zzz_gpu_3_ops.py -m gpu -q
-run pytest_direct 300 python -m pytest tests/test_zzz_gpu_3_direct.py -m gpu -q
+run pytest_staggered 300 python -m pytest tests/test_zzz_gpu_2_staggered.py -m gpu -q --runxfail
+run pytest_multigrid 600 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m gpu -q --runxfail
+run pytest_ops 300 python -m pytest tests/test_zzz_gpu_3_ops.py -m gpu -q --runxfail
+run pytest_direct 300 python -m pytest tests/test_zzz_gpu_3_direct.py -m gpu -q --runxfail
 # the optional multigrid paths through the same tests (environment switches read by b200ls_create)
-run pytest_multigrid_tail 600 env B200LS_MG_TAIL=1 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m gpu -q
-run pytest_multigrid_fuse 600 env B200LS_MG_FUSE=1 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m gpu -q
-run pytest_multigrid_graph 600 env B200LS_MG_GRAPH=1 B200LS_MG_TAIL=1 B200LS_MG_FUSE=1 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m gpu -q
+run pytest_multigrid_tail 600 env B200LS_MG_TAIL=1 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m gpu -q --runxfail
+run pytest_multigrid_fuse 600 env B200LS_MG_FUSE=1 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m gpu -q --runxfail
+run pytest_multigrid_graph 600 env B200LS_MG_GRAPH=1 B200LS_MG_TAIL=1 B200LS_MG_FUSE=1 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m gpu -q --runxfail
 # 2. round-2 kernel candidates against the default: 256^3 and the 8-GPU slab
 run tune_256 600 python scripts/tune_k1.py --tiles 10 18 30 31 32 33
 run tune_slab 300 python scripts/tune_k1.py --size 256 256 32 --tiles 10 13 18 30 31 32 33

@@ -8,7 +8,9 @@ import scipy.sparse as sp
 
 from tests.test_emulated_kernels import _forces_system
 
-pytestmark = pytest.mark.gpu
+from tests import helpers as H  # noqa: E402
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600), H.NOT_YET_RUN_ON_A_GPU]
 
 
 @pytest.fixture(scope="module")
