@@ -148,26 +148,18 @@ def main():
                 allok &= run_case(comm, shape, per, pc, reduce, halo)
     if "--c4" not in sys.argv and not args:
         # process grids PETSc's DMDA may pick instead of 1 x 1 x P.  These cases were written after round 1's GPU budget was
-        # spent and have not run on GPUs yet: until they have, they are reported but only count with B200_MGPU_BOX_STRICT=1
-        strict = os.environ.get("B200_MGPU_BOX_STRICT", "0") == "1"
-        boxok = True
-        try:
+        # spent and have not run on GPUs yet: they run (and count) with B200_MGPU_BOX=1 -- a one-sided failure inside the
+        # collective set-up would otherwise hang the validated checks above with it
+        if os.environ.get("B200_MGPU_BOX", "0") == "1":
             grids3 = {2: [(2, 1, 1), (1, 2, 1)], 4: [(2, 2, 1), (2, 1, 2)], 8: [(2, 2, 2)]}.get(comm.nranks, [])
             for procs in grids3:
-                boxok &= run_box_case(comm, (22, 18, 19), (0, 0, 0), procs)
-                boxok &= run_box_case(comm, (16, 14, 12), (1, 0, 1), procs)
+                allok &= run_box_case(comm, (22, 18, 19), (0, 0, 0), procs)
+                allok &= run_box_case(comm, (16, 14, 12), (1, 0, 1), procs)
             grids2 = {2: [(2, 1)], 4: [(2, 2)], 8: [(4, 2)]}.get(comm.nranks, [])
             for procs in grids2:
-                boxok &= run_box_case(comm, (30, 23), (0, 0), procs)
-        except Exception as exc:  # noqa: BLE001
-            if strict:
-                raise
-            boxok = False
-            print(f"[rank {comm.rank}] DMDA box cases raised: {exc!r}", flush=True)
-        if comm.rank == 0:
-            print("MGPU_BOX_CASES", "PASS" if boxok else "FAIL", "(strict)" if strict else "(reported only)", flush=True)
-        if strict:
-            allok &= boxok
+                allok &= run_box_case(comm, (30, 23), (0, 0), procs)
+        elif comm.rank == 0:
+            print("[SKIP] DMDA box cases (set B200_MGPU_BOX=1)", flush=True)
     comm.barrier()
     if comm.rank == 0:
         print("MGPU_CHECK", "PASS" if allok else "FAIL", flush=True)
