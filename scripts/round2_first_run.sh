@@ -46,3 +46,5 @@ run tts_256_stretched 600 python scripts/tts_bench.py --size 256 256 256 --pcs m
 # 4. the headline bench and the launch list of the same command
 run bench 600 python bench.py
 run launches 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_bench_256.csv python bench.py --steps 1 --warmup 1 --iters 40 --no-cpu-baseline
+# 5. on a box with several GPUs (gpurun --gpus 2): the multi-GPU paths that have not run on GPUs yet
+#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'B200_MGPU_BOX=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py p2p+store > gpurun_out/r02_mgpu_new.log 2>&1; tail -30 gpurun_out/r02_mgpu_new.log'
