@@ -56,12 +56,12 @@ __device__ __forceinline__ double sep_row(const SepDev &A, long long i, Fetch fe
         if (A.nf > 1 && i >= A.f[1].off) fi = 1;
         if (A.nf > 2 && i >= A.f[2].off) fi = 2;
         const SepField &f = A.f[fi];
-        const long long l = i - f.off;
+        const unsigned int l = (unsigned int)(i - f.off);  // the system has fewer than 2^31 rows (checked on the host)
         const int n0 = f.n0, n1 = f.n1, n2 = f.n2;
-        const long long row1 = l / n0;
-        const int i0 = (int)(l - row1 * n0);
-        const int i2 = (int)(row1 / n1);
-        const int i1 = (int)(row1 - (long long)i2 * n1);
+        const unsigned int row1 = l / (unsigned int)n0;
+        const int i0 = (int)(l - row1 * (unsigned int)n0);
+        const int i2 = (int)(row1 / (unsigned int)n1);
+        const int i1 = (int)(row1 - (unsigned int)i2 * (unsigned int)n1);
         const long long s1 = n0, s2 = (long long)n0 * n1;
         double cxm = f.cm[0][i0], cxp = f.cp[0][i0];
         double cym = f.cm[1][i1], cyp = f.cp[1][i1];
