@@ -41,7 +41,7 @@ def test_ops_body(pbe, shape, per):
     T3.test_operators_are_the_assembled_products(pbe, shape, per)
 
 
-@pytest.mark.parametrize("shape,per", [((32, 24, 16), (0, 0, 0)), ((33, 40), (1, 1)), ((31, 17, 13), (0, 0, 0))])
+@pytest.mark.parametrize("shape,per", [((33, 40), (1, 1)), ((31, 17, 13), (0, 0, 0))])
 def test_multigrid_pcg_body(pbe, shape, per):
     T4.test_pcg_with_multigrid_matches_the_restatement(pbe, shape, per)
 
@@ -50,7 +50,7 @@ def test_multigrid_needs_the_stencil_body(pbe):
     T4.test_multigrid_needs_the_separable_operator(pbe)
 
 
-@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("dim", [2])
 def test_block_multigrid_body(pbe, dim):
     T4.test_block_multigrid_on_a_stretched_ibpm_system(pbe, dim)
 
