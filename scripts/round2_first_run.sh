@@ -15,6 +15,7 @@ run() { # name timeout command...
 }
 # 1. the validated suite first (must stay green), then the new device tests one file at a time
 run pytest_validated 900 python -m pytest tests -m gpu -q -x --deselect tests/test_zzz_gpu_1_boxes.py --deselect tests/test_zzz_gpu_2_staggered.py --deselect tests/test_zzz_gpu_4_multigrid.py --deselect tests/test_zzz_gpu_3_ops.py --deselect tests/test_zzz_gpu_3_direct.py
+run pytest_shim_new 300 python -m pytest tests/test_gpu_shim.py -m gpu -q --runxfail
 run pytest_boxes 300 python -m pytest tests/test_zzz_gpu_1_boxes.py -m gpu -q
 run pytest_staggered 300 python -m pytest tests/test_zzz_gpu_2_staggered.py -m gpu -q --runxfail
 run pytest_multigrid 600 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m gpu -q --runxfail

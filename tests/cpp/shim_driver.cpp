@@ -33,6 +33,7 @@ int main(int argc, char **argv)
 {
     if (argc < 3) return 2;
     const std::string dir = argv[1], cfg = argv[2];
+    const std::string solverName = argc > 3 ? argv[3] : "poisson";   // "velocity" / "forces": other systems of the applications
     // meta: dim, nx, ny, nz, perx, pery, perz, has_const, with_grid, nsolves
     const auto meta = rd<int>(dir + "/meta.bin");
     const auto dtv = rd<double>(dir + "/dt.bin");
@@ -42,13 +43,19 @@ int main(int argc, char **argv)
     A.val = rd<double>(dir + "/val.bin");
     A.n = (int)A.rowptr.size() - 1;
     _p_MatNullSpace nsp;
-    nsp.has_const = meta[7] ? PETSC_TRUE : PETSC_FALSE;
-    A.nsp = &nsp;
+    nsp.has_const = meta[7] == 1 ? PETSC_TRUE : PETSC_FALSE;
+    _p_Vec nullvec;
+    if (meta[7] == 2)   // one explicit null-space vector (ibpm.cpp:251-267)
+    {
+        nullvec.a = rd<double>(dir + "/nullvec.bin");
+        nsp.vecs.push_back(&nullvec);
+    }
+    if (meta[7] != 0) A.nsp = &nsp;
     Mat Am = &A;
 
     std::shared_ptr<petibm::linsolver::LinSolverBase> solver;   // type::LinSolver
     {
-        auto s = std::make_shared<petibm::linsolver::LinSolverB200>("poisson", cfg);
+        auto s = std::make_shared<petibm::linsolver::LinSolverB200>(solverName, cfg);
         if (meta[8])
         {
             const PetscInt n[3] = {meta[1], meta[2], meta[3]};
@@ -74,8 +81,9 @@ int main(int argc, char **argv)
     solver->getIters(its);
     solver->getResidual(res);
     wr(dir + "/x.bin", x.a);
-    wr(dir + "/out.bin", std::vector<double>{(double)its, res, (double)ierr,
-                                             (double)(static_cast<petibm::linsolver::LinSolverB200 *>(solver.get())->getOperatorKind() == "stencil")});
+    const std::string kind = static_cast<petibm::linsolver::LinSolverB200 *>(solver.get())->getOperatorKind();
+    const double kindCode = kind == "stencil" ? 1.0 : kind == "hybrid" ? 2.0 : kind == "staggered" ? 3.0 : 0.0;
+    wr(dir + "/out.bin", std::vector<double>{(double)its, res, (double)ierr, kindCode});
     std::printf("type=%s its=%d res=%.6e ierr=%d\n", type.c_str(), its, res, ierr);
     solver->destroy();
     return 0;

@@ -90,3 +90,77 @@ def test_shim_reports_divergence_like_linsolverksp(tmp_path):
     open(cfg, "w").write("-poisson_pc_type gamg\n")
     res = subprocess.run([exe, d, cfg], capture_output=True, text=True, timeout=300)
     assert "not implemented by the B200 backend" in res.stderr
+
+
+def _write_matrix_case(d, widths, per, M, b, null_mode, nullvec=None, with_grid=True):
+    """Any assembled matrix (scipy CSR) with the grid description of the mesh: null_mode 0 none, 1 constant, 2 one vector."""
+    M = M.tocsr(); M.sort_indices()
+    dim = len(widths)
+    n = [len(w) for w in widths] + [1] * (3 - dim)
+    np.array([dim, *n, *(list(per) + [0] * (3 - dim)), int(null_mode), int(with_grid), 1], dtype=np.int32).tofile(os.path.join(d, "meta.bin"))
+    np.array([0.01]).tofile(os.path.join(d, "dt.bin"))
+    M.indptr.astype(np.int32).tofile(os.path.join(d, "rowptr.bin"))
+    M.indices.astype(np.int32).tofile(os.path.join(d, "col.bin"))
+    M.data.astype(np.float64).tofile(os.path.join(d, "val.bin"))
+    for name, w in zip(("dx", "dy", "dz"), widths):
+        np.asarray(w, dtype=np.float64).tofile(os.path.join(d, name + ".bin"))
+    np.asarray(b, dtype=np.float64).tofile(os.path.join(d, "b.bin"))
+    if nullvec is not None:
+        np.asarray(nullvec, dtype=np.float64).tofile(os.path.join(d, "nullvec.bin"))
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+@H.NOT_YET_RUN_ON_A_GPU
+def test_shim_picks_the_structured_operators_for_the_other_systems(tmp_path):
+    """The three other matrices the applications hand to setMatrix, through the C++ shim: the velocity system (bcgs + jacobi,
+    shipped velocity_solver.info) -> line-coefficient operator; IBPM's modified Poisson system on a stretched grid with
+    pc_type mg -> hybrid operator with the block multigrid; the decoupled-IBPM forces system (shipped forces_solver.info)
+    -> direct solve."""
+    d = str(tmp_path)
+    exe = _build(d)
+    rng = np.random.default_rng(8)
+    # velocity system
+    shape, per = (14, 12, 10), (0, 0, 0)
+    widths = H.make_widths(shape)
+    A, _ = H.velocity_system(widths, per, dt=0.01, nu=0.01)
+    b = rng.standard_normal(A.shape[0])
+    _write_matrix_case(d, widths, per, A, b, 0)
+    cfg = os.path.join(d, "velocity_solver.info")
+    open(cfg, "w").write("-velocity_ksp_type bcgs\n-velocity_ksp_atol 1.0E-08\n-velocity_ksp_rtol 0.0\n-velocity_ksp_max_it 1000\n"
+                         "-velocity_pc_type jacobi\n-velocity_pc_jacobi_type diagonal\n")
+    res = subprocess.run([exe, d, cfg, "velocity"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    its, resn, ierr, kind = np.fromfile(os.path.join(d, "out.bin"))
+    Ao = orc.Csr.from_arrays(A.shape[0], A.shape[1], A.indptr, A.indices, A.data)
+    ref = orc.ksp_solve(Ao, b, ksp_type="bcgs", pc_type="jacobi", rtol=0.0, atol=1e-8, max_it=1000)
+    assert ierr == 0 and kind == 3 and abs(int(its) - ref.its) <= 2
+    np.testing.assert_allclose(np.fromfile(os.path.join(d, "x.bin")), ref.x, rtol=0, atol=1e-6 * np.abs(ref.x).max())
+    # IBPM modified Poisson system, stretched grid, multigrid block preconditioner
+    sub = [{"end": 0.6, "cells": 10, "stretchRatio": 1.0 / 1.2}, {"end": 1.4, "cells": 20, "stretchRatio": 1.0},
+           {"end": 2.0, "cells": 10, "stretchRatio": 1.2}]
+    w = orc.axis_from_subdomains(0.0, sub)
+    widths = [w, w.copy()]
+    M, pN, nv = H.ibpm_system(widths, dt=0.01, nb=14)
+    xs = rng.standard_normal(M.shape[0]); xs -= (xs @ nv) * nv
+    b = M @ xs
+    _write_matrix_case(d, widths, (0, 0), M, b, 2, nullvec=nv)
+    cfg = os.path.join(d, "poisson_solver.info")
+    open(cfg, "w").write("-poisson_ksp_type cg\n-poisson_pc_type mg\n-poisson_ksp_rtol 1e-9\n-poisson_ksp_atol 1e-50\n-poisson_ksp_max_it 500\n")
+    res = subprocess.run([exe, d, cfg, "poisson"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    its, resn, ierr, kind = np.fromfile(os.path.join(d, "out.bin"))
+    assert ierr == 0 and kind == 2 and int(its) <= 80
+    np.testing.assert_allclose(np.fromfile(os.path.join(d, "x.bin")), xs, rtol=0, atol=1e-6 * np.abs(xs).max())
+    # forces system, direct solve
+    F = (-M[pN:, pN:]).tocsr()
+    b = rng.standard_normal(F.shape[0])
+    _write_matrix_case(d, widths, (0, 0), F, b, 0, with_grid=False)
+    cfg = os.path.join(d, "forces_solver.info")
+    open(cfg, "w").write("-forces_ksp_type preonly\n-forces_pc_type lu\n-forces_pc_factor_mat_solver_type superlu_dist\n")
+    res = subprocess.run([exe, d, cfg, "forces"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    its, resn, ierr, kind = np.fromfile(os.path.join(d, "out.bin"))
+    assert ierr == 0 and kind == 0 and int(its) == 1 and resn == 0.0
+    ref = np.linalg.solve(F.toarray(), b)
+    np.testing.assert_allclose(np.fromfile(os.path.join(d, "x.bin")), ref, rtol=0, atol=1e-11 * np.abs(ref).max())
