@@ -159,3 +159,23 @@ def test_axis_from_subdomains_matches_oracle_and_golden(golden_dir):
         sub = [{"end": float(e), "cells": int(rng.integers(1, 40)), "stretchRatio": float(rng.choice([1.0, 0.9, 1.1, 1.03]))}
                for e in ends]
         assert np.array_equal(axis_from_subdomains(-0.25, sub), orc.axis_from_subdomains(-0.25, sub))
+
+
+def test_the_header_is_plain_c_and_the_example_links(tmp_path):
+    """include/b200ls.h compiles as C99 and examples/poisson_cabi.c (the binding calls from plain C) links against the
+    library; without a CUDA device the program says so and exits with 2 -- there is no CPU path to fall back to."""
+    import subprocess
+
+    exe = str(tmp_path / "poisson_cabi")
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                          os.path.join(ROOT, "examples", "poisson_cabi.c"), "-L", os.path.join(ROOT, "petibm_b200"), "-lb200ls",
+                          "-Wl,-rpath," + os.path.join(ROOT, "petibm_b200"), "-lm", "-o", exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    L = _lib.lib()
+    n = C.c_int(-1)
+    have_gpu = L.b200ls_device_count(C.byref(n)) == 0 and n.value > 0
+    run = subprocess.run([exe, "16"], capture_output=True, text=True, timeout=300)
+    if have_gpu:
+        assert run.returncode == 0 and "CG iterations" in run.stdout, run.stdout + run.stderr
+    else:
+        assert run.returncode == 2 and "no CPU path" in run.stderr
