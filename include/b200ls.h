@@ -22,6 +22,13 @@
  *   b200ls_set_staggered                  the same call for the velocity system A = I/dt - c nu L
  *                                         (navierstokes.cpp:342-344, createlaplacian.cpp:134-159) and IBPM's
  *                                         modified Poisson system (ibpm.cpp:100-203)
+ *   b200ls_set_poisson_hybrid             the same call for IBPM's [D;E] BN [G,-H] on a stretched grid
+ *                                         applications/ibpm/ibpm.cpp:164-194 (pressure block = DBNG of the mesh)
+ *   options ksp_type preonly + pc_type lu KSPPREONLY + PCLU of the decoupled-IBPM forces system
+ *                                         examples/decoupledibpm/(case)/config/forces_solver.info,
+ *                                         applications/decoupledibpm/decoupledibpm.cpp:271-285
+ *   option pc_type mg                     stands in for -poisson_pc_type gamg / hypre / AmgX AMG of the shipped
+ *                                         examples/(app)/(case)/config/poisson_solver.info (extension: PETSc PCMG option names)
  *   b200ls_set_nullspace                  MatSetNullSpace on DBNG            navierstokes.cpp:404-413
  *   b200ls_solve                          LinSolverKSP::solve -> KSPSolve    linsolverksp.cpp:85-105
  *   b200ls_get_iters / _get_residual      LinSolverKSP::getIters/getResidual linsolverksp.cpp:110-132
