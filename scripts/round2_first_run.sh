@@ -18,9 +18,9 @@ run pytest_validated 900 python -m pytest tests -m gpu -q -x --deselect tests/te
 run pytest_shim_new 300 python -m pytest tests/test_gpu_shim.py -m gpu -q --runxfail
 run pytest_boxes 300 python -m pytest tests/test_zzz_gpu_1_boxes.py -m gpu -q
 run pytest_staggered 300 python -m pytest tests/test_zzz_gpu_2_staggered.py -m gpu -q --runxfail
-run pytest_multigrid 600 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m gpu -q --runxfail
 run pytest_ops 300 python -m pytest tests/test_zzz_gpu_3_ops.py -m gpu -q --runxfail
 run pytest_direct 300 python -m pytest tests/test_zzz_gpu_3_direct.py -m gpu -q --runxfail
+run pytest_multigrid 600 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m gpu -q --runxfail
 # the optional multigrid paths through the same tests (environment switches read by b200ls_create)
 run pytest_multigrid_tail 600 env B200LS_MG_TAIL=1 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m gpu -q --runxfail
 run pytest_multigrid_fuse 600 env B200LS_MG_FUSE=1 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m gpu -q --runxfail
