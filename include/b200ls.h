@@ -147,7 +147,8 @@ int b200ls_set_options(b200ls_solver *h, const b200ls_options *opts);
 int b200ls_get_options(const b200ls_solver *h, b200ls_options *opts);
 /* Launch-configuration knobs for experiments: "kz_chunk" (z planes per CTA of the SpMV kernel,
  * 0 = auto), "upd_blocks" (grid of the update kernel, 0 = auto), "tile" (SpMV tile variant),
- * "use_graph" (CUDA-graph the iteration batches, default 1), "mg_graph" (the same for pc_type mg, default 0),
+ * "use_graph" (CUDA-graph the iteration batches, default 1), "mg_graph" / "csr_graph" (the same for pc_type mg / the
+ * assembled-operator paths, default 0),
  * "mg_tail" (coarse levels of the multigrid cycle as one launch, default 0), "mg_fuse" (the residual update and the
  * reduction of the preconditioned CG loop folded into the first / last fine-level step of the cycle, default 0). */
 int b200ls_set_tuning(b200ls_solver *h, const char *key, int value);

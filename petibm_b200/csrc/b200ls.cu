@@ -130,7 +130,8 @@ struct b200ls_solver
     MgParams mg_prm;
     bool mg_ready = false;
     int mg_built_levels = 0;
-    int64_t mg_graph_launches = 0;
+    int64_t graph_launches = 0;   // launches inside the graph replayed by graph_batch (csr_solver.inc)
+    int csr_graph = 0;            // tuning "csr_graph": CG / BiCGStab batches of the assembled-operator paths as CUDA graphs
     int mg_fuse = 0;         // tuning "mg_fuse": r -= a w and the six sums ride on the first / last fine-level step of the cycle
     int mg_tail = 0;         // tuning "mg_tail": the coarse levels of the cycle as one launch (k_mg_tail; off until timed)
     MgOp *mg_tail_ops = nullptr;
@@ -1208,6 +1209,7 @@ int b200ls_create(b200ls_solver **out, int device)
     if (const char *e = getenv("B200LS_UPD_VARIANT")) h->upd_variant = atoi(e);
     // experiment switches of the multigrid path (same as b200ls_set_tuning): lets the whole device test-suite run with them
     if (const char *e = getenv("B200LS_MG_GRAPH")) h->mg_graph = atoi(e);
+    if (const char *e = getenv("B200LS_CSR_GRAPH")) h->csr_graph = atoi(e);
     if (const char *e = getenv("B200LS_MG_TAIL")) h->mg_tail = atoi(e);
     if (const char *e = getenv("B200LS_MG_FUSE")) h->mg_fuse = atoi(e);
     build_commdev(h);
@@ -1280,6 +1282,7 @@ int b200ls_set_tuning(b200ls_solver *h, const char *key, int value)
     else if (k == "use_graph") h->use_graph = value;
     else if (k == "use_pdl") h->use_pdl = value;
     else if (k == "mg_graph") h->mg_graph = value;
+    else if (k == "csr_graph") h->csr_graph = value;
     else if (k == "mg_tail") h->mg_tail = value;
     else if (k == "mg_fuse") h->mg_fuse = value;
     else return fail(h, B200LS_ERR_ARG, "unknown tuning key %s", key);

@@ -25,6 +25,7 @@ run pytest_multigrid 600 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m g
 run pytest_multigrid_tail 600 env B200LS_MG_TAIL=1 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m gpu -q --runxfail
 run pytest_multigrid_fuse 600 env B200LS_MG_FUSE=1 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m gpu -q --runxfail
 run pytest_multigrid_graph 600 env B200LS_MG_GRAPH=1 B200LS_MG_TAIL=1 B200LS_MG_FUSE=1 python -m pytest tests/test_zzz_gpu_4_multigrid.py -m gpu -q --runxfail
+run pytest_csr_graph 600 env B200LS_CSR_GRAPH=1 python -m pytest tests/test_gpu_csr.py tests/test_velocity_operator.py tests/test_zzz_gpu_2_staggered.py -m gpu -q --runxfail
 # 2. round-2 kernel candidates against the default: 256^3 and the 8-GPU slab
 run tune_256 600 python scripts/tune_k1.py --tiles 10 18 30 31 32 33
 run tune_slab 300 python scripts/tune_k1.py --size 256 256 32 --tiles 10 13 18 30 31 32 33
