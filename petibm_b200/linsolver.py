@@ -407,6 +407,13 @@ class LinSolverB200(LinSolverBase):
         _lib.check(self._L.b200ls_velocity_size(self._h, C.byref(nv), C.byref(npr)), self._h)
         return nv.value, npr.value
 
+    def _sync_stream(self, device):
+        """The *_device entry points are asynchronous on the solver's own stream: wait for it before torch reads the result
+        on its stream (an application that chains b200ls calls only would not need this)."""
+        import torch
+
+        torch.cuda.ExternalStream(int(self._L.b200ls_stream(self._h)), device=device).synchronize()
+
     @staticmethod
     def _dev(t, n):
         import torch
@@ -424,6 +431,7 @@ class LinSolverB200(LinSolverBase):
             out = torch.empty(npr, dtype=torch.float64, device=u.device) if out is None else out
             torch.cuda.current_stream(u.device).synchronize()
             _lib.check(self._L.b200ls_divergence_device(self._h, self._dev(u, nv), self._dev(out, npr)), self._h)
+            self._sync_stream(u.device)
             return out
         u = np.ascontiguousarray(u, dtype=np.float64)
         out = np.empty(npr)
@@ -440,6 +448,7 @@ class LinSolverB200(LinSolverBase):
             out = torch.empty(nv, dtype=torch.float64, device=p.device) if out is None else out
             torch.cuda.current_stream(p.device).synchronize()
             _lib.check(self._L.b200ls_gradient_device(self._h, self._dev(p, npr), self._dev(out, nv), int(bool(with_bn))), self._h)
+            self._sync_stream(p.device)
             return out
         p = np.ascontiguousarray(p, dtype=np.float64)
         out = np.empty(nv)
@@ -456,6 +465,7 @@ class LinSolverB200(LinSolverBase):
 
             torch.cuda.current_stream(u.device).synchronize()
             _lib.check(self._L.b200ls_project_device(self._h, self._dev(u, nv), self._dev(p, npr), self._dev(dp, npr)), self._h)
+            self._sync_stream(u.device)
             return u, p
         for a, m in ((u, nv), (p, npr)):
             if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.size == m):
