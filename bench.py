@@ -52,7 +52,9 @@ def parse_args():
     ap.add_argument("--halo", default="store", choices=["store", "memcpy"])
     ap.add_argument("--no-profile", action="store_true", help="no per-kernel events (CUDA-graph batches instead)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-iters", type=int, default=0, help="iterations of the CPU sample (0 = auto)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-bench history comparison with the oracle")
+    ap.add_argument("--cpu-iters", type=int, default=0, help="iterations of the CPU sample (0 = auto; reference arm: --iters)")
+    ap.add_argument("--cpu-budget", type=float, default=900.0, help="reference arm: seconds after which steps become bounded samples")
     ap.add_argument("--tune", nargs="*", default=[], help="key=value launch knobs (kz_chunk, tile, upd_blocks)")
     return ap.parse_args()
 
@@ -61,6 +63,68 @@ def parse_args():
 def workload_name(n, iters, pc):
     return (f"3D {n[0]}x{n[1]}x{n[2]} uniform staggered-grid pressure Poisson D(dt I)G, fp64, KSP CG, pc {pc}, "
             f"constant null space, {iters} iterations per solve")
+
+
+def common_config(n, iters, pc):
+    """The `config` object, identical in both arms (own and --impl reference): what is solved, nothing about how."""
+    return {"workload": workload_name(n, iters, pc), "size": list(n), "iterations_per_solve": int(iters), "pc": pc,
+            "ksp": "cg", "null_space": "constant", "dt": 0.01,
+            "l2": "no flush between steps: the working set is 5 fp64 vectors x %.0f MB = %.0f MB for the whole job, larger "
+                  "than the 126 MB L2 of a GPU for N <= %d GPUs (beyond that the strong-scaled slab is L2-resident by "
+                  "construction)" % (8e-6 * n[0] * n[1] * n[2], 40e-6 * n[0] * n[1] * n[2], max(1, int(40e-6 * n[0] * n[1] * n[2] // 126)))}
+
+
+def probe_petsc():
+    """Looks for a real PETSc on this box (SURVEY 8d: $PETSC_DIR, pkg-config, petsc4py).  The image used so far has none;
+    when one is found, oracle/petsc_ksp_driver.c (the calls of linsolverksp.cpp:62-66,78-79,92 on the same matrix)
+    can be built against it by oracle/build_petsc_driver.sh to time the real KSP and to pin the residual history."""
+    found = {}
+    d = os.environ.get("PETSC_DIR")
+    if d and os.path.isdir(d):
+        found["PETSC_DIR"] = d
+    try:
+        r = subprocess.run(["pkg-config", "--modversion", "PETSc"], capture_output=True, text=True, timeout=10)
+        if r.returncode == 0:
+            found["pkg-config"] = r.stdout.strip()
+        else:
+            r = subprocess.run(["pkg-config", "--modversion", "petsc"], capture_output=True, text=True, timeout=10)
+            if r.returncode == 0:
+                found["pkg-config"] = r.stdout.strip()
+    except Exception:
+        pass
+    try:
+        import importlib.util
+
+        if importlib.util.find_spec("petsc4py") is not None:
+            found["petsc4py"] = True
+    except Exception:
+        pass
+    return found or None
+
+
+def parity_block(n, pc, hist, nit=30, tol=1e-10):
+    """Outside every timed region: the first nit entries of the residual history of the benchmarked system against the
+    oracle's KSPSolve_CG on the same right-hand side (rank 0; every rank holds the same history)."""
+    from oracle import oracle as orc
+
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
+    orc.set_fast(True, threads)
+    widths = [np.full(m, 1.0 / m) for m in n]
+    A = orc.assemble_dbng(widths, (0, 0, 0), 0.01, literal=False)
+    rng = np.random.default_rng(SEED)
+    xs = rng.standard_normal(A.shape[0])
+    xs -= xs.mean()
+    b = A.spmv(xs)
+    nit = min(nit, len(hist) - 1)
+    ref = orc.ksp_solve(A, b, pc_type=pc, rtol=0.0, atol=0.0, max_it=nit, const_nullspace=True)
+    orc.set_fast(False, 0)
+    h = np.asarray(hist[: nit + 1])
+    rel = float(np.max(np.abs(h - ref.history[: nit + 1]) / ref.history[: nit + 1]))
+    return {"max_rel": rel, "tol": tol, "ok": bool(rel <= tol), "entries": int(nit + 1),
+            "against": "oracle KSPSolve_CG restatement (OpenMP summation), same right-hand side"}
 
 
 def peaks():
@@ -186,9 +250,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(n, iters, steps, warmup, pc, target_s=12.0):
+def cpu_reference_run(n, iters, steps, warmup, pc, target_s=12.0, budget_s=None):
     """The oracle's KSP CG (PETSc-style unfused passes over the assembled CSR) on all host threads.
     iters == 0: a 10-iteration probe sizes the sample to about target_s seconds of CPU work per step.
+    budget_s: iters is honoured unless the probe projects more than budget_s seconds for all steps.
     Returns (iterations/s, threads, seconds per step, description)."""
     from oracle import oracle as orc
 
@@ -207,11 +272,17 @@ def cpu_reference_run(n, iters, steps, warmup, pc, target_s=12.0):
     xs = rng.standard_normal(A.shape[0])
     xs -= xs.mean()
     b = A.spmv(xs)
-    if iters <= 0:
+    note = ""
+    if iters <= 0 or budget_s:
         t0 = time.perf_counter()
         orc.ksp_solve(A, b, pc_type=pc, rtol=0.0, atol=0.0, max_it=10, const_nullspace=True)
         rate = 10.0 / max(time.perf_counter() - t0, 1e-6)
-        iters = int(min(5000, max(20, target_s * rate)))
+        if iters <= 0:
+            iters = int(min(5000, max(20, target_s * rate)))
+        elif iters * (steps + warmup) / rate > budget_s:
+            asked = iters
+            iters = int(max(20, budget_s * rate / (steps + warmup)))
+            note = f" [bounded sample: {asked} asked, would exceed {budget_s:.0f} s]"
     times = []
     for s in range(warmup + steps):
         t0 = time.perf_counter()
@@ -224,7 +295,7 @@ def cpu_reference_run(n, iters, steps, warmup, pc, target_s=12.0):
     per_step = float(np.mean(times))
     return (iters / per_step, threads, per_step,
             f"{iters} CG iterations of the same {n[0]}x{n[1]}x{n[2]} system per step, {steps} step(s) "
-            f"(CSR assembly {t_asm:.1f} s not timed)")
+            f"(CSR assembly {t_asm:.1f} s not timed)" + note)
 
 
 def run_reference(args):
@@ -232,16 +303,18 @@ def run_reference(args):
     if rank != 0:
         return 0
     n = tuple(args.size)
-    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
-    # bounded sample: about a minute of CPU work in total, whatever --steps asks for
-    target = min(15.0, max(3.0, 60.0 / (steps + warmup)))
-    value, threads, per_step, sample = cpu_reference_run(n, args.cpu_iters, steps, warmup, args.pc, target)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    # the same workload as the own arm: --iters iterations per step, --warmup untimed steps.  Safety valve only: if a
+    # 10-iteration probe says the whole run would exceed --cpu-budget seconds, the step becomes a bounded sample.
+    iters = args.cpu_iters if args.cpu_iters > 0 else args.iters
+    value, threads, per_step, sample = cpu_reference_run(n, iters, steps, warmup, args.pc, budget_s=args.cpu_budget)
     line = {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(n, args.iters, args.pc), "host": "CPU, KSP restatement (oracle port; PETSc is not installable here)"},
+        "config": common_config(n, args.iters, args.pc),
+        "details": {"host": "CPU, KSP restatement (oracle port; PETSc is not installable here)", "petsc_found": probe_petsc()},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -372,6 +445,13 @@ def run_b200(args):
                 "measured_in": "K extra steps of the same workload with a CUDA-event pair around every launch "
                                "(%.2f ms/step there vs %.2f ms/step in the value region)" % (prof_ms_per_step, ms_per_step)}
 
+    # parity of the benchmarked system itself, at every N (outside the timed regions)
+    hist = solver.getHistory()
+    parity = None
+    if comm.rank == 0 and not args.no_parity:
+        parity = parity_block(n, args.pc, hist)
+    comm.barrier()
+
     cpu = None
     if comm.rank == 0 and comm.nranks == 1 and not args.no_cpu_baseline:
         v, threads, per_step, sample = cpu_reference_run(n, args.cpu_iters, 1, 0, args.pc, 12.0)
@@ -382,15 +462,16 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": comm.nranks, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": workload_name(n, args.iters, args.pc),
+            "config": common_config(n, args.iters, args.pc),
+            "details": {
                 "partition": f"z-slabs over {comm.nranks} GPU(s); halo {args.halo}, scalar all-reduce {args.reduce}" if comm.nranks > 1 else "single GPU",
                 "l2": ("inputs larger than L2: 5 vectors x %.0f MB per GPU" % (nloc * 8 / 1e6)) if nloc * 8 * 5 > 126e6
                       else ("per-GPU working set %.0f MB fits the 126 MB L2 (strong scaling of a fixed problem)" % (nloc * 8 * 5 / 1e6)),
                 "timing": "CUDA events on the solver stream inside libb200ls (scatter of b .. gather of x), max over ranks; "
                           "iteration batches are CUDA graphs with programmatic dependent launch",
-                "wall_s_timed_region": wall_max, "final_residual_norm": resid,
+                "wall_s_timed_region": wall_max, "final_residual_norm": resid, "petsc_found": probe_petsc(),
             },
+            "parity": parity,
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 8 * N,
                     "ms_per_step": e2e_ms_max / args.steps},

@@ -7,15 +7,6 @@ from oracle import oracle as orc
 
 SEED = 20240521
 
-# Device tests of code that was written after round 1's GPU budget was spent: their bodies run on the CPU emulation
-# (tests/test_gpu_tests_on_emulation.py), but no GPU has executed them yet.  Until one has, a failure is reported as
-# "xfailed" and a pass as "xpassed" instead of turning the validated suite red; scripts/round2_first_run.sh runs them with
-# --runxfail, and the marker is removed file by file once they have passed on a B200.
-import pytest  # noqa: E402
-
-NOT_YET_RUN_ON_A_GPU = pytest.mark.xfail(strict=False, reason="written after the round-1 GPU budget was spent: runs on the CPU "
-                                         "emulation, has not run on a GPU yet (DESIGN.md section 0)")
-
 
 def make_widths(shape, stretched=True, seed=SEED):
     rng = np.random.default_rng(seed)

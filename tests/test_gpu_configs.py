@@ -80,12 +80,13 @@ def test_c1_cavity32_through_the_config_files(pb, tmp_path):
 
 
 @pytest.mark.parametrize("pc", ["none", "jacobi"])
-def test_c2_128cubed_against_the_oracle(pb, pc):
-    n = (128, 128, 128)
+@pytest.mark.parametrize("n,nit", [((128, 128, 128), 60), ((256, 256, 256), 40)])
+def test_c2_128cubed_and_headline_256cubed_against_the_oracle(pb, pc, n, nit):
+    """C2 and the headline bench configuration itself (256^3 uniform): the residual history of the first nit
+    iterations against the oracle's KSPSolve_CG (OpenMP summation mode: about 1 s at 256^3), rtol 1e-10."""
     grid = pb.Grid.uniform(n, dt=0.01)
     A = orc.assemble_dbng(grid.widths, (0, 0, 0), 0.01, literal=False)
     b, xs = H.consistent_rhs(A)
-    nit = 60
     orc.set_fast(True, 0)
     ref = orc.ksp_solve(A, b, pc_type=pc, rtol=0.0, atol=0.0, max_it=nit, const_nullspace=True)
     orc.set_fast(False, 0)
@@ -141,9 +142,13 @@ def test_wider_stencil_takes_the_csr_fallback(pb):
     """BN order N > 1 widens DBNG (createbn.cpp:59-92): setMatrix must not mistake it for the 7-point form."""
     shape, per = (12, 11, 10), (0, 0, 0)
     widths = H.make_widths(shape)
-    A = H.oracle_matrix(widths, per).to_scipy()
-    W = (A - 0.05 * (A @ A)).tocsr()                           # symmetric, negative semi-definite, constants in the null space
+    _, Lap = H.velocity_system(widths, per, dt=0.01, nu=0.01, c=0.5)
+    Lo = orc.Csr.from_arrays(Lap.shape[0], Lap.shape[1], Lap.indptr, Lap.indices, Lap.data)
+    # the reference's own product: BN = dt I + dt^2 (c nu) L (createbn.cpp:59-92), then D (BN G) (navierstokes.cpp:351-356)
+    B2 = orc.bnhead(Lo, 0.01, 0.5 * 0.01, 2)
+    W = orc.matmatmult(orc.assemble_divergence(widths, per), orc.matmatmult(B2, orc.assemble_gradient(widths, per))).to_scipy().tocsr()
     W.sort_indices()
+    assert W.getnnz(axis=1).max() > 7                          # 13-/25-point rows
     Wo = orc.Csr.from_arrays(W.shape[0], W.shape[1], W.indptr, W.indices, W.data)
     b = W @ (lambda v: v - v.mean())(np.random.default_rng(6).standard_normal(W.shape[0]))
     s = pb.LinSolverB200("poisson", "None")

@@ -258,7 +258,8 @@ def test_device_resident_vectors(pb):
 
 @pytest.mark.parametrize("n,per", [((256, 256, 256), (0, 0, 0)), ((128, 128, 128), (1, 1, 1))])
 def test_full_size_properties(pb, n, per):
-    """BASELINE sizes: no oracle solve (too slow); size-independent properties instead."""
+    """BASELINE sizes through size-independent properties (the direct history comparison with the oracle at 128^3
+    and 256^3 is tests/test_gpu_configs.py::test_c2_128cubed_and_headline_256cubed_against_the_oracle)."""
     grid = pb.Grid.uniform(n, periodic=per, dt=0.01)
     s = _solver(pb, grid, rtol=1e-9, atol=1e-50, max_it=5000)
     s.setNullSpace(True)

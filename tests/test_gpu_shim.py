@@ -111,7 +111,6 @@ def _write_matrix_case(d, widths, per, M, b, null_mode, nullvec=None, with_grid=
 
 @pytest.mark.gpu
 @pytest.mark.timeout(600)
-@H.NOT_YET_RUN_ON_A_GPU
 def test_shim_picks_the_structured_operators_for_the_other_systems(tmp_path):
     """The three other matrices the applications hand to setMatrix, through the C++ shim: the velocity system (bcgs + jacobi,
     shipped velocity_solver.info) -> line-coefficient operator; IBPM's modified Poisson system on a stretched grid with

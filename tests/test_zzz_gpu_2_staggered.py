@@ -108,7 +108,6 @@ def test_a_matrix_without_the_structure_keeps_the_csr_operator(pb):
     s.destroy()
 
 
-@H.NOT_YET_RUN_ON_A_GPU
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("dim", [2, 3])
 def test_hybrid_operator_on_a_stretched_ibpm_system(pb, dim):

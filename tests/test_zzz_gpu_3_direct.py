@@ -10,7 +10,7 @@ from tests.test_emulated_kernels import _forces_system
 
 from tests import helpers as H  # noqa: E402
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600), H.NOT_YET_RUN_ON_A_GPU]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 
 @pytest.fixture(scope="module")

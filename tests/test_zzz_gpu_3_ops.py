@@ -8,7 +8,7 @@ import pytest
 from oracle import oracle as orc
 from tests import helpers as H
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600), H.NOT_YET_RUN_ON_A_GPU]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 
 @pytest.fixture(scope="module")

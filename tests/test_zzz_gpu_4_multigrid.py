@@ -9,7 +9,7 @@ from oracle import oracle as orc
 from tests import helpers as H
 from tests import mg_reference as R
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600), H.NOT_YET_RUN_ON_A_GPU]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 
 @pytest.fixture(scope="module")
