@@ -75,7 +75,7 @@ extern "C" {
 #define B200LS_KSP_PREONLY 2 /* with B200LS_PC_LU: direct solve of a small assembled system (decoupled IBPM forces system) */
 #define B200LS_PC_NONE 0
 #define B200LS_PC_JACOBI 1
-#define B200LS_PC_LU 3 /* dense LU of a matrix with at most 4096 rows; only with B200LS_KSP_PREONLY */
+#define B200LS_PC_LU 3 /* dense LU with partial pivoting of a matrix with at most 16384 rows; only with B200LS_KSP_PREONLY */
 #define B200LS_PC_MG 2 /* geometric multigrid on the separable pressure operator (extension, single GPU) */
 #define B200LS_NORM_NONE 0
 #define B200LS_NORM_PRECONDITIONED 1

@@ -939,13 +939,23 @@ extern "C" EMU_API int emu_stag_ops(int mode, int dim, const int64_t *n, const i
 extern "C" EMU_API int emu_dense_solve(int64_t n, const int64_t *rowptr, const int32_t *col, const double *val, int nrhs,
                                        const double *b, double *x, int threads)
 {
-    std::vector<double> a((size_t)n * (size_t)n, 0.0);
-    int info = -1;
-    emu::launch(dim3(2), dim3(256), 0, [&] { k_dense_fill(n, rowptr, col, val, a.data()); });
-    emu::launch(dim3(1), dim3(threads), 0, [&] { k_dense_lu((int)n, a.data(), &info); });
+    const int lda = (int)((n + 3) & ~(int64_t)3);
+    std::vector<double> a((size_t)n * (size_t)lda, 0.0);
+    std::vector<int> piv(n, -1), perm(n, -1);
+    int info = 0;
+    emu::launch(dim3(2), dim3(256), 0, [&] { k_dense_fill(n, lda, rowptr, col, val, a.data()); });
+    for (int kb = 0; kb < (int)n; kb += LU_NB)   // the launch sequence of dense_solver.inc
+    {
+        const int nb = std::min<int>(LU_NB, (int)n - kb), rest = (int)n - kb - nb, ncols = (int)n - nb;
+        emu::launch(dim3(1), dim3(threads), 0, [&] { k_lu_panel((int)n, lda, a.data(), kb, piv.data(), &info); });
+        if (ncols > 0) emu::launch(dim3((ncols + 127) / 128), dim3(128), 0, [&] { k_lu_swap_trsm((int)n, lda, a.data(), kb, piv.data(), &info); });
+        if (rest > 0) emu::launch(dim3((rest + 63) / 64, (rest + 63) / 64), dim3(256), 0, [&] { k_lu_gemm((int)n, lda, a.data(), kb, &info); });
+    }
     if (info != 0) return info;
+    emu::launch(dim3(1), dim3(32), 0, [&] { k_lu_perm((int)n, piv.data(), perm.data()); });
+    const size_t smem = sizeof(double) * ((size_t)lda + (size_t)LU_NB * (LU_NB + 1));
     for (int q = 0; q < nrhs; ++q)
-        emu::launch(dim3(1), dim3(threads), 0, [&] { k_dense_solve((int)n, a.data(), b + (size_t)q * n, x + (size_t)q * n); });
+        emu::launch(dim3(1), dim3(threads), smem, [&] { k_dense_solve((int)n, lda, a.data(), perm.data(), b + (size_t)q * n, x + (size_t)q * n); });
     return 0;
 }
 

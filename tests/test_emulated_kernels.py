@@ -560,3 +560,22 @@ def test_emulated_direct_solve_of_the_forces_system(emu):
     S = sp.csr_matrix(np.array([[1.0, 2.0, 0.0], [2.0, 4.0, 0.0], [0.0, 0.0, 1.0]]))
     rc, _ = _dense_solve(emu, S, np.ones(3), 32)
     assert rc == 2                                  # zero pivot in column 1 (1-based: 2): KSP_DIVERGED_PC_FAILED on the device path
+
+
+@pytest.mark.parametrize("n", [3, 31, 32, 33, 75, 130])
+def test_emulated_direct_solve_pivots(emu, n):
+    """Partial pivoting (what PETSc's LU / superlu_dist do): a matrix with a zero diagonal and rows of very different
+    scale, sizes around the panel width of 32; unpivoted elimination fails or loses all digits on these."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(100 + n)
+    A = rng.standard_normal((n, n))
+    A[np.arange(n), np.arange(n)] = 0.0             # no usable diagonal pivot to start with
+    A[rng.integers(0, n, 2)] *= 1e6
+    assert np.linalg.cond(A) < 1e12
+    B = rng.standard_normal((2, n))
+    rc, X = _dense_solve(emu, sp.csr_matrix(A), B, 64)
+    assert rc == 0
+    ref = np.linalg.solve(A, B.T).T
+    np.testing.assert_allclose(X, ref, rtol=0, atol=1e-13 * np.linalg.cond(A) * np.abs(ref).max())
+    assert np.abs(A @ X.T - B.T).max() <= 1e-12 * (np.abs(A).max() * np.abs(X).max() * n)

@@ -45,6 +45,26 @@ def test_forces_system_direct_solve(pb, tmp_path):
     s.destroy()
 
 
+@pytest.mark.parametrize("n", [33, 130, 1000])
+def test_direct_solve_pivots(pb, n):
+    """Partial pivoting on the device (blocked LU, dense_kernels.cuh): zero diagonal, badly scaled rows, sizes that are
+    not multiples of the panel width; against LAPACK."""
+    rng = np.random.default_rng(100 + n)
+    A = rng.standard_normal((n, n))
+    A[np.arange(n), np.arange(n)] = 0.0
+    A[rng.integers(0, n, 2)] *= 1e6
+    s = pb.LinSolverB200("forces", "None")
+    s.setOptions(ksp_type="preonly", pc_type="lu")
+    s.setMatrix(pb.Mat.from_scipy(sp.csr_matrix(A)))
+    b = rng.standard_normal(n)
+    x = np.empty(n)
+    s.solve(x, b)
+    ref = np.linalg.solve(A, b)
+    np.testing.assert_allclose(x, ref, rtol=0, atol=1e-13 * np.linalg.cond(A) * np.abs(ref).max())
+    assert np.abs(A @ x - b).max() <= 1e-12 * (np.abs(A).max() * np.abs(x).max() * n)
+    s.destroy()
+
+
 def test_direct_solve_refusals(pb):
     s = pb.LinSolverB200("forces", "None")
     with pytest.raises(pb.B200Error):
