@@ -17,12 +17,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <map>
 #include <string>
 #include <vector>
 
 #include "kernels.cuh"
 #include "spmv2.cuh"
 #include "spmv3.cuh"
+#include "spmv4.cuh"
 #include "update_fly.cuh"
 #include "csr_kernels.cuh"
 #include "sep_kernels.cuh"
@@ -184,6 +186,7 @@ struct b200ls_solver
     int num_sms = 148;
     int kz_chunk = 0;        // 0 = auto
     int upd_blocks = 0;      // 0 = auto
+    std::map<std::pair<const void *, int>, TmaMap> tma_maps;  // (vector, box kind) -> tensor map of k_spmv4
     int tile = -1;           // K1 tile variant (-1: cost model picks 10 or 18; 10+: k_spmv2; <10: k_spmv)
     int upd_variant = 0;     // 0: flat k_update2, 1: first-generation k_update, 2: k_update2f (Jacobi diagonal on the fly)
     int upd_reverse = 1;     // k_update2 walks the owned range top-down (L2 reuse of what k_spmv2 wrote last)
@@ -270,6 +273,7 @@ void free_vectors(b200ls_solver *h)
     fr(h->d_val);
     fr(h->d_nullvecs);
     h->sep_hybrid = false;
+    h->tma_maps.clear();
     fr(h->d_dense);
     fr(h->d_dense_info);
     h->dense_ready = false;
@@ -397,16 +401,24 @@ inline TileCfg tile_dims(int tile)
         case 18: return {32, 12};  // 64 x 10 tile, S = 3, 2 CTAs/SM
         case 30: case 32: return {32, 12};  // k_spmv3 (balanced split; 32: + split barrier), 64 x 10 tile -- round-2 candidates
         case 31: case 33: return {32, 8};   // k_spmv3 (balanced split; 33: + split barrier), 64 x 6 tile  -- round-2 candidates
+        case 40: return {32, 9};   // k_spmv4 (TMA): 64 x 8 tile + producer warp, S = 4, 2 CTAs/SM
+        case 41: return {32, 5};   // k_spmv4: 64 x 4 tile, S = 4, 4 CTAs/SM
+        case 42: return {32, 9};   // k_spmv4: 64 x 8 tile, S = 3, 3 CTAs/SM
+        case 43: return {32, 17};  // k_spmv4: 64 x 16 tile, S = 3, 1 CTA/SM
         default: return {32, 8};   // 10: 64 x 6 tile, S = 4, 3 CTAs/SM
     }
 }
+inline bool tile_is_tma(int tile) { return tile >= 40 && tile < 50; }
+// rows of a tile that produce results
+inline int tile_rows(int tile) { const TileCfg t = tile_dims(tile); return tile_is_tma(tile) ? t.tyt - 1 : t.tyt - 2; }
 inline int tile_ctas_per_sm(int tile)
 {
     switch (tile)
     {
-        case 13: return 4;
-        case 18: case 30: case 32: return 2;
+        case 13: case 41: return 4;
+        case 18: case 30: case 32: case 40: return 2;
         case 0: return 2;
+        case 43: return 1;
         default: return 3;
     }
 }
@@ -421,7 +433,9 @@ inline K1Cfg k1_config(const b200ls_solver *h)
     const int nzl = h->g.nzl;
     int tiles[2] = {10, 18};
     int ntiles = 2;
-    if (h->tile >= 0)
+    // the TMA kernel covers non-periodic grids (periodic wrap rows re-sort their columns: k_spmv2<PER>)
+    const bool tma_refused = tile_is_tma(h->tile) && (h->per[0] || h->per[1] || h->per[2]);
+    if (h->tile >= 0 && !tma_refused)
     {
         tiles[0] = h->tile;
         ntiles = 1;
@@ -431,7 +445,7 @@ inline K1Cfg k1_config(const b200ls_solver *h)
     for (int q = 0; q < ntiles; ++q)
     {
         const TileCfg t = tile_dims(tiles[q]);
-        const int ty = t.tyt - 2;
+        const int ty = tile_rows(tiles[q]);
         const int64_t xy = (int64_t)((h->g.nx + 2 * t.txt - 1) / (2 * t.txt)) * ((h->g.ny + ty - 1) / ty);
         const int64_t slots = (int64_t)h->num_sms * tile_ctas_per_sm(tiles[q]);
         const int max_nch = (h->kz_chunk > 0) ? 1 : std::max(1, std::min(64, nzl / 4));
@@ -540,12 +554,87 @@ int launch_spmv3_cfg(b200ls_solver *h, const VecSet &v, int ghost_store)
     return B200LS_OK;
 }
 
+// ---- k_spmv4: tensor maps (one per vector and box shape, cached in the handle) and launch
+using TmaEncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline TmaEncodeFn tma_encoder()
+{
+    static TmaEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried)
+    {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<TmaEncodeFn>(p);
+    }
+    return fn;
+}
+
+// box (bw x bh x 1) over a solver-layout vector [nzl+2][ny][px]; the extents are (nx, ny, nzl+2), so the pad columns of
+// the row pitch and everything outside the grid read as zeros
+int tma_map_for(b200ls_solver *h, const double *vec, int bw, int bh, const TmaMap **out)
+{
+    const auto key = std::make_pair((const void *)vec, bw * 1024 + bh);
+    auto it = h->tma_maps.find(key);
+    if (it == h->tma_maps.end())
+    {
+        TmaEncodeFn enc = tma_encoder();
+        if (!enc) return fail(h, B200LS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        TmaMap m;
+        const cuuint64_t dims[3] = {(cuuint64_t)h->g.nx, (cuuint64_t)h->g.ny, (cuuint64_t)h->g.nzl + 2};
+        const cuuint64_t strides[2] = {(cuuint64_t)h->g.px * 8, (cuuint64_t)h->g.plane * 8};
+        const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult rc = enc(&m.m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)vec, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) return fail(h, B200LS_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d (box %d x %d)", (int)rc, bw, bh);
+        it = h->tma_maps.emplace(key, m).first;
+    }
+    *out = &it->second;
+    return B200LS_OK;
+}
+
+template <int TY, int S, int MINB, bool JAC>
+int launch_spmv4_cfg(b200ls_solver *h, const VecSet &v, int ghost_store, dim3 grid, int kz)
+{
+    using L = Spmv4Smem<TY, S, JAC>;
+    const SolveConsts kc = make_consts(h);
+    dim3 block(32, TY + 1);
+    Spmv4Maps maps;
+    const TmaMap *m = nullptr;
+    TRY(tma_map_for(h, v.r, L::BW, L::BH, &m));
+    maps.r = *m;
+    TRY(tma_map_for(h, v.p_in, L::BW, L::BH, &m));
+    maps.p = *m;
+    TRY(tma_map_for(h, v.x, L::BX, TY, &m));
+    maps.x = *m;
+    if (JAC) TRY(tma_map_for(h, v.dinv, L::BW, L::BH, &m));
+    maps.d = *m;  // without Jacobi: any valid map (never read)
+    auto kern = k_spmv4<TY, S, MINB, JAC>;
+    static bool attr_done = false;
+    if (!attr_done)
+    {
+        CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total(512)));
+        attr_done = true;
+    }
+    CU(h, launch_k(h, h->in_loop && pdl_on(h), kern, grid, block, L::total(kz), maps, h->g, v, kz, h->ws, h->cm, h->d_state, kc,
+                   h->d_hist, ghost_store));
+    return B200LS_OK;
+}
+
 template <bool JAC, bool APPLY>
 int launch_spmv_t(b200ls_solver *h, const VecSet &v, int ghost_store)
 {
     const TileCfg t = tile_cfg(h);
     const int kz = auto_kz_chunk(h);
-    dim3 grid((unsigned)((h->g.nx + 2 * t.txt - 1) / (2 * t.txt)), (unsigned)((h->g.ny + t.tyt - 3) / (t.tyt - 2)),
+    const int tile = k1_config(h).tile;
+    const int rows = tile_rows(tile);
+    dim3 grid((unsigned)((h->g.nx + 2 * t.txt - 1) / (2 * t.txt)), (unsigned)((h->g.ny + rows - 1) / rows),
               (unsigned)((h->g.nzl + kz - 1) / kz));
     dim3 block(t.txt, t.tyt);
     const SolveConsts kc = make_consts(h);
@@ -553,7 +642,6 @@ int launch_spmv_t(b200ls_solver *h, const VecSet &v, int ghost_store)
 #define B200_SPMV_CASE(TXT, TYT)                                                                               \
     k_spmv<TXT, TYT, JAC, APPLY><<<grid, block, 0, h->stream>>>(h->g, v, kz, h->ws, h->cm, h->d_state, kc, \
                                                                  h->d_hist, ghost_store)
-    const int tile = k1_config(h).tile;
     if (APPLY && tile >= 10) return launch_spmv2_cfg<8, 4, 3, JAC, APPLY>(h, v, ghost_store, dim3(grid.x, (unsigned)((h->g.ny + 5) / 6), grid.z), kz);
     switch (tile)
     {
@@ -565,6 +653,10 @@ int launch_spmv_t(b200ls_solver *h, const VecSet &v, int ghost_store)
         case 31: return launch_spmv3_cfg<8, 4, 3, JAC, false>(h, v, ghost_store);
         case 32: return launch_spmv3_cfg<12, 3, 2, JAC, true>(h, v, ghost_store);
         case 33: return launch_spmv3_cfg<8, 4, 3, JAC, true>(h, v, ghost_store);
+        case 40: return launch_spmv4_cfg<8, 4, 2, JAC>(h, v, ghost_store, grid, kz);
+        case 41: return launch_spmv4_cfg<4, 4, 4, JAC>(h, v, ghost_store, grid, kz);
+        case 42: return launch_spmv4_cfg<8, 3, 3, JAC>(h, v, ghost_store, grid, kz);
+        case 43: return launch_spmv4_cfg<16, 3, 1, JAC>(h, v, ghost_store, grid, kz);
         default: return launch_spmv2_cfg<8, 4, 3, JAC, false>(h, v, ghost_store, grid, kz);
     }
 #undef B200_SPMV_CASE
@@ -575,8 +667,8 @@ int spmv_grid_blocks(const b200ls_solver *h)
 {
     const TileCfg t = tile_cfg(h);
     const int kz = auto_kz_chunk(h);
-    return (int)(((h->g.nx + 2 * t.txt - 1) / (2 * t.txt)) * ((h->g.ny + t.tyt - 3) / (t.tyt - 2)) *
-                 ((h->g.nzl + kz - 1) / kz));
+    const int rows = tile_rows(k1_config(h).tile);
+    return (int)(((h->g.nx + 2 * t.txt - 1) / (2 * t.txt)) * ((h->g.ny + rows - 1) / rows) * ((h->g.nzl + kz - 1) / kz));
 }
 
 int upd_grid_blocks(const b200ls_solver *h)

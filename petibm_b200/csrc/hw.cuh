@@ -7,9 +7,31 @@
 #ifdef B200_EMULATE
 #include "cuda_emu.h"
 #else
+#include <cuda.h>  // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 #include <cuda_runtime.h>
 
 namespace b200 {
+
+// ---- TMA (cp.async.bulk.tensor, sm_90+): one elected thread moves a whole box global -> shared; completion is
+// signalled on an mbarrier by transaction bytes.  Out-of-bounds elements of the box are filled with zeros.
+struct alignas(64) TmaMap { CUtensorMap m; };
+__device__ __forceinline__ void tma_prefetch_desc(const TmaMap *map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(unsigned int smem_dst, const TmaMap *map, unsigned int mbar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_dst),
+        "l"(map), "r"(mbar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned int a, unsigned int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+// after mbarrier.init, before the barriers are used by the async proxy (TMA)
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 __device__ __forceinline__ unsigned long long global_timer_ns()
 {

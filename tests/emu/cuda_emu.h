@@ -22,6 +22,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __grid_constant__
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
 
@@ -73,6 +74,7 @@ inline int bar_arrived = 0;
 inline unsigned char *dyn_smem = nullptr;
 inline unsigned long long fake_clock = 0;
 inline long progress = 0;
+inline void (*block_end_check)() = nullptr;  // installed by the TMA emulation: no box copy may be left undelivered
 // schedule fuzzing (emu_set_schedule): shuffled fiber order and random preemption at shared-memory accesses, so
 // that a missing barrier shows up as a result that depends on the schedule
 inline unsigned long long rng = 0;
@@ -218,6 +220,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F &&kernel_body)
                 }
                 for (auto &f : fibers)
                     if (!f.pending.empty()) { fprintf(stderr, "emu: cp.async copies never waited for\n"); abort(); }
+                if (block_end_check) block_end_check();
             }
     body = nullptr;
     cur = nullptr;
@@ -300,29 +303,91 @@ inline void cp_async_wait()
     }
     pend.resize(keep);
 }
-// mbarrier: {pending arrivals, expected count, parity of the current (incomplete) phase}; an arrival always counts
-// towards the CURRENT phase (as on hardware), so protocol errors show up as wrong results / deadlocks
-struct EmuMbar { unsigned int pending; unsigned short count; unsigned short phase; };
-inline void mbar_init(unsigned int a, unsigned int count)
+// mbarrier: {outstanding transaction bytes, pending arrivals, expected count, parity of the current (incomplete)
+// phase}; an arrival always counts towards the CURRENT phase (as on hardware), a phase completes when both the
+// arrivals and the transaction bytes have reached zero; protocol errors show up as wrong results / deadlocks
+struct EmuMbar { int tx : 31; unsigned int phase : 1; unsigned short pending; unsigned short count; };
+static_assert(sizeof(EmuMbar) == 8, "an mbarrier is one 64-bit shared-memory word");
+inline void mbar_check(EmuMbar *m)
 {
-    EmuMbar m = {count, (unsigned short)count, 0};
-    memcpy(smem_ptr(a), &m, 8);
-}
-inline void mbar_arrive(unsigned int a)
-{
-    emu::maybe_yield();
-    EmuMbar *m = reinterpret_cast<EmuMbar *>(smem_ptr(a));
-    if (--m->pending == 0)
+    if (m->pending == 0 && m->tx == 0)
     {
         m->phase ^= 1;
         m->pending = m->count;
     }
+}
+inline void mbar_init(unsigned int a, unsigned int count)
+{
+    EmuMbar m = {0, 0u, (unsigned short)count, (unsigned short)count};
+    memcpy(smem_ptr(a), &m, 8);
+}
+inline void mbar_init_fence() {}
+inline void mbar_arrive(unsigned int a)
+{
+    emu::maybe_yield();
+    EmuMbar *m = reinterpret_cast<EmuMbar *>(smem_ptr(a));
+    --m->pending;
+    mbar_check(m);
     ++emu::progress;
+}
+inline void mbar_arrive_expect_tx(unsigned int a, unsigned int bytes)
+{
+    emu::maybe_yield();
+    EmuMbar *m = reinterpret_cast<EmuMbar *>(smem_ptr(a));
+    m->tx += (int)bytes;
+    --m->pending;
+    mbar_check(m);
+    ++emu::progress;
+}
+// TMA: a 3-D box copy global -> shared with zero fill outside the tensor; like cp.async it is performed as LATE as
+// possible -- when a thread waits on the barrier the copy reports to and finds the phase incomplete
+struct TmaMap { const double *base; int dim[3]; long long stride[3]; int box[3]; };  // strides in elements
+struct EmuPendingTma { unsigned int dst, mbar; TmaMap map; int c[3]; };
+inline std::vector<EmuPendingTma> emu_tma_pending;
+inline void tma_prefetch_desc(const TmaMap *) {}
+inline void tma_load_3d(unsigned int dst, const TmaMap *map, unsigned int mbar, int c0, int c1, int c2)
+{
+    if (dst % 128 != 0) { fprintf(stderr, "emu: TMA destination not 128-byte aligned\n"); abort(); }
+    if ((map->box[0] * 8) % 16 != 0) { fprintf(stderr, "emu: TMA inner box extent not a multiple of 16 bytes\n"); abort(); }
+    emu_tma_pending.push_back({dst, mbar, *map, {c0, c1, c2}});
+    emu::block_end_check = [] {
+        if (!emu_tma_pending.empty()) { fprintf(stderr, "emu: a TMA copy was still in flight when the CTA exited\n"); abort(); }
+    };
+    ++emu::progress;
+}
+inline void emu_tma_deliver(unsigned int mbar)
+{
+    size_t keep = 0;
+    for (size_t q = 0; q < emu_tma_pending.size(); ++q)
+    {
+        const EmuPendingTma &t = emu_tma_pending[q];
+        if (t.mbar != mbar) { emu_tma_pending[keep++] = t; continue; }
+        double *dst = reinterpret_cast<double *>(smem_ptr(t.dst));
+        const TmaMap &m = t.map;
+        for (int z = 0; z < m.box[2]; ++z)
+            for (int y = 0; y < m.box[1]; ++y)
+                for (int x = 0; x < m.box[0]; ++x)
+                {
+                    const int gx = t.c[0] + x, gy = t.c[1] + y, gz = t.c[2] + z;
+                    const bool in = gx >= 0 && gx < m.dim[0] && gy >= 0 && gy < m.dim[1] && gz >= 0 && gz < m.dim[2];
+                    *dst++ = in ? m.base[gx * m.stride[0] + gy * m.stride[1] + gz * m.stride[2]] : 0.0;
+                }
+        EmuMbar *b = reinterpret_cast<EmuMbar *>(smem_ptr(mbar));
+        b->tx -= 8 * m.box[0] * m.box[1] * m.box[2];
+        mbar_check(b);
+        ++emu::progress;
+    }
+    emu_tma_pending.resize(keep);
 }
 inline void mbar_wait(unsigned int a, unsigned int parity)
 {
     const EmuMbar *m = reinterpret_cast<const EmuMbar *>(smem_ptr(a));
-    while (m->phase == parity) emu::yield();
+    if (m->phase == parity) emu_tma_deliver(a);
+    while (m->phase == parity)
+    {
+        emu::yield();
+        if (m->phase == parity) emu_tma_deliver(a);
+    }
     emu::maybe_yield();
 }
 inline double2 lds128(unsigned int a) { emu::maybe_yield(); double2 v; memcpy(&v, smem_ptr(a), 16); return v; }

@@ -9,6 +9,7 @@
 
 #include "spmv2.cuh"
 #include "spmv3.cuh"
+#include "spmv4.cuh"
 #include "update_fly.cuh"
 #include "csr_kernels.cuh"
 #include "sep_kernels.cuh"
@@ -137,11 +138,44 @@ void launch_spmv3(const Problem &P, const VecSet &v, int nctas, Ws &W, DevState 
         emu::launch(dim3(grid), dim3(32, TYT), L::total(max_seg), [&] { k_spmv3<32, TYT, S, MINB, JAC, false, false, SPLIT>(g, v, ppc, max_seg, W.ws, W.cm, st, kc, hist, 0); });
 }
 
+// k_spmv4 (TMA boxes + mbarrier pipeline): the emulated tensor map carries what cuTensorMapEncodeTiled is given in
+// b200ls.cu (tma_map_for): extents (nx, ny, nzl+2), strides (1, px, plane), box (bw, bh, 1)
+inline TmaMap emu_tma_map(const GridDev &g, const double *vec, int bw, int bh)
+{
+    TmaMap m;
+    m.base = vec;
+    m.dim[0] = g.nx; m.dim[1] = g.ny; m.dim[2] = g.nzl + 2;
+    m.stride[0] = 1; m.stride[1] = g.px; m.stride[2] = g.plane;
+    m.box[0] = bw; m.box[1] = bh; m.box[2] = 1;
+    return m;
+}
+template <int TY, int S, int MINB, bool JAC>
+void launch_spmv4(const Problem &P, const VecSet &v, int kz, Ws &W, DevState *st, const SolveConsts &kc, double *hist, int ghost_store = 0)
+{
+    using L = Spmv4Smem<TY, S, JAC>;
+    const GridDev &g = P.g;
+    dim3 grid((unsigned)((g.nx + 63) / 64), (unsigned)((g.ny + TY - 1) / TY), (unsigned)((g.nzl + kz - 1) / kz));
+    Spmv4Maps maps;
+    maps.r = emu_tma_map(g, v.r, L::BW, L::BH);
+    maps.p = emu_tma_map(g, v.p_in, L::BW, L::BH);
+    maps.x = emu_tma_map(g, v.x, L::BX, TY);
+    maps.d = emu_tma_map(g, JAC ? v.dinv : v.r, L::BW, L::BH);
+    emu::launch(grid, dim3(32, TY + 1), L::total(kz), [&] { k_spmv4<TY, S, MINB, JAC>(maps, g, v, kz, W.ws, W.cm, st, kc, hist, ghost_store); });
+}
+
 template <bool JAC, bool APPLY>
 void spmv(const Problem &P, int tile, const VecSet &v, int kz, Ws &W, DevState *st, const SolveConsts &kc, double *hist)
 {
     if constexpr (!APPLY)
     {
+        const bool periodic = P.per[0] || P.per[1] || P.per[2];
+        if (tile >= 40 && tile < 50 && !periodic)
+        {
+            if (tile == 40) return launch_spmv4<8, 4, 2, JAC>(P, v, kz, W, st, kc, hist);
+            if (tile == 41) return launch_spmv4<4, 4, 4, JAC>(P, v, kz, W, st, kc, hist);
+            if (tile == 42) return launch_spmv4<8, 3, 3, JAC>(P, v, kz, W, st, kc, hist);
+            return launch_spmv4<16, 3, 1, JAC>(P, v, kz, W, st, kc, hist);
+        }
         if (tile == 30) return launch_spmv3<12, 3, 2, JAC, false>(P, v, kz, W, st, kc, hist);
         if (tile == 31) return launch_spmv3<8, 4, 3, JAC, false>(P, v, kz, W, st, kc, hist);
         if (tile == 32) return launch_spmv3<12, 3, 2, JAC, true>(P, v, kz, W, st, kc, hist);
@@ -235,7 +269,7 @@ EMU_API int emu_stencil_cg(int dim, const int64_t *n, const int *per, const doub
     DevState st{};
     emu::launch(dim3(1), dim3(32), 0, [&] { k_state_reset(&st); });
     emu::launch(dim3(4), dim3(256), 0, [&] { k_scatter(P.g, b, r.data(), x.data()); });
-    if (kz <= 0 && tile < 30) kz = P.g.nzl;
+    if (kz <= 0 && (tile < 30 || tile >= 40)) kz = P.g.nzl;
     if (upd_blocks <= 0) upd_blocks = 3;
     UpdVecs uv{r.data(), w.data(), jacobi ? dinv.data() : nullptr, upd_reverse};
     if (has_const)

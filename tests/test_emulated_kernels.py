@@ -20,7 +20,7 @@ LIB = os.path.join(EMU, "libb200emu.so")
 SRC = [os.path.join(EMU, f) for f in ("emu_solver.cpp", "cuda_emu.h")] + \
       [os.path.join(ROOT, "petibm_b200", "csrc", f) for f in ("kernels.cuh", "spmv2.cuh", "spmv3.cuh", "hw.cuh", "csr_kernels.cuh",
                                                             "sep_kernels.cuh", "mg_kernels.cuh", "mg_schedule.h",
-                                                            "ops_kernels.cuh", "update_fly.cuh", "dense_kernels.cuh")]
+                                                            "ops_kernels.cuh", "update_fly.cuh", "dense_kernels.cuh", "spmv4.cuh")]
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -112,6 +112,43 @@ def test_emulated_cg_matches_oracle(emu, tile, pc):
         assert (its, reason) == (ref.its, ref.reason) == (nit, -3) and hist.size == nit + 1 and rn == hist[-1]
         np.testing.assert_allclose(hist, ref.history, rtol=1e-10)
         np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-9 * np.abs(ref.x).max())
+
+
+@pytest.mark.parametrize("tile", [40, 41, 42, 43])
+@pytest.mark.parametrize("pc", ["none", "jacobi"])
+def test_emulated_tma_kernel_matches_oracle(emu, tile, pc):
+    """k_spmv4 (TMA boxes with zero fill outside the grid, mbarrier full/empty pipeline, neighbours' p rebuilt from the
+    staged r / p', row sum closed one plane later): ragged tiles in x and y, several z chunks, 2-D, tiny grids."""
+    for shape, per, kz in (((12, 10, 8), (0, 0, 0), 3), ((70, 9, 5), (0, 0, 0), 0), ((67, 21, 7), (0, 0, 0), 2),
+                           ((33, 31), (0, 0), 0), ((5, 3, 3), (0, 0, 0), 1), ((1, 1, 7), (0, 0, 0), 0)):
+        widths = H.make_widths(shape)
+        A = H.oracle_matrix(widths, per)
+        b, _ = H.consistent_rhs(A)
+        nit = min(12, A.shape[0] - 3)                # 7 unknowns: exact convergence after 6 iterations, noise beyond
+        ref = orc.ksp_solve(A, b, pc_type=pc, rtol=0, atol=0, max_it=nit, const_nullspace=True)
+        x, hist, its, reason, rn = _cg(emu, widths, per, b, pc=pc, max_it=nit, tile=tile, kz=kz)
+        assert (its, reason) == (ref.its, ref.reason) == (nit, -3) and hist.size == nit + 1 and rn == hist[-1]
+        np.testing.assert_allclose(hist, ref.history, rtol=1e-10)
+        np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-9 * np.abs(ref.x).max())
+        # against the cp.async kernel: the same numbers up to the order of the block partial sums of p.w
+        x2, hist2, _, _, _ = _cg(emu, widths, per, b, pc=pc, max_it=nit, tile=10, kz=kz)
+        np.testing.assert_allclose(hist, hist2, rtol=1e-12)
+
+
+def test_emulated_tma_kernel_does_not_depend_on_the_thread_schedule(emu):
+    shape, per = (70, 13, 9), (0, 0, 0)
+    widths = H.make_widths(shape)
+    A = H.oracle_matrix(widths, per)
+    b, _ = H.consistent_rhs(A)
+    for tile in (40, 41):
+        x0, h0, _, _, _ = _cg(emu, widths, per, b, pc="jacobi", max_it=6, tile=tile, kz=3)
+        try:
+            for seed in (1, 2, 3):
+                emu.emu_set_schedule(seed)
+                x, h, _, _, _ = _cg(emu, widths, per, b, pc="jacobi", max_it=6, tile=tile, kz=3)
+                assert np.array_equal(h, h0) and np.array_equal(x, x0)
+        finally:
+            emu.emu_set_schedule(0)
 
 
 def test_emulated_convergence_logic_and_traversal_order(emu):
