@@ -41,6 +41,7 @@
  *   b200ls_divergence / _gradient / _project   MatMult(D, ...), MatMult(G / BNG, ...), VecAXPY around the solve
  *                                         navierstokes.cpp:442,540-551,583-615; createdivergence.cpp:140-223,
  *                                         creategradient.cpp:70-128
+ *   b200ls_convection                         MatMult(N, ...) of the convection MatShell, createconvection.cpp:39-332
  *   b200ls_repart_*                       the DMDA ownership the Vecs/Mat rows arrive in
  *                                         src/mesh/cartesianmesh.cpp:500-538,709-721 (DMDACreate3d,
  *                                         AOApplicationToPetsc) -> slab partition of the solver
@@ -302,6 +303,16 @@ int b200ls_velocity_size(b200ls_solver *h, int64_t *nvel, int64_t *npressure);
 int b200ls_divergence_device(b200ls_solver *h, const double *u_dev, double *out_dev);               /* out = D u */
 int b200ls_gradient_device(b200ls_solver *h, const double *p_dev, double *out_dev, int with_bn);   /* out = G p or (BN G) p */
 int b200ls_project_device(b200ls_solver *h, double *u_dev, double *p_dev, const double *dp_dev);   /* u -= BNG dp; p += dp (p may be null) */
+/* Convection term N(q) (createconvection.cpp:39-332, the MatShell H of navierstokes.cpp:446-470) on the GHOSTED local
+ * arrays of u, v, w: one ghost layer on every side, i fastest -- what DMCompositeScatterArray +
+ * Boundary::copyValues2LocalVecs produce in PetIBM (createconvection.cpp:217-221).  Output: packed [u|v|w].
+ * b200ls_ghosted_sizes gives the lengths of the three arrays; b200ls_ghosted_from_packed_device fills their interior
+ * and the wrap layers of periodic axes from a packed vector (DMGlobalToLocal); the ghost layers of non-periodic axes
+ * are the boundary conditions' values and stay with the caller.  qw may be null in 2-D. */
+int b200ls_ghosted_sizes(b200ls_solver *h, int64_t sizes[3]);
+int b200ls_convection_device(b200ls_solver *h, const double *qu_dev, const double *qv_dev, const double *qw_dev, double *out_dev);
+int b200ls_ghosted_from_packed_device(b200ls_solver *h, const double *packed_dev, double *qu_dev, double *qv_dev, double *qw_dev);
+int b200ls_convection(b200ls_solver *h, const double *qu_host, const double *qv_host, const double *qw_host, double *out_host);
 int b200ls_divergence(b200ls_solver *h, const double *u_host, double *out_host);
 int b200ls_gradient(b200ls_solver *h, const double *p_host, double *out_host, int with_bn);
 int b200ls_project(b200ls_solver *h, double *u_host, double *p_host, const double *dp_host);

@@ -87,6 +87,8 @@ def lib():
     L.orc_assemble_dbng_literal.restype = vp
     L.orc_assemble_dbng_closed.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_double]
     L.orc_assemble_dbng_closed.restype = vp
+    L.orc_convection.argtypes = [C.c_int, _ip, C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_dp)]
+    L.orc_convection.restype = None
     L.orc_set_fast.argtypes = [C.c_int, C.c_int]
     L.orc_max_threads.restype = C.c_int
     L.orc_spmv.argtypes = [vp, _dp, _dp]
@@ -147,6 +149,54 @@ def velocity_axis(dLp, vmin, vmax, same_dir, periodic):
     n = lib().orc_velocity_axis(dLp.size, vmin, vmax, p, int(same_dir), int(periodic),
                                 dl.ctypes.data_as(_dp), co.ctypes.data_as(_dp), C.byref(ln))
     return n, dl[: ln.value].copy(), co[: ln.value].copy()
+
+
+def field_sizes(n, periodic):
+    """Points of the velocity fields per direction (cartesianmesh.cpp:212-355: n - 1 along the field's own direction,
+    n when that direction is periodic; the pressure count otherwise)."""
+    dim = len(n)
+    return [[int(n[d]) - (1 if (d == f and not periodic[d]) else 0) for d in range(dim)] for f in range(dim)]
+
+
+def field_spacings(widths, periodic):
+    """mesh->dL[f][d] (interior part) for every field and direction, through orc_velocity_axis."""
+    dim = len(widths)
+    out = []
+    for f in range(dim):
+        row = []
+        for d in range(dim):
+            w = np.asarray(widths[d], dtype=np.float64)
+            nv, dl, _ = velocity_axis(w, 0.0, float(w.sum()), f == d, bool(periodic[d]))
+            row.append(np.ascontiguousarray(dl[1: 1 + nv]))
+        out.append(row)
+    return out
+
+
+def convection(widths, periodic, qlocal):
+    """N(q) of createconvection.cpp on the ghosted local arrays qlocal[f] (shape (nz_f+2, ny_f+2, nx_f+2), 2-D:
+    (ny_f+2, nx_f+2)); returns the list of interior fields (the blocks of the packed vector)."""
+    dim = len(widths)
+    n = [len(w) for w in widths]
+    nf = field_sizes(n, periodic)
+    dL = field_spacings(widths, periodic)
+    nf_flat = np.zeros(9, dtype=np.int32)
+    PD = _dp * 9
+    PQ = _dp * 3
+    dl_ptrs, q_ptrs, o_ptrs = PD(), PQ(), PQ()
+    keep, outs = [], []
+    for f in range(dim):
+        for d in range(dim):
+            nf_flat[3 * f + d] = nf[f][d]
+            dl_ptrs[3 * f + d] = dL[f][d].ctypes.data_as(_dp)
+        q = np.ascontiguousarray(qlocal[f], dtype=np.float64)
+        assert q.shape == tuple(m + 2 for m in reversed(nf[f])), (q.shape, nf[f])
+        keep.append(q)
+        q_ptrs[f] = q.ctypes.data_as(_dp)
+        o = np.empty(tuple(reversed(nf[f])))
+        outs.append(o)
+        o_ptrs[f] = o.ctypes.data_as(_dp)
+    lib().orc_convection(dim, nf_flat.ctypes.data_as(_ip), dl_ptrs, q_ptrs, o_ptrs)
+    return outs
 
 
 # ---------------------------------------------------------------------------- CSR

@@ -1130,3 +1130,91 @@ ORC_API int orc_ksp_solve(const orc_csr *A, const orc_ksp_opts *opts, const doub
     free(c.dinv);
     return reason;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Convection operator N(q) of createconvection.cpp (a MatShell: ConvectionMult2D :205-262 /
+ * ConvectionMult3D :266-332 with the point kernels kernelU/kernelV/kernelW :39-200).
+ *
+ * Input: the LOCAL (ghosted) arrays of the velocity fields, what DMCompositeScatterArray +
+ * Boundary::copyValues2LocalVecs leave in ctx->qLocal (:217-221, :285-289): field f has nf[3f+0..2]
+ * points per direction, stored with one ghost layer on every side, i fastest:
+ *     q[f][(i+1) + (nx_f+2)*((j+1) + (ny_f+2)*(k+1))]     (2-D: no k)
+ * dL[3f+d] = mesh->dL[f][d] (interior part: index 0 = first real point; cartesianmesh.cpp:212-355,
+ * produced by orc_velocity_axis).  Output: the three fields, interior points only, i fastest
+ * (the blocks of the packed vector [u | v | w]).
+ * The expressions are the reference's, term by term and in its order; this file is compiled with
+ * -ffp-contract=off, which is what an x86-64 build of PetIBM without -march flags executes.
+ * No golden vector: the reference has no test for this operator ("parity unpinned" for it). */
+#define QF(f, i, j, k) \
+    q[f][((i) + 1) + (size_t)(nf[3 * (f)] + 2) * (((j) + 1) + (size_t)(nf[3 * (f) + 1] + 2) * (dim == 3 ? (k) + 1 : 0))]
+ORC_API void orc_convection(int dim, const int *nf, const double *const *dL, const double *const *q,
+                            double *const *out)
+{
+    for (int f = 0; f < dim; ++f)
+    {
+        const int nx = nf[3 * f], ny = nf[3 * f + 1], nz = dim == 3 ? nf[3 * f + 2] : 1;
+        const double *dLx = dL[3 * f], *dLy = dL[3 * f + 1], *dLz = dL[3 * f + 2];
+        for (int k = 0; k < nz; ++k)
+            for (int j = 0; j < ny; ++j)
+                for (int i = 0; i < nx; ++i)
+                {
+                    double r;
+                    if (f == 0)
+                    { /* kernelU :39-64 (2-D), :94-126 (3-D) */
+                        const double uSelf = QF(0, i, j, k);
+                        const double uW = (uSelf + QF(0, i - 1, j, k)) / 2.0;
+                        const double uE = (uSelf + QF(0, i + 1, j, k)) / 2.0;
+                        const double uS = (uSelf + QF(0, i, j - 1, k)) / 2.0;
+                        const double uN = (uSelf + QF(0, i, j + 1, k)) / 2.0;
+                        const double vS = (QF(1, i, j - 1, k) + QF(1, i + 1, j - 1, k)) / 2.0;
+                        const double vN = (QF(1, i, j, k) + QF(1, i + 1, j, k)) / 2.0;
+                        r = (uE * uE - uW * uW) / dLx[i] + (vN * uN - vS * uS) / dLy[j];
+                        if (dim == 3)
+                        {
+                            const double uB = (uSelf + QF(0, i, j, k - 1)) / 2.0;
+                            const double uF = (uSelf + QF(0, i, j, k + 1)) / 2.0;
+                            const double wB = (QF(2, i, j, k - 1) + QF(2, i + 1, j, k - 1)) / 2.0;
+                            const double wF = (QF(2, i, j, k) + QF(2, i + 1, j, k)) / 2.0;
+                            r = r + (wF * uF - wB * uB) / dLz[k];
+                        }
+                    }
+                    else if (f == 1)
+                    { /* kernelV :67-91, :129-162 */
+                        const double vSelf = QF(1, i, j, k);
+                        const double uW = (QF(0, i - 1, j, k) + QF(0, i - 1, j + 1, k)) / 2.0;
+                        const double uE = (QF(0, i, j, k) + QF(0, i, j + 1, k)) / 2.0;
+                        const double vW = (vSelf + QF(1, i - 1, j, k)) / 2.0;
+                        const double vE = (vSelf + QF(1, i + 1, j, k)) / 2.0;
+                        const double vS = (vSelf + QF(1, i, j - 1, k)) / 2.0;
+                        const double vN = (vSelf + QF(1, i, j + 1, k)) / 2.0;
+                        r = (uE * vE - uW * vW) / dLx[i] + (vN * vN - vS * vS) / dLy[j];
+                        if (dim == 3)
+                        {
+                            const double vB = (vSelf + QF(1, i, j, k - 1)) / 2.0;
+                            const double vF = (vSelf + QF(1, i, j, k + 1)) / 2.0;
+                            const double wB = (QF(2, i, j, k - 1) + QF(2, i, j + 1, k - 1)) / 2.0;
+                            const double wF = (QF(2, i, j, k) + QF(2, i, j + 1, k)) / 2.0;
+                            r = r + (wF * vF - wB * vB) / dLz[k];
+                        }
+                    }
+                    else
+                    { /* kernelW :165-200 */
+                        const double wSelf = QF(2, i, j, k);
+                        const double uW = (QF(0, i - 1, j, k) + QF(0, i - 1, j, k + 1)) / 2.0;
+                        const double uE = (QF(0, i, j, k) + QF(0, i, j, k + 1)) / 2.0;
+                        const double vS = (QF(1, i, j - 1, k) + QF(1, i, j - 1, k + 1)) / 2.0;
+                        const double vN = (QF(1, i, j, k) + QF(1, i, j, k + 1)) / 2.0;
+                        const double wW = (wSelf + QF(2, i - 1, j, k)) / 2.0;
+                        const double wE = (wSelf + QF(2, i + 1, j, k)) / 2.0;
+                        const double wS = (wSelf + QF(2, i, j - 1, k)) / 2.0;
+                        const double wN = (wSelf + QF(2, i, j + 1, k)) / 2.0;
+                        const double wB = (wSelf + QF(2, i, j, k - 1)) / 2.0;
+                        const double wF = (wSelf + QF(2, i, j, k + 1)) / 2.0;
+                        r = (uE * wE - uW * wW) / dLx[i] + (vN * wN - vS * wS) / dLy[j] +
+                            (wF * wF - wB * wB) / dLz[k];
+                    }
+                    out[f][i + (size_t)nx * (j + (size_t)ny * k)] = r;
+                }
+    }
+}
+#undef QF

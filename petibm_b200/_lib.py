@@ -96,6 +96,10 @@ SIGNATURES = {
     "b200ls_divergence_device": (C.c_int, [_vp, _vp, _vp]),
     "b200ls_gradient_device": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "b200ls_project_device": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "b200ls_ghosted_sizes": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
+    "b200ls_convection_device": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "b200ls_ghosted_from_packed_device": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "b200ls_convection": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "b200ls_divergence": (C.c_int, [_vp, _vp, _vp]),
     "b200ls_gradient": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "b200ls_project": (C.c_int, [_vp, _vp, _vp, _vp]),

@@ -25,6 +25,7 @@
 #include "spmv2.cuh"
 #include "spmv3.cuh"
 #include "spmv4.cuh"
+#include "spmv5.cuh"
 #include "update_fly.cuh"
 #include "csr_kernels.cuh"
 #include "sep_kernels.cuh"
@@ -405,12 +406,20 @@ inline TileCfg tile_dims(int tile)
         case 41: return {32, 5};   // k_spmv4: 64 x 4 tile, S = 4, 4 CTAs/SM
         case 42: return {32, 9};   // k_spmv4: 64 x 8 tile, S = 3, 3 CTAs/SM
         case 43: return {32, 17};  // k_spmv4: 64 x 16 tile, S = 3, 1 CTA/SM
+        case 50: case 51: case 53: case 54: case 55: case 56: return {32, 8};  // k_spmv5 (no staging, cache-resident slabs): 64 x 8 rows, 4 / 8 / 16 planes per thread
+        case 52: return {32, 4};                    // k_spmv5: 64 x 4 rows, 2 planes per thread
         default: return {32, 8};   // 10: 64 x 6 tile, S = 4, 3 CTAs/SM
     }
 }
 inline bool tile_is_tma(int tile) { return tile >= 40 && tile < 50; }
+inline bool tile_is_direct(int tile) { return tile >= 50 && tile < 60; }
+inline int tile_direct_planes(int tile) { return (tile == 50 || tile == 54 || tile == 56) ? 4 : (tile == 51 || tile == 55) ? 8 : tile == 52 ? 2 : 16; }
 // rows of a tile that produce results
-inline int tile_rows(int tile) { const TileCfg t = tile_dims(tile); return tile_is_tma(tile) ? t.tyt - 1 : t.tyt - 2; }
+inline int tile_rows(int tile)
+{
+    const TileCfg t = tile_dims(tile);
+    return tile_is_direct(tile) ? t.tyt : tile_is_tma(tile) ? t.tyt - 1 : t.tyt - 2;
+}
 inline int tile_ctas_per_sm(int tile)
 {
     switch (tile)
@@ -434,7 +443,8 @@ inline K1Cfg k1_config(const b200ls_solver *h)
     int tiles[2] = {10, 18};
     int ntiles = 2;
     // the TMA kernel covers non-periodic grids (periodic wrap rows re-sort their columns: k_spmv2<PER>)
-    const bool tma_refused = tile_is_tma(h->tile) && (h->per[0] || h->per[1] || h->per[2]);
+    const bool tma_refused = (tile_is_tma(h->tile) || tile_is_direct(h->tile)) && (h->per[0] || h->per[1] || h->per[2]);
+    if (tile_is_direct(h->tile) && !tma_refused) return {h->tile, std::min(tile_direct_planes(h->tile), std::max(1, nzl))};
     if (h->tile >= 0 && !tma_refused)
     {
         tiles[0] = h->tile;
@@ -627,6 +637,15 @@ int launch_spmv4_cfg(b200ls_solver *h, const VecSet &v, int ghost_store, dim3 gr
     return B200LS_OK;
 }
 
+template <int TY, int KB, int MINB, bool JAC>
+int launch_spmv5_cfg(b200ls_solver *h, const VecSet &v, int ghost_store, dim3 grid)
+{
+    const SolveConsts kc = make_consts(h);
+    CU(h, launch_k(h, h->in_loop && pdl_on(h), k_spmv5<TY, KB, MINB, JAC>, grid, dim3(32, TY), 0, h->g, v, h->ws, h->cm, h->d_state, kc,
+                   h->d_hist, ghost_store));
+    return B200LS_OK;
+}
+
 template <bool JAC, bool APPLY>
 int launch_spmv_t(b200ls_solver *h, const VecSet &v, int ghost_store)
 {
@@ -657,6 +676,13 @@ int launch_spmv_t(b200ls_solver *h, const VecSet &v, int ghost_store)
         case 41: return launch_spmv4_cfg<4, 4, 4, JAC>(h, v, ghost_store, grid, kz);
         case 42: return launch_spmv4_cfg<8, 3, 3, JAC>(h, v, ghost_store, grid, kz);
         case 43: return launch_spmv4_cfg<16, 3, 1, JAC>(h, v, ghost_store, grid, kz);
+        case 50: return launch_spmv5_cfg<8, 4, 2, JAC>(h, v, ghost_store, grid);
+        case 51: return launch_spmv5_cfg<8, 8, 2, JAC>(h, v, ghost_store, grid);
+        case 52: return launch_spmv5_cfg<4, 2, 4, JAC>(h, v, ghost_store, grid);
+        case 53: return launch_spmv5_cfg<8, 16, 2, JAC>(h, v, ghost_store, grid);
+        case 54: return launch_spmv5_cfg<8, 4, 3, JAC>(h, v, ghost_store, grid);
+        case 55: return launch_spmv5_cfg<8, 8, 3, JAC>(h, v, ghost_store, grid);
+        case 56: return launch_spmv5_cfg<8, 4, 4, JAC>(h, v, ghost_store, grid);
         default: return launch_spmv2_cfg<8, 4, 3, JAC, false>(h, v, ghost_store, grid, kz);
     }
 #undef B200_SPMV_CASE

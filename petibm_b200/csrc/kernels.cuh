@@ -333,10 +333,27 @@ __device__ __forceinline__ void grid_reduce_finalize(double (&acc)[NS], int kind
     double tot[NS];
 #pragma unroll
     for (int q = 0; q < NS; ++q) tot[q] = 0.0;
-    for (unsigned int b = tid; b < nblocks; b += nthr)
+    // four independent loads in flight per thread and sum (each costs an L2 round trip); the grouping of the additions
+    // is a fixed function of (nblocks, block size), so the result stays deterministic
     {
+        unsigned int b = tid;
+        for (; b + 3u * nthr < nblocks; b += 4u * nthr)
+        {
+            double v[4][NS];
 #pragma unroll
-        for (int q = 0; q < NS; ++q) tot[q] += __ldcg(&ws.partials[(size_t)b * B200_NSUM + q]);
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int q = 0; q < NS; ++q) v[u][q] = __ldcg(&ws.partials[(size_t)(b + u * nthr) * B200_NSUM + q]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int q = 0; q < NS; ++q) tot[q] += v[u][q];
+        }
+        for (; b < nblocks; b += nthr)
+        {
+#pragma unroll
+            for (int q = 0; q < NS; ++q) tot[q] += __ldcg(&ws.partials[(size_t)b * B200_NSUM + q]);
+        }
     }
     __syncthreads();
 #pragma unroll

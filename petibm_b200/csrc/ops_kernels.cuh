@@ -127,6 +127,114 @@ __global__ void __launch_bounds__(256) k_gradient(StagGrid g, const double *p, d
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Convection term N(q) of the staggered grid (createconvection.cpp: ConvectionMult2D :205-262, ConvectionMult3D :266-332,
+// point kernels :39-200) -- the explicit part of rhs1 every time step (navierstokes.cpp:446-470).
+// Input: the GHOSTED local arrays of u, v, w (one ghost layer on every side, i fastest), i.e. what PetIBM's
+// DMCompositeScatterArray + Boundary::copyValues2LocalVecs hand to the point kernels; output: the packed vector [u|v|w].
+// For field f and direction d, with e_d the unit index offset:
+//     d == f : ((a+ a+) - (a- a-)) / dL        a+- = (q_f(c) + q_f(c +- e_d)) / 2
+//     d != f : ((t+ a+) - (t- a-)) / dL        t+ = (q_d(c) + q_d(c + e_f)) / 2,  t- = (q_d(c - e_d) + q_d(c - e_d + e_f)) / 2
+// summed over d = x, y, z in that order.  dL = mesh->dL[f][d]: the cell width for d != f, the mean of the two adjacent
+// widths for d == f (cartesianmesh.cpp:237-247; wrap pair on a periodic axis :251-273).  Products, differences, halvings
+// and divisions are separate IEEE operations in the reference's order: bit-identical to the oracle's restatement.
+// FP64 divisions make this kernel compute-heavier than its 16 B/point of traffic; it runs once per time step.
+struct GhostedDims
+{
+    int nx[3], ny[3], nz[3];   // interior points of field f per direction
+    long long off[3];          // first index of field f in the packed vector
+};
+__device__ __forceinline__ GhostedDims ghosted_dims(const StagGrid &g)
+{
+    GhostedDims d;
+    d.nx[0] = g.nu; d.ny[0] = g.ny; d.nz[0] = g.nz;
+    d.nx[1] = g.nx; d.ny[1] = g.nv; d.nz[1] = g.nz;
+    d.nx[2] = g.nx; d.ny[2] = g.ny; d.nz[2] = g.nw;
+    d.off[0] = 0; d.off[1] = g.offv; d.off[2] = g.offw;
+    return d;
+}
+
+__global__ void __launch_bounds__(256) k_convection(StagGrid g, const double *qu, const double *qv, const double *qw, double *out)
+{
+    const GhostedDims D = ghosted_dims(g);
+    const double *const q[3] = {qu, qv, qw};
+    const long long ntot = D.off[g.dim - 1] + (long long)D.nx[g.dim - 1] * D.ny[g.dim - 1] * D.nz[g.dim - 1];
+    const bool three = g.dim == 3;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < ntot; t += (long long)gridDim.x * blockDim.x)
+    {
+        const int f = (three && t >= D.off[2]) ? 2 : (t >= D.off[1] ? 1 : 0);
+        const long long l = t - D.off[f];
+        const int c[3] = {(int)(l % D.nx[f]), (int)((l / D.nx[f]) % D.ny[f]), (int)(l / ((long long)D.nx[f] * D.ny[f]))};
+        // ghosted index of field fl at integer position (a0, a1, a2)
+        auto at = [&](int fl, int a0, int a1, int a2) -> double {
+            const long long px = D.nx[fl] + 2, py = D.ny[fl] + 2;
+            return q[fl][(a0 + 1) + px * ((a1 + 1) + py * (three ? a2 + 1 : 0))];
+        };
+        auto half = [](double a, double b) { return __dmul_rn(__dadd_rn(a, b), 0.5); };
+        const double self = at(f, c[0], c[1], c[2]);
+        double sum = 0.0;
+        for (int d = 0; d < g.dim; ++d)
+        {
+            int cp[3] = {c[0], c[1], c[2]}, cm[3] = {c[0], c[1], c[2]};
+            cp[d] += 1;
+            cm[d] -= 1;
+            const double ap = half(self, at(f, cp[0], cp[1], cp[2]));
+            const double am = half(self, at(f, cm[0], cm[1], cm[2]));
+            const double *w = d == 0 ? g.dx : (d == 1 ? g.dy : g.dz);
+            const int nd = d == 0 ? g.nx : (d == 1 ? g.ny : g.nz);
+            double dl, tp, tm;
+            if (d == f)
+            {
+                dl = __dmul_rn(0.5, __dadd_rn(w[c[d] + 1 < nd ? c[d] + 1 : 0], w[c[d]]));
+                tp = ap;
+                tm = am;
+            }
+            else
+            {
+                dl = w[c[d]];
+                int c2[3] = {c[0], c[1], c[2]}, m2[3] = {cm[0], cm[1], cm[2]};
+                c2[f] += 1;
+                m2[f] += 1;
+                tp = half(at(d, c[0], c[1], c[2]), at(d, c2[0], c2[1], c2[2]));
+                tm = half(at(d, cm[0], cm[1], cm[2]), at(d, m2[0], m2[1], m2[2]));
+            }
+            const double term = __ddiv_rn(__dadd_rn(__dmul_rn(tp, ap), -__dmul_rn(tm, am)), dl);
+            sum = d == 0 ? term : __dadd_rn(sum, term);
+        }
+        out[t] = sum;
+    }
+}
+
+// Interior of the ghosted arrays from the packed vector, plus the wrap layers of periodic axes (what DMGlobalToLocal
+// leaves in a DMDA local vector); the ghost layers of non-periodic axes belong to the boundary conditions
+// (Boundary::copyValues2LocalVecs) and are not touched.
+__global__ void __launch_bounds__(256) k_ghosted_from_packed(StagGrid g, const double *packed, double *qu, double *qv, double *qw)
+{
+    const GhostedDims D = ghosted_dims(g);
+    double *const q[3] = {qu, qv, qw};
+    const int per[3] = {g.perx, g.pery, g.perz};
+    const bool three = g.dim == 3;
+    for (int f = 0; f < g.dim; ++f)
+    {
+        const long long px = D.nx[f] + 2, py = D.ny[f] + 2, pz = three ? D.nz[f] + 2 : 1;
+        const int n[3] = {D.nx[f], D.ny[f], D.nz[f]};
+        for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < px * py * pz; t += (long long)gridDim.x * blockDim.x)
+        {
+            int a[3] = {(int)(t % px) - 1, (int)((t / px) % py) - 1, three ? (int)(t / (px * py)) - 1 : 0};
+            bool ok = true;
+            for (int d = 0; d < g.dim; ++d)
+            {
+                if (a[d] < 0 || a[d] >= n[d])
+                {
+                    if (per[d]) a[d] = a[d] < 0 ? n[d] - 1 : 0;
+                    else ok = false;
+                }
+            }
+            if (ok) q[f][t] = packed[D.off[f] + a[0] + (long long)n[0] * (a[1] + (long long)n[1] * a[2])];
+        }
+    }
+}
+
 // p = p + 1.0 * dp   (VecAXPY(pGlobal, 1.0, dP))
 __global__ void __launch_bounds__(256) k_axpy_one(long long n, double *p, const double *dp)
 {

@@ -457,6 +457,48 @@ class LinSolverB200(LinSolverBase):
                    self._h)
         return out
 
+    def ghostedSizes(self):
+        sz = (C.c_int64 * 3)()
+        _lib.check(self._L.b200ls_ghosted_sizes(self._h, sz), self._h)
+        return [int(v) for v in sz]
+
+    def convection(self, qlocal, out=None):
+        """out = N(q): the convection MatShell of createconvection.cpp on the ghosted local arrays qlocal[f] (one ghost
+        layer on every side, i fastest; what Boundary::copyValues2LocalVecs leaves in ctx->qLocal); packed [u|v|w] out."""
+        nv, _ = self.velocitySize()
+        sizes = self.ghostedSizes()
+        dim = 3 if sizes[2] else 2
+        if _is_torch_cuda(qlocal[0]):
+            import torch
+
+            dev = qlocal[0].device
+            out = torch.empty(nv, dtype=torch.float64, device=dev) if out is None else out
+            torch.cuda.current_stream(dev).synchronize()
+            ptrs = [self._dev(qlocal[f], sizes[f]) for f in range(dim)] + ([C.c_void_p(0)] if dim == 2 else [])
+            _lib.check(self._L.b200ls_convection_device(self._h, ptrs[0], ptrs[1], ptrs[2], self._dev(out, nv)), self._h)
+            self._sync_stream(dev)
+            return out
+        q = [np.ascontiguousarray(qlocal[f], dtype=np.float64) for f in range(dim)]
+        for f in range(dim):
+            assert q[f].size == sizes[f], (q[f].size, sizes[f])
+        out = np.empty(nv)
+        _lib.check(self._L.b200ls_convection(self._h, C.c_void_p(q[0].ctypes.data), C.c_void_p(q[1].ctypes.data),
+                                             C.c_void_p(q[2].ctypes.data if dim == 3 else 0), C.c_void_p(out.ctypes.data)), self._h)
+        return out
+
+    def ghostedFromPacked(self, packed, qlocal):
+        """Interior and periodic wrap layers of the ghosted device arrays from a packed device vector (DMGlobalToLocal)."""
+        import torch
+
+        nv, _ = self.velocitySize()
+        sizes = self.ghostedSizes()
+        dim = 3 if sizes[2] else 2
+        torch.cuda.current_stream(packed.device).synchronize()
+        ptrs = [self._dev(qlocal[f], sizes[f]) for f in range(dim)] + ([C.c_void_p(0)] if dim == 2 else [])
+        _lib.check(self._L.b200ls_ghosted_from_packed_device(self._h, self._dev(packed, nv), ptrs[0], ptrs[1], ptrs[2]), self._h)
+        self._sync_stream(packed.device)
+        return qlocal
+
     def project(self, u, p, dp):
         """u <- u - (BN G) dp ; p <- p + dp, in place   (navierstokes.cpp:583-615)."""
         nv, npr = self.velocitySize()

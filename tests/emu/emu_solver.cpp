@@ -10,6 +10,7 @@
 #include "spmv2.cuh"
 #include "spmv3.cuh"
 #include "spmv4.cuh"
+#include "spmv5.cuh"
 #include "update_fly.cuh"
 #include "csr_kernels.cuh"
 #include "sep_kernels.cuh"
@@ -169,6 +170,19 @@ void spmv(const Problem &P, int tile, const VecSet &v, int kz, Ws &W, DevState *
     if constexpr (!APPLY)
     {
         const bool periodic = P.per[0] || P.per[1] || P.per[2];
+        if (tile >= 50 && tile < 60 && !periodic)
+        {
+            const GridDev &g = P.g;
+            auto run = [&](auto ty_c, auto kb_c) {
+                constexpr int TY = decltype(ty_c)::value, KB = decltype(kb_c)::value;
+                dim3 grid((unsigned)((g.nx + 63) / 64), (unsigned)((g.ny + TY - 1) / TY), (unsigned)((g.nzl + KB - 1) / KB));
+                emu::launch(grid, dim3(32, TY), 0, [&] { k_spmv5<TY, KB, 1, JAC>(g, v, W.ws, W.cm, st, kc, hist, 0); });
+            };
+            if (tile == 50) return run(std::integral_constant<int, 8>{}, std::integral_constant<int, 4>{});
+            if (tile == 51) return run(std::integral_constant<int, 8>{}, std::integral_constant<int, 8>{});
+            if (tile == 52) return run(std::integral_constant<int, 4>{}, std::integral_constant<int, 2>{});
+            return run(std::integral_constant<int, 8>{}, std::integral_constant<int, 16>{});
+        }
         if (tile >= 40 && tile < 50 && !periodic)
         {
             if (tile == 40) return launch_spmv4<8, 4, 2, JAC>(P, v, kz, W, st, kc, hist);
@@ -961,10 +975,19 @@ extern "C" EMU_API int emu_stag_ops(int mode, int dim, const int64_t *n, const i
     if (mode == 0) emu::launch(dim3(3), dim3(256), 0, [&] { k_divergence(s, in, io); });
     else if (mode == 1) emu::launch(dim3(3), dim3(256), 0, [&] { k_gradient<0>(s, in, io); });
     else if (mode == 2) emu::launch(dim3(3), dim3(256), 0, [&] { k_gradient<1>(s, in, io); });
-    else
+    else if (mode == 3)
     {
         emu::launch(dim3(3), dim3(256), 0, [&] { k_gradient<2>(s, in, io); });
         emu::launch(dim3(3), dim3(256), 0, [&] { k_axpy_one(np, io2, in); });
+    }
+    else
+    {
+        // mode 4: io = N(q), in = the three ghosted arrays back to back;  mode 5: io = ghosted arrays (back to back) from packed in
+        const long long zu = dim == 3 ? s.nz + 2 : 1, zw = dim == 3 ? s.nw + 2 : 0;
+        const long long su = (long long)(s.nu + 2) * (s.ny + 2) * zu, sv = (long long)(s.nx + 2) * (s.nv + 2) * zu;
+        (void)zw;
+        if (mode == 4) emu::launch(dim3(3), dim3(256), 0, [&] { k_convection(s, in, in + su, in + su + sv, io); });
+        else emu::launch(dim3(3), dim3(256), 0, [&] { k_ghosted_from_packed(s, in, io, io + su, io + su + sv); });
     }
     return 0;
 }

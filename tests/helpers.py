@@ -195,3 +195,24 @@ def ibpm_system(widths, dt=0.01, nb=24, radius=0.3, centre=None):
     nv = np.zeros(M.shape[0])
     nv[:pN] = 1.0 / np.sqrt(pN)
     return M, pN, nv
+
+
+def ghosted_fields(shape, periodic, seed=3):
+    """Random ghosted local arrays of the velocity fields (one ghost layer on every side; on periodic axes the ghost
+    layers hold the wrap values, as DMGlobalToLocal leaves them), the interior packed vector, and the field sizes."""
+    rng = np.random.default_rng(seed)
+    dim = len(shape)
+    nf = orc.field_sizes(shape, periodic)
+    q, packed = [], []
+    for f in range(dim):
+        a = rng.standard_normal(tuple(m + 2 for m in reversed(nf[f])))
+        for d in range(dim):
+            if periodic[d]:
+                ax = dim - 1 - d
+                lo = [slice(None)] * dim; hi = [slice(None)] * dim; first = [slice(None)] * dim; last = [slice(None)] * dim
+                lo[ax], hi[ax], first[ax], last[ax] = 0, -1, 1, -2
+                a[tuple(lo)] = a[tuple(last)]
+                a[tuple(hi)] = a[tuple(first)]
+        q.append(a)
+        packed.append(a[tuple([slice(1, -1)] * dim)].ravel())
+    return q, np.concatenate(packed), nf

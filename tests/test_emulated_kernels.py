@@ -20,7 +20,7 @@ LIB = os.path.join(EMU, "libb200emu.so")
 SRC = [os.path.join(EMU, f) for f in ("emu_solver.cpp", "cuda_emu.h")] + \
       [os.path.join(ROOT, "petibm_b200", "csrc", f) for f in ("kernels.cuh", "spmv2.cuh", "spmv3.cuh", "hw.cuh", "csr_kernels.cuh",
                                                             "sep_kernels.cuh", "mg_kernels.cuh", "mg_schedule.h",
-                                                            "ops_kernels.cuh", "update_fly.cuh", "dense_kernels.cuh", "spmv4.cuh")]
+                                                            "ops_kernels.cuh", "update_fly.cuh", "dense_kernels.cuh", "spmv4.cuh", "spmv5.cuh")]
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -114,7 +114,7 @@ def test_emulated_cg_matches_oracle(emu, tile, pc):
         np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-9 * np.abs(ref.x).max())
 
 
-@pytest.mark.parametrize("tile", [40, 41, 42, 43])
+@pytest.mark.parametrize("tile", [40, 41, 42, 43, 50, 51, 52, 53])
 @pytest.mark.parametrize("pc", ["none", "jacobi"])
 def test_emulated_tma_kernel_matches_oracle(emu, tile, pc):
     """k_spmv4 (TMA boxes with zero fill outside the grid, mbarrier full/empty pipeline, neighbours' p rebuilt from the
@@ -534,6 +534,39 @@ def test_emulated_divergence_gradient_projection_are_the_assembled_products(emu,
     A = H.oracle_matrix(widths, per)
     lhs = run(0, run(2, pr, np.empty(UN)), np.empty(pN))
     np.testing.assert_allclose(lhs, A.spmv(pr), rtol=0, atol=1e-12 * np.abs(lhs).max())
+
+
+@pytest.mark.parametrize("shape,per", [((9, 7), (0, 0)), ((8, 6), (1, 1)), ((7, 6, 5), (0, 0, 0)), ((6, 5, 7), (1, 0, 1)), ((70, 4, 3), (0, 1, 0))])
+def test_emulated_convection_is_the_reference_stencil(emu, shape, per):
+    """k_convection (ops_kernels.cuh) against the oracle's restatement of createconvection.cpp:39-332 on random ghosted
+    fields: bit-identical; k_ghosted_from_packed reproduces the interior and the periodic wrap layers."""
+    emu.emu_stag_ops.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int64), _ip, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp]
+    widths = H.make_widths(shape)
+    dim, n, p, w, dz = _grid_args(widths, per)
+    q, packed, nf = H.ghosted_fields(shape, per)
+    ref = np.concatenate([o.ravel() for o in orc.convection(widths, per, q)])
+    qin = np.ascontiguousarray(np.concatenate([a.ravel() for a in q]))
+    out = np.empty(ref.size)
+    emu.emu_stag_ops(4, dim, n, p, w[0].ctypes.data_as(_dp), w[1].ctypes.data_as(_dp), dz, 0.01, qin.ctypes.data_as(_dp),
+                     out.ctypes.data_as(_dp), None)
+    assert np.array_equal(out, ref)
+    # interior + periodic wrap layers from the packed vector; the other ghost layers keep what the caller put there
+    g = np.full(qin.size, -7.0)
+    emu.emu_stag_ops(5, dim, n, p, w[0].ctypes.data_as(_dp), w[1].ctypes.data_as(_dp), dz, 0.01,
+                     np.ascontiguousarray(packed).ctypes.data_as(_dp), g.ctypes.data_as(_dp), None)
+    off = 0
+    for f in range(dim):
+        a = g[off: off + q[f].size].reshape(q[f].shape)
+        off += q[f].size
+        filled = a != -7.0
+        assert np.array_equal(a[filled], q[f][filled])
+        inner = tuple([slice(1, -1)] * dim)
+        assert filled[inner].all()
+        for d in range(dim):                      # a face ghost layer is filled exactly when its axis is periodic
+            ax = dim - 1 - d
+            sl = [slice(1, -1)] * dim
+            sl[ax] = 0
+            assert filled[tuple(sl)].all() == bool(per[d]) and filled[tuple(sl)].any() == bool(per[d])
 
 
 @pytest.mark.parametrize("shape,per", [((24, 10, 9), (0, 0, 0)), ((67, 9, 6), (1, 1, 0)), ((16, 12, 10), (0, 0, 1)), ((33, 21), (1, 0))])

@@ -40,6 +40,47 @@ def test_operators_are_the_assembled_products(pb, shape, per):
     s.destroy()
 
 
+@pytest.mark.parametrize("shape,per", [((33, 20), (0, 0)), ((16, 12), (1, 1)), ((20, 14, 10), (0, 0, 0)), ((12, 9, 11), (1, 0, 1)),
+                                       ((70, 5, 4), (0, 1, 0))])
+def test_convection_is_the_reference_stencil(pb, shape, per):
+    """b200ls_convection (k_convection) against the oracle's restatement of createconvection.cpp:39-332: bit-identical,
+    host buffers and device-resident (ghosted arrays filled on the device from the packed vector + caller's ghost values)."""
+    import torch
+
+    widths = H.make_widths(shape)
+    s = pb.LinSolverB200("poisson", "None")
+    s.setStencil(H.grid_of(widths, per))
+    q, packed, nf = H.ghosted_fields(shape, per)
+    ref = np.concatenate([o.ravel() for o in orc.convection(widths, per, q)])
+    assert s.ghostedSizes()[: len(shape)] == [a.size for a in q]
+    assert np.array_equal(s.convection(q), ref)
+    dev = torch.device("cuda", 0)
+    qd = [torch.from_numpy(a.ravel().copy()).to(dev) for a in q]
+    assert np.array_equal(s.convection(qd).cpu().numpy(), ref)
+    # interior + periodic wrap layers refreshed on the device from a new packed vector, ghost values kept
+    rng = np.random.default_rng(8)
+    packed2 = rng.standard_normal(packed.size)
+    s.ghostedFromPacked(torch.from_numpy(packed2).to(dev), qd)
+    q2, off = [], 0
+    dim = len(shape)
+    for f in range(dim):
+        a = q[f].copy()
+        m = int(np.prod(nf[f]))
+        a[tuple([slice(1, -1)] * dim)] = packed2[off: off + m].reshape(tuple(reversed(nf[f])))
+        off += m
+        for d in range(dim):
+            if per[d]:
+                ax = dim - 1 - d
+                lo = [slice(None)] * dim; hi = [slice(None)] * dim; first = [slice(None)] * dim; last = [slice(None)] * dim
+                lo[ax], hi[ax], first[ax], last[ax] = 0, -1, 1, -2
+                a[tuple(lo)] = a[tuple(last)]
+                a[tuple(hi)] = a[tuple(first)]
+        q2.append(a)
+    ref2 = np.concatenate([o.ravel() for o in orc.convection(widths, per, q2)])
+    assert np.array_equal(s.convection(qd).cpu().numpy(), ref2)
+    s.destroy()
+
+
 def test_device_resident_projection_step(pb):
     """One fractional-step projection with everything on the device: rhs2 = D u*, CG for dP, u = u* - BNG dP.  The
     projected field is divergence-free to the tolerance of the solve."""
