@@ -944,6 +944,17 @@ struct UpdItem
     }
 };
 
+// Item order with neighbour GPUs: the two boundary planes FIRST (their values leave over NVLink while the interior is
+// still streaming, so the system-scope fence before the ticket finds those stores long performed), then the interior
+// planes bottom-up or top-down.
+__device__ __forceinline__ unsigned int push_order(unsigned int j, unsigned int plane2, unsigned int nb2, unsigned int last0, bool rev)
+{
+    if (j < plane2) return j;                       // bottom plane
+    if (j < nb2) return last0 + (j - plane2);       // top plane
+    const unsigned int jj = j - nb2;                // interior planes 1 .. nzl-2
+    return rev ? last0 - 1u - jj : plane2 + jj;
+}
+
 template <bool JACOBI, bool INIT, bool PADDED, bool PUSH, int U>
 __global__ void __launch_bounds__(256) k_update2(GridDev g, UpdVecs v, int fin_kind, ReduceWs ws, CommDev cm,
                                                  DevState *st, SolveConsts kc, double *hist)
@@ -968,6 +979,7 @@ __global__ void __launch_bounds__(256) k_update2(GridDev g, UpdVecs v, int fin_k
     unsigned int i0 = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int top = n2 - 1u;
     const bool rev = v.reverse != 0;
+    const unsigned int nb2 = g.nzl >= 2 ? 2u * plane2 : plane2;  // items of the boundary planes (PUSH: processed first)
     // main loop: all U items in range (n2 - i0 > (U-1)*stride, written without overflow)
     while (i0 < n2 && n2 - i0 > (unsigned int)(U - 1) * stride)
     {
@@ -977,7 +989,7 @@ __global__ void __launch_bounds__(256) k_update2(GridDev g, UpdVecs v, int fin_k
         for (int u = 0; u < U; ++u)
         {
             const unsigned int j = i0 + u * stride;
-            idx[u] = rev ? top - j : j;
+            idx[u] = PUSH ? push_order(j, plane2, nb2, last0, rev) : (rev ? top - j : j);
             rr[u] = r2[idx[u]];
             if (!INIT) wr[u] = w2[idx[u]];
             if (JACOBI) dr[u] = d2[idx[u]];
@@ -995,7 +1007,7 @@ __global__ void __launch_bounds__(256) k_update2(GridDev g, UpdVecs v, int fin_k
     }
     for (; i0 < n2; i0 = (n2 - i0 > stride) ? i0 + stride : n2)
     {
-        const unsigned int i = rev ? top - i0 : i0;
+        const unsigned int i = PUSH ? push_order(i0, plane2, nb2, last0, rev) : (rev ? top - i0 : i0);
         double2 rr = r2[i], wr = make_double2(0, 0), dr = make_double2(0, 0);
         if (!INIT) wr = w2[i];
         if (JACOBI) dr = d2[i];

@@ -102,6 +102,58 @@ def velocity_system(widths, periodic, dt=0.01, nu=0.01, c=0.5, vmin=0.0):
     return A, L
 
 
+def velocity_system_fast(widths, periodic, dt=0.01, nu=0.01, c=0.5, vmin=0.0):
+    """velocity_system vectorised with numpy (same entries bit for bit, checked on small grids by
+    tests/test_velocity_operator.py); for the sizes of scripts/velocity_bench.py.  Periodic axes need >= 3 cells."""
+    import scipy.sparse as sp
+
+    dim = len(widths)
+    per = list(periodic) + [0] * (3 - dim)
+    ext = [float(np.sum(w)) for w in widths]
+    ax = [[orc.velocity_axis(widths[d], vmin, vmin + ext[d], same_dir=(f == d), periodic=bool(per[d])) for d in range(dim)]
+          for f in range(dim)]
+    nn = [[ax[f][d][0] for d in range(dim)] + [1] * (3 - dim) for f in range(dim)]
+    off = np.concatenate([[0], np.cumsum([int(np.prod(nn[f])) for f in range(dim)])])
+    R, Cc, V = [], [], []
+    for f in range(dim):
+        n0, n1, n2 = nn[f]
+        idx = np.meshgrid(np.arange(n0), np.arange(n1), np.arange(n2), indexing="ij")   # [d][i, j, k]
+        row = off[f] + idx[0] + n0 * (idx[1] + n1 * idx[2])
+        vm, vp = [], []
+        for d in range(dim):
+            _, dL, co = ax[f][d]
+            s = np.arange(nn[f][d])
+            dls = dL[s + 1]
+            vm.append(1.0 / ((co[s + 1] - co[s]) * dls))
+            vp.append(1.0 / ((co[s + 2] - co[s + 1]) * dls))
+        acc = np.zeros(row.shape)
+        for d in range(dim):
+            acc = acc + vm[d][idx[d]]
+            acc = acc + vp[d][idx[d]]
+        diag = -acc
+        for d in range(dim):
+            nd = nn[f][d]
+            for side, coef1 in ((-1, vm[d]), (+1, vp[d])):
+                coef = coef1[idx[d]]
+                nb = idx[d] + side
+                inside = (nb >= 0) & (nb < nd)
+                if per[d]:
+                    assert nd >= 3
+                    nb = nb % nd
+                    inside = np.ones_like(inside)
+                else:
+                    a0 = 0.0 if d == f else -1.0
+                    diag = np.where(inside, diag, diag + coef * a0)
+                nbi = [idx[0], idx[1], idx[2]]
+                nbi[d] = nb
+                col = off[f] + nbi[0] + n0 * (nbi[1] + n1 * nbi[2])
+                R.append(row[inside]); Cc.append(col[inside]); V.append((-(c * nu)) * coef[inside])
+        R.append(row.ravel()); Cc.append(row.ravel()); V.append(((-(c * nu)) * diag + 1.0 / dt).ravel())
+    A = sp.csr_matrix((np.concatenate(V), (np.concatenate(R), np.concatenate(Cc))), shape=(off[-1], off[-1]))
+    A.sort_indices()
+    return A
+
+
 def box_local_system(A, b, dim, n, procs, rank):
     """What one MPI rank of PetIBM holds when the DMDA uses the process grid `procs` (cartesianmesh.cpp:500-538,
     709-721): the rows of its box in PETSc ordering with PETSc global column indices, and its part of b.

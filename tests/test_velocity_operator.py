@@ -30,6 +30,15 @@ def test_velocity_operator_structure():
     assert Ap.shape[0] == 9 * 8 + 9 * 7
 
 
+@pytest.mark.parametrize("shape,per", [((10, 9, 8), (0, 0, 0)), ((7, 6, 5), (1, 0, 1)), ((9, 8), (0, 1))])
+def test_vectorised_assembly_is_the_same_matrix(shape, per):
+    widths = H.make_widths(shape)
+    A, _ = H.velocity_system(widths, per, dt=0.02, nu=0.03, c=0.5)
+    B = H.velocity_system_fast(widths, per, dt=0.02, nu=0.03, c=0.5)
+    assert A.shape == B.shape and np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
+    assert np.array_equal(A.data, B.data)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("dt,nu", [(0.01, 0.01), (0.5, 1.0)])
 def test_velocity_system_bcgs_jacobi(tmp_path, dt, nu):
