@@ -450,6 +450,15 @@ inline K1Cfg k1_config(const b200ls_solver *h)
         tiles[0] = h->tile;
         ntiles = 1;
     }
+    else if (h->tile < 0 && !(h->per[0] || h->per[1] || h->per[2]) &&
+             40.0 * (double)(nzl + 2) * (double)h->g.plane <= 110.0e6)
+    {
+        // the five solver vectors fit the 126 MB L2 (8-GPU slabs of 256^3, 128^3 on one GPU): the TMA kernel with 64 x 4
+        // tiles wins there (18.4 us against 24.1 us per launch on a 256 x 256 x 32 slab, profiles/r02_trace_2gpu_slab.log);
+        // out of HBM the two kernels are level and the cp.async kernel keeps its tuned launch shape
+        tiles[0] = 41;
+        ntiles = 1;
+    }
     K1Cfg best{tiles[0], std::max(1, std::min(nzl, 512))};
     double best_score = -1.0;
     for (int q = 0; q < ntiles; ++q)
@@ -908,6 +917,8 @@ void build_commdev(b200ls_solver *h)
     cm.rank = h->rank;
     cm.nranks = h->nranks;
     cm.mode = 0;
+    cm.push_items = getenv("B200LS_PUSH_ITEMS") ? atoi(getenv("B200LS_PUSH_ITEMS")) : 0;
+    cm.dbg_flags = getenv("B200LS_DBG_FLAGS") ? atoi(getenv("B200LS_DBG_FLAGS")) : 0;
     cm.sendbuf = h->d_sendrecv;
     if (h->nranks > 1) cm.mode = (h->reduce_mode == B200LS_REDUCE_NCCL) ? 2 : 1;
 }
@@ -1786,8 +1797,8 @@ int b200ls_set_nullspace(b200ls_solver *h, int has_const, int nvecs, const doubl
     if (nvecs < 0 || (nvecs > 0 && !vecs)) return B200LS_ERR_ARG;
     cudaSetDevice(h->device);
     if (h->op == OP_STENCIL && nvecs > 0) return fail(h, B200LS_ERR_UNSUPPORTED, "explicit null-space vectors need the CSR operator");
+    if (h->op == OP_CSR || h->op == OP_SEP) TRY(csr_set_nullvecs(h, has_const ? 1 : 0, nvecs, vecs));  // validates before anything changes
     h->has_const = has_const ? 1 : 0;
-    if (h->op == OP_CSR || h->op == OP_SEP) TRY(csr_set_nullvecs(h, nvecs, vecs));
     invalidate_graph(h);
     return B200LS_OK;
 }

@@ -81,6 +81,8 @@ struct CommDev
     double *sendbuf;             // NCCL mode: local sums
     double *r_ghost_dn;          // neighbour below: address of ITS top ghost plane of r (or null)
     double *r_ghost_up;          // neighbour above: address of ITS bottom ghost plane of r (or null)
+    int push_items;              // items per pusher thread of k_update2 (0 = 2); experiment knob B200LS_PUSH_ITEMS
+    int dbg_flags;               // bit 0: skip the system-scope fence of the pushers (TIMING EXPERIMENTS ONLY: unsafe)
 };
 
 
@@ -944,15 +946,18 @@ struct UpdItem
     }
 };
 
-// Item order with neighbour GPUs: the two boundary planes FIRST (their values leave over NVLink while the interior is
-// still streaming, so the system-scope fence before the ticket finds those stores long performed), then the interior
-// planes bottom-up or top-down.
-__device__ __forceinline__ unsigned int push_order(unsigned int j, unsigned int plane2, unsigned int nb2, unsigned int last0, bool rev)
+// With neighbour GPUs (PUSH) the CTAs split into two roles.  The first `npush` CTAs own the two boundary planes: their new
+// r values also go into the neighbours' ghost planes (peer stores over NVLink), and only these CTAs pay the system-scope
+// fence before their ticket.  All other CTAs stream the interior planes exactly like the single-GPU kernel.  (Letting
+// every CTA touch the boundary planes -- first or last -- put slow remote stores and a system fence on the path of all
+// of them: 24.6 us against 9.1 us for the same slab on one GPU, profiles/r02_trace_2gpu_slab.log.)
+__device__ __forceinline__ unsigned int update_pushers(unsigned int nb2, unsigned int nblocks, int items)
 {
-    if (j < plane2) return j;                       // bottom plane
-    if (j < nb2) return last0 + (j - plane2);       // top plane
-    const unsigned int jj = j - nb2;                // interior planes 1 .. nzl-2
-    return rev ? last0 - 1u - jj : plane2 + jj;
+    const unsigned int per = 256u * (unsigned int)(items > 0 ? items : 2);  // 2 double2 items per pusher thread (8: +2.6 us, 32: +5 us; profiles/r02_trace_2gpu_slab.log)
+    unsigned int np = (nb2 + per - 1u) / per;
+    const unsigned int cap = nblocks > 4u ? nblocks / 2u : 1u;
+    if (np > cap) np = cap;
+    return np < 1u ? 1u : np;
 }
 
 template <bool JACOBI, bool INIT, bool PADDED, bool PUSH, int U>
@@ -972,48 +977,82 @@ __global__ void __launch_bounds__(256) k_update2(GridDev g, UpdVecs v, int fin_k
     const double2 *const __restrict__ d2 = reinterpret_cast<const double2 *>(v.dinv + (JACOBI ? g.plane : 0));
     double2 *const gdn = reinterpret_cast<double2 *>(cm.r_ghost_dn);
     double2 *const gup = reinterpret_cast<double2 *>(cm.r_ghost_up);
-    const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int pxh = (unsigned int)g.px >> 1;
     const unsigned int nx = (unsigned int)g.nx;
     double acc[6] = {0, 0, 0, 0, 0, 0};
-    unsigned int i0 = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned int top = n2 - 1u;
     const bool rev = v.reverse != 0;
-    const unsigned int nb2 = g.nzl >= 2 ? 2u * plane2 : plane2;  // items of the boundary planes (PUSH: processed first)
-    // main loop: all U items in range (n2 - i0 > (U-1)*stride, written without overflow)
-    while (i0 < n2 && n2 - i0 > (unsigned int)(U - 1) * stride)
+    // the range of items a CTA role covers: [lo, lo + span), walked by `nb` CTAs of that role.  Single GPU: one role, all
+    // items.  PUSH: role 0 = the boundary planes (pusher CTAs), role 1 = the interior planes (all other CTAs; the pushers
+    // themselves when the grid has no other CTA).
+    bool pusher = false;
+    unsigned int npush = 0;
+    if (PUSH)
     {
-        double2 rr[U], wr[U], dr[U];
-        unsigned int idx[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-        {
-            const unsigned int j = i0 + u * stride;
-            idx[u] = PUSH ? push_order(j, plane2, nb2, last0, rev) : (rev ? top - j : j);
-            rr[u] = r2[idx[u]];
-            if (!INIT) wr[u] = w2[idx[u]];
-            if (JACOBI) dr[u] = d2[idx[u]];
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            UpdItem<JACOBI, INIT, PADDED, PUSH>::run(idx[u], rr[u], wr[u], dr[u], ma, c, r2, gdn, gup, plane2, last0, pxh, nx,
-                                                     acc);
-        if (n2 - i0 <= (unsigned int)U * stride)
-        {
-            i0 = n2;
-            break;
-        }
-        i0 += U * stride;
+        const unsigned int nb2 = g.nzl >= 2 ? 2u * plane2 : plane2;  // items of the boundary planes
+        npush = update_pushers(nb2, gridDim.x, cm.push_items);
+        pusher = blockIdx.x < npush;
     }
-    for (; i0 < n2; i0 = (n2 - i0 > stride) ? i0 + stride : n2)
+    const bool no_interior_ctas = PUSH && npush >= gridDim.x;
+    for (int role = (PUSH && !pusher) ? 1 : 0; role < ((PUSH && (no_interior_ctas || !pusher)) ? 2 : 1); ++role)
     {
-        const unsigned int i = PUSH ? push_order(i0, plane2, nb2, last0, rev) : (rev ? top - i0 : i0);
-        double2 rr = r2[i], wr = make_double2(0, 0), dr = make_double2(0, 0);
-        if (!INIT) wr = w2[i];
-        if (JACOBI) dr = d2[i];
-        UpdItem<JACOBI, INIT, PADDED, PUSH>::run(i, rr, wr, dr, ma, c, r2, gdn, gup, plane2, last0, pxh, nx, acc);
+        unsigned int lo = 0, span = n2, nb = gridDim.x, bid = blockIdx.x;
+        const bool boundary = PUSH && role == 0;
+        if (PUSH)
+        {
+            if (boundary)
+            {
+                // boundary planes as one virtual range [0, nb2): the bottom plane, then the top plane (mapped below)
+                span = g.nzl >= 2 ? 2u * plane2 : plane2;
+                nb = npush;
+            }
+            else
+            {
+                lo = plane2;
+                span = g.nzl > 2 ? last0 - plane2 : 0u;
+                nb = no_interior_ctas ? gridDim.x : gridDim.x - npush;
+                bid = no_interior_ctas ? blockIdx.x : blockIdx.x - npush;
+            }
+        }
+        const unsigned int stride = nb * blockDim.x;
+        unsigned int i0 = bid * blockDim.x + threadIdx.x;
+        const unsigned int n2r = span;  // items of this role
+        // main loop: all U items in range (n2r - i0 > (U-1)*stride, written without overflow)
+        while (i0 < n2r && n2r - i0 > (unsigned int)(U - 1) * stride)
+        {
+            double2 rr[U], wr[U], dr[U];
+            unsigned int idx[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+            {
+                const unsigned int j = i0 + u * stride;
+                idx[u] = lo + (rev ? span - 1u - j : j);
+                if (boundary && idx[u] >= plane2) idx[u] = last0 + (idx[u] - plane2);  // second half: the top plane
+                rr[u] = r2[idx[u]];
+                if (!INIT) wr[u] = w2[idx[u]];
+                if (JACOBI) dr[u] = d2[idx[u]];
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                UpdItem<JACOBI, INIT, PADDED, PUSH>::run(idx[u], rr[u], wr[u], dr[u], ma, c, r2, gdn, gup, plane2, last0, pxh, nx,
+                                                         acc);
+            if (n2r - i0 <= (unsigned int)U * stride)
+            {
+                i0 = n2r;
+                break;
+            }
+            i0 += U * stride;
+        }
+        for (; i0 < n2r; i0 = (n2r - i0 > stride) ? i0 + stride : n2r)
+        {
+            unsigned int i = lo + (rev ? span - 1u - i0 : i0);
+            if (boundary && i >= plane2) i = last0 + (i - plane2);  // second half of the boundary range: the top plane
+            double2 rr = r2[i], wr = make_double2(0, 0), dr = make_double2(0, 0);
+            if (!INIT) wr = w2[i];
+            if (JACOBI) dr = d2[i];
+            UpdItem<JACOBI, INIT, PADDED, PUSH>::run(i, rr, wr, dr, ma, c, r2, gdn, gup, plane2, last0, pxh, nx, acc);
+        }
     }
-    grid_reduce_finalize<6>(acc, fin_kind, ws, cm, st, kc, hist, PUSH);
+    grid_reduce_finalize<6>(acc, fin_kind, ws, cm, st, kc, hist, PUSH && pusher && !(cm.dbg_flags & 1));
 }
 
 // ------------------------------------------------------------------------------------------

@@ -287,10 +287,12 @@ class LinSolverB200(LinSolverBase):
         return False
 
     def _try_staggered(self, A: Mat) -> bool:
-        if self._try_hybrid(A):
-            return True
+        """Same order as LinSolverB200::setMatrix in the PetIBM shim (linsolverb200.cpp): the packed velocity layout,
+        then the hybrid form (pressure operator of the mesh + coupling rows), then the single-field line-coefficient
+        form with a remainder -- a matrix that fits more than one form is the same operator kind in both front ends."""
         layouts, per = self._staggered_layouts(A.nrows)
-        for dims in layouts:
+
+        def staggered(dims):
             d = np.ascontiguousarray(dims, dtype=np.int64).reshape(-1)
             rc = self._L.b200ls_set_staggered(self._h, len(dims), d.ctypes.data_as(_lib._i64p), (C.c_int * 3)(*per), A.nrows,
                                               A.indptr.ctypes.data_as(_lib._i64p), A.indices.ctypes.data_as(_lib._i32p),
@@ -301,6 +303,16 @@ class LinSolverB200(LinSolverBase):
                 return True
             if rc != _lib.ERR_MISMATCH:
                 _lib.check(rc, self._h)
+            return False
+
+        for dims in layouts:
+            if len(dims) > 1 and staggered(dims):       # packed [u | v | w]
+                return True
+        if self._try_hybrid(A):
+            return True
+        for dims in layouts:
+            if len(dims) == 1 and staggered(dims):      # pressure block + remainder
+                return True
         return False
 
     def setMatrix(self, A: Mat):

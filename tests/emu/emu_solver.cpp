@@ -389,7 +389,7 @@ EMU_API int emu_stencil_cg_ranks(int nranks, const int64_t *n, const int *per, c
         {
             UpdVecs uv{k.r.data(), k.w.data(), jacobi ? k.dinv.data() : nullptr, 1};
             const GridDev &g = k.P.g;
-#define EMU_UPD(JAC, INIT, PAD) emu::launch(dim3(3), dim3(256), 0, [&] { k_update2<JAC, INIT, PAD, true, 4>(g, uv, kind, k.W.ws, k.W.cm, &k.st, kc, k.hist.data()); })
+#define EMU_UPD(JAC, INIT, PAD) emu::launch(dim3(getenv("EMU_UPD_BLOCKS") ? atoi(getenv("EMU_UPD_BLOCKS")) : 3), dim3(256), 0, [&] { k_update2<JAC, INIT, PAD, true, 4>(g, uv, kind, k.W.ws, k.W.cm, &k.st, kc, k.hist.data()); })
             const bool pad = g.px != g.nx;
             if (jacobi) { if (init) { if (pad) EMU_UPD(true, true, true); else EMU_UPD(true, true, false); } else { if (pad) EMU_UPD(true, false, true); else EMU_UPD(true, false, false); } }
             else { if (init) { if (pad) EMU_UPD(false, true, true); else EMU_UPD(false, true, false); } else { if (pad) EMU_UPD(false, false, true); else EMU_UPD(false, false, false); } }

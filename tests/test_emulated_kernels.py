@@ -239,10 +239,12 @@ def test_results_do_not_depend_on_the_thread_schedule(emu, tile):
         emu.emu_set_schedule(0)
 
 
-@pytest.mark.parametrize("nranks", [2, 3])
-def test_emulated_2d_grid_on_several_ranks(emu, nranks):
+@pytest.mark.parametrize("nranks,upd_blocks", [(2, 3), (3, 3), (2, 1), (2, 8)])
+def test_emulated_2d_grid_on_several_ranks(emu, nranks, upd_blocks, monkeypatch):
     """A 2-D grid on several GPUs is the 3-D code on (nx, 1, ny) with y-slabs (b200ls_set_poisson_stencil); the result
-    must match the 2-D oracle operator (bit-identical arithmetic: products with 1.0, additions of exact zeros)."""
+    must match the 2-D oracle operator (bit-identical arithmetic: products with 1.0, additions of exact zeros).
+    upd_blocks: grid of the update kernel -- one CTA (the pusher also owns the interior), few, several pushers."""
+    monkeypatch.setenv("EMU_UPD_BLOCKS", str(upd_blocks))
     for shape, per in (((33, 14), (0, 0)), ((20, 12), (1, 1))):
         widths = H.make_widths(shape)
         A = H.oracle_matrix(widths, per)                      # the 2-D reference operator
