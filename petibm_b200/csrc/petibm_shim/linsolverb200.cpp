@@ -96,7 +96,29 @@ PetscErrorCode LinSolverB200::init()
                      "B200 linear solver \"%s\": %s", name.c_str(), err);
     }
     B200CHK(handle, b200ls_set_options(handle, &opts));
+    savedOpts = opts;
     if (nranks > 1) B200CHK(handle, b200ls_comm_init(handle, rank, nranks, B200LS_REDUCE_P2P, B200LS_HALO_STORE));
+    PetscFunctionReturn(0);
+}
+
+// A fresh handle with the options of init(): single-rank (a replica of a general system) or wired to the communicator
+// again.  Collective: every rank first drops its mappings of the peers' exchange arenas.
+PetscErrorCode LinSolverB200::newHandle(bool withComm)
+{
+    PetscErrorCode ierr;
+    PetscFunctionBeginUser;
+    B200CHK(handle, b200ls_comm_disconnect(handle));
+    ierr = MPI_Barrier(PETSC_COMM_WORLD); CHKERRQ(ierr);
+    b200ls_destroy(handle);
+    handle = nullptr;
+    int ndev = 0;
+    if (b200ls_device_count(&ndev) != B200LS_OK || ndev <= 0)
+        SETERRQ(PETSC_COMM_WORLD, PETSC_ERR_SUP, "B200 linear solver: no CUDA device (there is no CPU fallback).");
+    const int rc = b200ls_create(&handle, rank % ndev);
+    if (rc != B200LS_OK)
+        SETERRQ1(PETSC_COMM_WORLD, PETSC_ERR_LIB, "B200 linear solver: b200ls_create failed: %s", b200ls_error_string(rc));
+    B200CHK(handle, b200ls_set_options(handle, &savedOpts));
+    if (withComm && nranks > 1) B200CHK(handle, b200ls_comm_init(handle, rank, nranks, B200LS_REDUCE_P2P, B200LS_HALO_STORE));
     PetscFunctionReturn(0);
 }
 
@@ -153,6 +175,12 @@ PetscErrorCode LinSolverB200::setMatrix(const Mat &A)
     bool recognised = false;
     if (plan) b200ls_repart_destroy(plan);
     plan = nullptr;
+    if (replicated)
+    {
+        // the previous matrix was solved as replicas on a single-rank handle: back to a distributed one
+        ierr = newHandle(true); CHKERRQ(ierr);
+        replicated = false;
+    }
     if (haveGrid && nranks == 1)
     {
         const int64_t nslow = (gdim == 3) ? gn[2] : 1;   // one GPU owns the whole grid (2-D: a single "plane")
@@ -254,16 +282,58 @@ PetscErrorCode LinSolverB200::setMatrix(const Mat &A)
     }
     else
     {
+        int64_t nlocRows = (int64_t)nloc;
         if (nranks > 1)
-            SETERRQ1(PETSC_COMM_WORLD, PETSC_ERR_SUP,
-                     "B200 linear solver \"%s\": the matrix is not the separable pressure stencil of the mesh and the "
-                     "assembled-operator paths run on one GPU only.", name.c_str());
+        {
+            // Any other system on several ranks (LinSolverKSP solves the velocity, modified-Poisson and forces systems on
+            // any rank count, linsolverksp.cpp:72-105): gather the rows (global column indices, so the rank-ordered
+            // concatenation IS the global matrix in PETSc ordering) and solve a replica on every GPU.
+            std::vector<PetscMPIInt> nnzCounts((size_t)nranks), nnzDispls((size_t)nranks);
+            repCounts.assign((size_t)nranks, 0);
+            repDispls.assign((size_t)nranks, 0);
+            const long long mine[2] = {(long long)nloc, (long long)col.size()};
+            std::vector<long long> all((size_t)2 * nranks);
+            ierr = MPI_Allgather(mine, 2 * (int)sizeof(long long), MPI_BYTE, all.data(), 2 * (int)sizeof(long long), MPI_BYTE,
+                                 PETSC_COMM_WORLD); CHKERRQ(ierr);
+            long long rowsTotal = 0, nnzTotal = 0;
+            for (int r = 0; r < nranks; ++r)
+            {
+                if (all[2 * r] > 2147483647LL || all[2 * r + 1] > 2147483647LL || nnzTotal + all[2 * r + 1] > 2147483647LL)
+                    SETERRQ(PETSC_COMM_WORLD, PETSC_ERR_SUP, "B200 linear solver: replicated system exceeds the MPI count range.");
+                repCounts[(size_t)r] = (PetscMPIInt)all[2 * r];
+                repDispls[(size_t)r] = (PetscMPIInt)rowsTotal;
+                nnzCounts[(size_t)r] = (PetscMPIInt)all[2 * r + 1];
+                nnzDispls[(size_t)r] = (PetscMPIInt)nnzTotal;
+                rowsTotal += all[2 * r];
+                nnzTotal += all[2 * r + 1];
+            }
+            std::vector<int32_t> gcol((size_t)nnzTotal);
+            std::vector<double> gval((size_t)nnzTotal);
+            std::vector<long long> rowLen((size_t)nloc), gLen((size_t)rowsTotal);
+            for (PetscInt r = 0; r < nloc; ++r) rowLen[(size_t)r] = rowptr[(size_t)r + 1] - rowptr[(size_t)r];
+            ierr = MPI_Allgatherv(col.data(), (PetscMPIInt)col.size(), MPI_INT, gcol.data(), nnzCounts.data(), nnzDispls.data(),
+                                  MPI_INT, PETSC_COMM_WORLD); CHKERRQ(ierr);
+            ierr = MPI_Allgatherv(val.data(), (PetscMPIInt)val.size(), MPI_DOUBLE, gval.data(), nnzCounts.data(),
+                                  nnzDispls.data(), MPI_DOUBLE, PETSC_COMM_WORLD); CHKERRQ(ierr);
+            ierr = MPI_Allgatherv(rowLen.data(), (PetscMPIInt)nloc, MPI_LONG_LONG, gLen.data(), repCounts.data(),
+                                  repDispls.data(), MPI_LONG_LONG, PETSC_COMM_WORLD); CHKERRQ(ierr);
+            rowptr.assign((size_t)rowsTotal + 1, 0);
+            for (long long r = 0; r < rowsTotal; ++r) rowptr[(size_t)r + 1] = rowptr[(size_t)r] + gLen[(size_t)r];
+            col.swap(gcol);
+            val.swap(gval);
+            nlocRows = rowsTotal;
+            ierr = newHandle(false); CHKERRQ(ierr);
+            replicated = true;
+            repB.assign((size_t)rowsTotal, 0.0);
+            repX.assign((size_t)rowsTotal, 0.0);
+        }
+        const int64_t nloc = nlocRows;  // from here on: the rows this handle holds (all of them for a replica)
         // 2. a staggered-grid matrix with one-dimensional coefficients: the packed velocity system [u | v | w]
         //    (cartesianmesh.cpp:251-273: one point fewer than cells along the field's own direction unless periodic)
         //    or the pressure block followed by IBPM's Lagrangian force rows (ibpm.cpp:164-194).  The structure is read
         //    out of A and verified against every entry by b200ls_set_staggered.
         bool staggered = false, hybrid = false;
-        if (haveGrid)
+        if (haveGrid && !replicated)
         {
             const int64_t n3[3] = {gn[0], gn[1], gdim == 3 ? gn[2] : 1};
             int64_t vel[9], velTotal = 0;
@@ -319,7 +389,15 @@ PetscErrorCode LinSolverB200::setMatrix(const Mat &A)
         {
             const PetscScalar *arr;
             ierr = VecGetArrayRead(vecs[q], &arr); CHKERRQ(ierr);
-            flat.insert(flat.end(), arr, arr + nloc);
+            if (replicated)
+            {
+                const size_t at = flat.size();
+                flat.resize(at + repB.size());
+                ierr = MPI_Allgatherv(arr, (PetscMPIInt)nloc, MPI_DOUBLE, flat.data() + at, repCounts.data(), repDispls.data(),
+                                      MPI_DOUBLE, PETSC_COMM_WORLD); CHKERRQ(ierr);
+            }
+            else
+                flat.insert(flat.end(), arr, arr + nloc);
             ierr = VecRestoreArrayRead(vecs[q], &arr); CHKERRQ(ierr);
         }
         B200CHK(handle, b200ls_set_nullspace(handle, hasConst ? 1 : 0, (int)nv, nv ? flat.data() : nullptr));
@@ -340,7 +418,16 @@ PetscErrorCode LinSolverB200::solve(Vec &x, Vec &b)
     ierr = VecGetArrayRead(b, &barr); CHKERRQ(ierr);
     ierr = VecGetArray(x, &xarr); CHKERRQ(ierr);
     int rc;
-    if (plan && !planIdentity)
+    if (replicated)
+    {
+        // every rank solves the whole system on its GPU: all-gather b, keep the own rows of x
+        ierr = MPI_Allgatherv(barr, repCounts[(size_t)rank], MPI_DOUBLE, repB.data(), repCounts.data(), repDispls.data(),
+                              MPI_DOUBLE, PETSC_COMM_WORLD); CHKERRQ(ierr);
+        rc = b200ls_solve(handle, repB.data(), repX.data());
+        if (rc == B200LS_OK || rc == B200LS_ERR_DIVERGED)
+            std::memcpy(xarr, repX.data() + repDispls[(size_t)rank], sizeof(double) * (size_t)repCounts[(size_t)rank]);
+    }
+    else if (plan && !planIdentity)
     {
         // DMDA boxes -> slabs, solve, slabs -> boxes: one MPI_Alltoallv per direction (what VecScatter does inside
         // PETSc's MatMult); the box side needs no packing (b200ls.h, b200ls_repart_*)

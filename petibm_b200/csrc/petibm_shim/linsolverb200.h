@@ -72,6 +72,14 @@ protected:
     bool planIdentity = true;               // 1 x 1 x P process grid: the boxes are the slabs
     std::vector<PetscMPIInt> xcounts[4];    // box counts / displs, slab counts / displs (MPI_Alltoallv)
     std::vector<double> xbuf, bslab, xslab; // slab-side exchange buffer and slab-ordered b / x
+    // several ranks and a matrix that is not the pressure stencil (velocity system, IBPM's modified Poisson system,
+    // forces system): every rank holds a replica of the whole system on its GPU (single-rank handle); solve()
+    // all-gathers b and keeps the caller's rows of x
+    bool replicated = false;
+    std::vector<PetscMPIInt> repCounts, repDispls;  // rows per rank / first row of every rank (MPI_Allgatherv)
+    std::vector<double> repB, repX;
+    b200ls_options savedOpts;                        // to re-create the handle (replica <-> distributed)
+    PetscErrorCode newHandle(bool withComm);
 };  // LinSolverB200
 
 }  // end of namespace linsolver

@@ -82,6 +82,24 @@ class Comm:
             return float(value)
         return max(float(v) for v in self.allgather_bytes(float(value)))
 
+    def gather_matrix(self, nrows, indptr, indices, data, has_const=False, null_vecs=None):
+        """All-gathers a row-distributed CSR matrix (global column indices) and its explicit null-space vectors: every
+        rank receives the whole system -- the replicated solve of general systems on several ranks (LinSolverB200).
+        Returns (indptr, indices, data, row offsets of the ranks, has_const, null_vecs)."""
+        parts = self.allgather_bytes((int(nrows), np.asarray(indptr), np.asarray(indices), np.asarray(data), bool(has_const),
+                                      None if null_vecs is None else np.asarray(null_vecs)))
+        offs = np.concatenate([[0], np.cumsum([p[0] for p in parts])]).astype(np.int64)
+        ips, base = [np.zeros(1, dtype=np.int64)], 0
+        for p in parts:
+            ip = np.asarray(p[1], dtype=np.int64)
+            ips.append(ip[1:] + base)
+            base += int(ip[-1])
+        nv = None
+        if parts[0][5] is not None:
+            nv = np.ascontiguousarray(np.concatenate([np.atleast_2d(p[5]) for p in parts], axis=1), dtype=np.float64)
+        return (np.concatenate(ips), np.concatenate([np.asarray(p[2], dtype=np.int32) for p in parts]),
+                np.concatenate([np.asarray(p[3], dtype=np.float64) for p in parts]), offs, parts[0][4], nv)
+
     # ---- solver plumbing -----------------------------------------------------------------
     def init_solver(self, solver):
         _lib.check(solver._L.b200ls_comm_init(solver._h, self.rank, self.nranks, REDUCE[self.reduce], HALO[self.halo]),

@@ -108,6 +108,7 @@ class LinSolverB200(LinSolverBase):
         self._procs = None     # DMDA process grid, if the caller knows it (setProcessGrid)
         self._repart = None    # box <-> slab exchange plan when the vectors arrive as DMDA boxes
         self._staggered = True # setMatrix may use the line-coefficient form for velocity / IBPM matrices
+        self._replicated = None  # (row_lo, row_hi, nrows_global) when several ranks solve replicas of a general system
         self.operator = None   # "stencil" | "hybrid" | "staggered" | "csr" after setMatrix
         if device is None:
             device = comm.device if comm is not None else 0
@@ -315,6 +316,32 @@ class LinSolverB200(LinSolverBase):
                 return True
         return False
 
+    def _replicate(self, A: Mat) -> Mat:
+        """Collective: all-gathers the rows (PETSc global column indices) and the explicit null-space vectors over the
+        host transport, turns this solver into a single-GPU replica (fresh handle, same options) and returns the
+        global matrix.  solve() all-gathers b and hands back the caller's rows of x."""
+        comm = self._comm
+        indptr, indices, data, offs, has_const, nv = comm.gather_matrix(A.nrows, A.indptr, A.indices, A.data, A.null_has_const,
+                                                                        A.null_vecs)
+        G = Mat(indptr, indices, data, int(offs[-1]))
+        G.setNullSpace(has_const, nv)
+        self._new_handle(with_comm=False)
+        self._replicated = (int(offs[comm.rank]), int(offs[comm.rank + 1]), int(offs[-1]))
+        return G
+
+    def _new_handle(self, with_comm: bool):
+        """A fresh C handle with the options of the old one, single-rank (replica) or wired to the communicator again.
+        Collective: every rank drops its peer mappings first."""
+        opts = self.options()
+        _lib.check(self._L.b200ls_comm_disconnect(self._h), self._h)
+        self._comm.barrier()
+        self._L.b200ls_destroy(self._h)
+        self._h = C.c_void_p()
+        _lib.check(self._L.b200ls_create(C.byref(self._h), int(self._comm.device)))
+        _lib.check(self._L.b200ls_set_options(self._h, C.byref(opts)), self._h)
+        if with_comm:
+            self._comm.init_solver(self)
+
     def setMatrix(self, A: Mat):
         """LinSolverKSP::setMatrix (linsolverksp.cpp:72-82).  The matrix is copied/recognised here, the
         caller keeps ownership (as with AmgXSolver::setA, linsolveramgx.cpp:84)."""
@@ -323,6 +350,9 @@ class LinSolverB200(LinSolverBase):
         recognised = False
         self._repart = None
         multi = self._comm is not None and self._comm.nranks > 1
+        if multi and getattr(self, "_replicated", None) is not None:
+            self._new_handle(with_comm=True)     # the previous matrix was solved as replicas: distributed handle again
+            self._replicated = None
         if self._grid is not None and multi:
             self._repart = self._verify_boxes(A)
             recognised = self._repart is not None
@@ -340,18 +370,23 @@ class LinSolverB200(LinSolverBase):
                     recognised = True
                 elif rc != _lib.ERR_MISMATCH:
                     _lib.check(rc, self._h)
-        if not recognised and not multi and self._grid is not None and self._staggered:
+        if not recognised and multi:
+            # Any other system on several ranks (velocity system, IBPM's modified Poisson system, forces system, BN > 1;
+            # LinSolverKSP solves them on any rank count, linsolverksp.cpp:72-105): every rank gathers the whole matrix
+            # and solves the same system on its own GPU -- bit-identical replicas, each keeps its rows of x.
+            A = self._replicate(A)
+            multi = False
+        if not recognised and not multi and self._grid is not None and self._staggered and self._replicated is None:
             recognised = self._try_staggered(A)
         if not recognised:
-            if multi:
-                raise B200Error(_lib.ERR_UNSUPPORTED, "the matrix is not the separable pressure stencil of the mesh "
-                                "and the general CSR operator runs on one GPU only")
             # general assembled operator, still on the GPU (IBPM modified Poisson, velocity system, BN > 1)
             _lib.check(self._L.b200ls_set_csr(self._h, A.nrows, A.indptr.ctypes.data_as(_lib._i64p),
                                               A.indices.ctypes.data_as(_lib._i32p), A.data.ctypes.data_as(_lib._dp)),
                        self._h)
             self.operator = "csr"
             self.nlocal = A.nrows
+        if self._replicated is not None:
+            self.nlocal = self._replicated[1] - self._replicated[0]   # the caller's vectors hold its own rows
         nv = 0 if A.null_vecs is None else int(A.null_vecs.shape[0])
         pv = A.null_vecs.ctypes.data_as(_lib._dp) if nv else None
         _lib.check(self._L.b200ls_set_nullspace(self._h, int(A.null_has_const), nv, pv), self._h)
@@ -364,6 +399,21 @@ class LinSolverB200(LinSolverBase):
 
     # ---- LinSolverKSP::solve (linsolverksp.cpp:85-105): zero initial guess, error if reason < 0
     def solve(self, x, b):
+        rep = getattr(self, "_replicated", None)
+        if rep is not None:
+            lo, hi, ntot = rep
+            if _is_torch_cuda(b) or _is_torch_cuda(x) or not isinstance(x, np.ndarray):
+                raise ValueError("vectors of a replicated solve are host numpy arrays")
+            if np.size(b) != hi - lo or x.size != hi - lo:
+                raise ValueError("vector length does not match the operator")
+            bf = np.frombuffer(b"".join(self._comm.allgather_bytes(np.ascontiguousarray(b, dtype=np.float64).tobytes())),
+                               dtype=np.float64).copy()
+            xf = np.empty(ntot, dtype=np.float64)
+            rc = self._L.b200ls_solve(self._h, C.c_void_p(bf.ctypes.data), C.c_void_p(xf.ctypes.data))
+            if rc in (_lib.OK, _lib.ERR_DIVERGED):
+                x[...] = xf[lo:hi].reshape(x.shape)
+            _lib.check(rc, self._h)
+            return x
         rp = getattr(self, "_repart", None)
         if rp is not None and not rp.identity:
             # the caller's vectors are DMDA boxes: one all-to-all into the solver's slabs and one back (what

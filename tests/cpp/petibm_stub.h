@@ -20,6 +20,7 @@ typedef int MPI_Op;
 #define MPI_INT 1
 #define MPI_BYTE 2
 #define MPI_DOUBLE 3
+#define MPI_LONG_LONG 4
 #define MPI_MIN 1
 #define PETSC_ERR_SUP 56
 #define PETSC_ERR_ARG_WRONG 62
@@ -42,6 +43,9 @@ inline int MPI_Barrier(MPI_Comm) { return 0; }
 inline int MPI_Allreduce(const void *s, void *r, int n, MPI_Datatype, MPI_Op, MPI_Comm) { for (int i = 0; i < n; ++i) ((int *)r)[i] = ((const int *)s)[i]; return 0; }
 inline int MPI_Alltoallv(const void *s, const int *sc, const int *sd, MPI_Datatype, void *r, const int *, const int *rd, MPI_Datatype, MPI_Comm) { for (int i = 0; i < sc[0]; ++i) ((double *)r)[rd[0] + i] = ((const double *)s)[sd[0] + i]; return 0; }
 inline int MPI_Allgather(const void *s, int n, MPI_Datatype, void *r, int, MPI_Datatype, MPI_Comm) { for (int i = 0; i < n; ++i) ((char *)r)[i] = ((const char *)s)[i]; return 0; }
+
+inline int stub_mpi_size(MPI_Datatype t) { return t == MPI_BYTE ? 1 : t == MPI_INT ? 4 : 8; }
+inline int MPI_Allgatherv(const void *s, int n, MPI_Datatype t, void *r, const int *, const int *rd, MPI_Datatype, MPI_Comm) { const int b = stub_mpi_size(t); for (long i = 0; i < (long)n * b; ++i) ((char *)r)[(long)rd[0] * b + i] = ((const char *)s)[i]; return 0; }
 
 struct _p_Vec { std::vector<double> a; };
 typedef _p_Vec *Vec;

@@ -46,6 +46,22 @@ def main():
     lo3, hi3 = plan.slab
     assert np.array_equal(slab, field[lo3 * 42: hi3 * 42])
     assert np.array_equal(plan.slab_to_box(slab), box)
+    # a row-distributed matrix (uneven blocks, global column indices) gathered on every rank: the replicated solve
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(5)
+    ntot = 23
+    M = (sp.random(ntot, ntot, density=0.3, random_state=7, format="csr") + sp.identity(ntot)).tocsr()
+    M.sort_indices()
+    cuts = np.linspace(0, ntot, comm.nranks + 1).astype(int)
+    cuts[1:-1] += (np.arange(1, comm.nranks) % 2)            # uneven
+    mine_rows = M[cuts[comm.rank]: cuts[comm.rank + 1]]
+    vec = rng.standard_normal(ntot)
+    ip, ix, dv, offs, hc, nv = comm.gather_matrix(mine_rows.shape[0], mine_rows.indptr, mine_rows.indices, mine_rows.data, False,
+                                                  vec[cuts[comm.rank]: cuts[comm.rank + 1]])
+    assert np.array_equal(offs, cuts) and not hc
+    assert np.array_equal(ip, M.indptr) and np.array_equal(ix, M.indices) and np.array_equal(dv, M.data)
+    assert nv.shape == (1, ntot) and np.array_equal(nv[0], vec)
     comm.barrier()
     import torch.distributed as dist
 

@@ -126,6 +126,81 @@ def run_box_case(comm, shape, per, procs):
     return allok
 
 
+def run_replicated_case(comm, kind):
+    """Systems that are not the pressure stencil, on several ranks (the velocity system A = I/dt - c nu L with BiCGStab +
+    Jacobi, navierstokes.cpp:342-344,524-537; IBPM's modified Poisson system with its explicit null vector, ibpm.cpp:164-194,
+    251-267): rows are split over the ranks in uneven contiguous blocks with global column indices, as a parallel Mat
+    arrives; every rank solves a replica on its GPU.  Checked against the oracle's solve of the whole system."""
+    import scipy.sparse as sp
+
+    if kind == "velocity":
+        widths = H.make_widths((14, 12, 10))
+        A, _ = H.velocity_system(widths, (0, 0, 0), dt=0.01, nu=0.01, c=0.5)
+        nv, opts = None, dict(ksp_type="bcgs", pc_type="jacobi", rtol=0.0, atol=1e-9, max_it=500)
+        grid = H.grid_of(widths, (0, 0, 0))
+    else:
+        w = orc.axis_from_subdomains(0.0, [{"end": 0.8, "cells": 10, "stretchRatio": 1.0 / 1.15}, {"end": 1.2, "cells": 16, "stretchRatio": 1.0},
+                                           {"end": 2.0, "cells": 10, "stretchRatio": 1.15}])
+        widths = [w, w.copy()]
+        A, pN, nv = H.ibpm_system(widths, dt=0.01, nb=20)
+        opts = dict(ksp_type="cg", pc_type="jacobi", rtol=0.0, atol=0.0, max_it=40)
+        grid = H.grid_of(widths, (0, 0))
+    n = A.shape[0]
+    Ao = orc.Csr.from_arrays(n, n, A.indptr, A.indices, A.data)
+    rng = np.random.default_rng(12)
+    xs = rng.standard_normal(n)
+    if nv is not None:
+        xs -= (xs @ nv) * nv
+    b = A @ xs
+    cuts = np.linspace(0, n, comm.nranks + 1).astype(int)
+    cuts[1:-1] += 3 * (np.arange(1, comm.nranks) % 2)
+    lo, hi = int(cuts[comm.rank]), int(cuts[comm.rank + 1])
+    loc = A[lo:hi].tocsr()
+    loc.sort_indices()
+    c = Comm(comm.rank, comm.nranks, comm.device, "p2p", "store")
+    s = pb.LinSolverB200(kind, "None", comm=c, device=comm.device)
+    s.setOptions(**opts)
+    s.setGrid(grid)
+    M = pb.Mat(loc.indptr.astype(np.int64), loc.indices.astype(np.int32), loc.data, n)
+    M.setNullSpace(False, None if nv is None else nv[lo:hi])
+    msgs = []
+    ok = True
+    for rep in range(2):                         # a second setMatrix (moving bodies) goes through the same path
+        s.setMatrix(M)
+        if s.operator != "csr" or s.nlocal != hi - lo:
+            ok = False
+            msgs.append(f"operator {s.operator} nlocal {s.nlocal}")
+        x = np.empty(hi - lo)
+        try:
+            s.solve(x, b[lo:hi])
+        except pb.B200Error as e:
+            if e.code != -5:
+                raise
+        ref = orc.ksp_solve(Ao, b, nullvecs=nv, **{k: v for k, v in opts.items()})
+        hist = s.getHistory()
+        if kind == "ibpm":
+            if hist.size != ref.history.size or (np.abs(hist - ref.history) / ref.history).max() > 1e-10:
+                ok = False
+                msgs.append("history differs from the oracle")
+        else:
+            if s.getReason() != ref.reason or abs(s.getIters() - ref.its) > 2:
+                ok = False
+                msgs.append(f"its {s.getIters()} vs {ref.its}, reason {s.getReason()} vs {ref.reason}")
+        if np.abs(x - ref.x[lo:hi]).max() > 1e-7 * np.abs(ref.x).max():
+            ok = False
+            msgs.append(f"x diff {np.abs(x - ref.x[lo:hi]).max():.3e}")
+        allh = c.allgather_bytes(hist.tobytes())
+        if any(h != allh[0] for h in allh):
+            ok = False
+            msgs.append("histories differ between ranks")
+    s.destroy()
+    allok = all(c.allgather_bytes(ok))
+    if comm.rank == 0:
+        print(f"[{'PASS' if allok else 'FAIL'}] replicated solve of the {kind} system on {comm.nranks} ranks ({n} rows) {'; '.join(msgs)}",
+              flush=True)
+    return allok
+
+
 def main():
     import torch
 
@@ -162,6 +237,9 @@ def main():
                 allok &= run_box_case(comm, (30, 23), (0, 0), procs)
         elif comm.rank == 0:
             print("[SKIP] 2-D grids and DMDA box cases on several GPUs (set B200_MGPU_BOX=1)", flush=True)
+        if new_cases:
+            allok &= run_replicated_case(comm, "velocity")
+            allok &= run_replicated_case(comm, "ibpm")
     comm.barrier()
     if comm.rank == 0:
         print("MGPU_CHECK", "PASS" if allok else "FAIL", flush=True)
