@@ -986,7 +986,11 @@ extern "C" EMU_API int emu_stag_ops(int mode, int dim, const int64_t *n, const i
         const long long zu = dim == 3 ? s.nz + 2 : 1, zw = dim == 3 ? s.nw + 2 : 0;
         const long long su = (long long)(s.nu + 2) * (s.ny + 2) * zu, sv = (long long)(s.nx + 2) * (s.nv + 2) * zu;
         (void)zw;
-        if (mode == 4) emu::launch(dim3(3), dim3(256), 0, [&] { k_convection(s, in, in + su, in + su + sv, io); });
+        if (mode == 4)
+        {
+            if (dim == 3) emu::launch(dim3(3), dim3(256), 0, [&] { k_convection<3>(s, in, in + su, in + su + sv, io); });
+            else emu::launch(dim3(3), dim3(256), 0, [&] { k_convection<2>(s, in, in + su, in + su + sv, io); });
+        }
         else emu::launch(dim3(3), dim3(256), 0, [&] { k_ghosted_from_packed(s, in, io, io + su, io + su + sv); });
     }
     return 0;
