@@ -923,11 +923,37 @@ void build_commdev(b200ls_solver *h)
     if (h->nranks > 1) cm.mode = (h->reduce_mode == B200LS_REDUCE_NCCL) ? 2 : 1;
 }
 
-// arena layout: [mailboxes 2 parities * nranks records * 16 LL words | pad to 256 B | r]
-inline size_t arena_head_bytes(int nranks)
+// arena layout: [mailboxes 2 parities * nranks records * 16 LL words | pad to 256 B | halo flags (2 words) | pad to 256 B | r]
+inline size_t arena_flags_offset(int nranks)
 {
     const size_t b = sizeof(unsigned long long) * 2 * (size_t)nranks * B200_LLW;
     return (size_t)round_up((int64_t)b, 256);
+}
+inline size_t arena_head_bytes(int nranks) { return arena_flags_offset(nranks) + 256; }
+
+// The halo hand-shake (CommDev::halo_flag_*) needs both sides: k_update2 publishes, every fused SpMV kernel waits.  Used with
+// the fused transport and the flat update kernel; otherwise the pushers fence before their ticket as before.
+void apply_halo_flag_policy(b200ls_solver *h)
+{
+    CommDev &cm = h->cm;
+    cm.halo_flag_local = cm.halo_flag_dn_peer = cm.halo_flag_up_peer = nullptr;
+    cm.push_counter = nullptr;
+    if (!h->connected || h->nranks < 2 || h->reduce_mode != B200LS_REDUCE_P2P || h->halo_mode != B200LS_HALO_STORE) return;
+    if (h->upd_variant != 0 || h->op != OP_STENCIL) return;  // the same on every rank: tuning keys are set collectively
+    // Opt-in (B200LS_HALO_FLAGS=1): verified on 2 GPUs (tests/mgpu_check.py, all cases) but it buys nothing measurable --
+    // k_update2 15.5 us with the hand-shake, 15.4 us with the pushers' fence before their ticket, 13.2 us with no system
+    // fence at all (unsafe floor), same box (profiles/r02_trace_2gpu_slab.log): the fence is not what the reduction waits for.
+    if (!getenv("B200LS_HALO_FLAGS")) return;
+    const size_t fo = arena_flags_offset(h->nranks);
+    auto flags = [&](int q) { return reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(h->peer_base[q]) + fo); };
+    const bool perz = h->dim == 3 && h->per[2];
+    int dn = h->rank - 1, up = h->rank + 1;
+    if (dn < 0) dn = perz ? h->nranks - 1 : -1;
+    if (up >= h->nranks) up = perz ? 0 : -1;
+    cm.halo_flag_local = flags(h->rank);
+    if (dn >= 0) cm.halo_flag_dn_peer = flags(dn) + 1;  // I am above it: its "ghost plane above is ready"
+    if (up >= 0) cm.halo_flag_up_peer = flags(up) + 0;  // I am below it
+    cm.push_counter = h->ws.counter + 1;
 }
 
 int setup_stencil_vectors(b200ls_solver *h)
@@ -1415,6 +1441,7 @@ int b200ls_set_tuning(b200ls_solver *h, const char *key, int value)
     else if (k == "mg_tail") h->mg_tail = value;
     else if (k == "mg_fuse") h->mg_fuse = value;
     else return fail(h, B200LS_ERR_ARG, "unknown tuning key %s", key);
+    apply_halo_flag_policy(h);
     invalidate_graph(h);
     return B200LS_OK;
 }
@@ -1499,6 +1526,7 @@ int b200ls_comm_connect(b200ls_solver *h, const void *handles, int nranks)
         cm.r_ghost_dn = h->ghost_dn;
         cm.r_ghost_up = h->ghost_up;
     }
+    apply_halo_flag_policy(h);
     invalidate_graph(h);
     return B200LS_OK;
 }

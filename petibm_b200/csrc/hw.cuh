@@ -30,6 +30,8 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned int a, unsigned i
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
 }
+// orders this thread's earlier generic-proxy accesses (an acquire load of a flag) before its later async-proxy copies
+__device__ __forceinline__ void proxy_async_fence() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // after mbarrier.init, before the barriers are used by the async proxy (TMA)
 __device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 

@@ -81,6 +81,13 @@ struct CommDev
     double *sendbuf;             // NCCL mode: local sums
     double *r_ghost_dn;          // neighbour below: address of ITS top ghost plane of r (or null)
     double *r_ghost_up;          // neighbour above: address of ITS bottom ghost plane of r (or null)
+    // halo hand-shake of the fused transport (mode 1): the pusher CTAs of k_update2 publish "my boundary plane of reduction
+    // number s has landed in your ghost plane" in the neighbours' arenas AFTER their system-scope fence, off the path of
+    // the scalar all-reduce; the next fused SpMV kernel waits for the flags of its two ghost planes before reading them
+    unsigned long long *halo_flag_local;    // [0]: ghost plane below is ready (written by rank-1), [1]: above (rank+1); or null
+    unsigned long long *halo_flag_dn_peer;  // neighbour below: its flag [1]
+    unsigned long long *halo_flag_up_peer;  // neighbour above: its flag [0]
+    unsigned int *push_counter;             // pusher CTAs that have fenced (local)
     int push_items;              // items per pusher thread of k_update2 (0 = 2); experiment knob B200LS_PUSH_ITEMS
     int dbg_flags;               // bit 0: skip the system-scope fence of the pushers (TIMING EXPERIMENTS ONLY: unsafe)
 };
@@ -276,6 +283,30 @@ __device__ __forceinline__ bool mailbox_allreduce(double (&S)[B200_NSUM], const 
 #pragma unroll
     for (int q = 0; q < B200_NSUM; ++q) S[q] = __shfl_sync(0xffffffffu, mine, q);
     return ok;
+}
+
+// One thread: wait until the neighbours' boundary planes of reduction number `seq` have landed in this rank's ghost planes
+// (see CommDev::halo_flag_*).  Bounded like the mailbox spin: a peer that never arrives also fails the next all-reduce,
+// which reports the error.
+__device__ __forceinline__ void halo_wait_thread(const CommDev &cm, unsigned long long seq, bool need_dn, bool need_up)
+{
+    if (cm.mode != 1 || cm.halo_flag_local == nullptr) return;
+    const unsigned long long t0 = global_timer_ns();
+    for (int side = 0; side < 2; ++side)
+    {
+        const bool need = side == 0 ? (need_dn && cm.halo_flag_dn_peer != nullptr) : (need_up && cm.halo_flag_up_peer != nullptr);
+        if (!need) continue;
+        unsigned int spins = 0;
+        while (ld_acquire_sys(cm.halo_flag_local + side) < seq)
+            if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > 4000000000ull) break;
+    }
+}
+// CTA-wide form: thread 0 waits, everybody meets at a barrier
+__device__ __forceinline__ void halo_wait_cta(const CommDev &cm, unsigned long long seq, bool need_dn, bool need_up)
+{
+    if (cm.mode != 1 || cm.halo_flag_local == nullptr) return;
+    if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) halo_wait_thread(cm, seq, need_dn, need_up);
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -519,6 +550,7 @@ __global__ void __launch_bounds__(TXT *TYT) k_spmv(GridDev g, VecSet v, int kz_c
     const int i0 = blockIdx.x * BX, j0 = blockIdx.y * TY;
     const int k0 = blockIdx.z * kz_chunk;
     const int k1 = min(k0 + kz_chunk, g.nzl);
+    if (!APPLY) halo_wait_cta(cm, st->seq, k0 == 0, k1 == g.nzl);  // ghost planes of r from the neighbour GPUs
     const int i = i0 + 2 * tx;  // first of the two x points of this thread
     const int jr = j0 - 1 + ty; // row (may be -1 or >= ny)
     // row mapping (wrap if periodic, clamp otherwise: clamped rows only meet zero coefficients)
@@ -969,6 +1001,7 @@ __global__ void __launch_bounds__(256) k_update2(GridDev g, UpdVecs v, int fin_k
     trace_kernel_start(ws);
     const double ma = INIT ? 0.0 : -st->a;
     const double c = st->c;
+    const unsigned long long seq0 = PUSH ? st->seq : 0ull;      // this kernel's reduction will be number seq0 + 1
     const unsigned int plane2 = (unsigned int)(g.plane >> 1);
     const unsigned int n2 = plane2 * (unsigned int)g.nzl;       // host guarantees < 2^32
     const unsigned int last0 = plane2 * (unsigned int)(g.nzl - 1);
@@ -1052,7 +1085,25 @@ __global__ void __launch_bounds__(256) k_update2(GridDev g, UpdVecs v, int fin_k
             UpdItem<JACOBI, INIT, PADDED, PUSH>::run(i, rr, wr, dr, ma, c, r2, gdn, gup, plane2, last0, pxh, nx, acc);
         }
     }
-    grid_reduce_finalize<6>(acc, fin_kind, ws, cm, st, kc, hist, PUSH && pusher && !(cm.dbg_flags & 1));
+    // with the halo hand-shake the pushers' system fence comes AFTER their ticket: it no longer delays the reduction
+    const bool flagged = PUSH && cm.mode == 1 && cm.halo_flag_local != nullptr;
+    grid_reduce_finalize<6>(acc, fin_kind, ws, cm, st, kc, hist, PUSH && pusher && !flagged && !(cm.dbg_flags & 1));
+    if (flagged && pusher)
+    {
+        __threadfence_system();  // this thread's peer stores are performed
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            const unsigned int t = atomicAdd(cm.push_counter, 1u);
+            if (t == npush - 1u)
+            {
+                *cm.push_counter = 0u;  // the next launch cannot start before this grid has completed
+                __threadfence_system();
+                if (cm.halo_flag_dn_peer) st_release_sys(cm.halo_flag_dn_peer, seq0 + 1ull);
+                if (cm.halo_flag_up_peer) st_release_sys(cm.halo_flag_up_peer, seq0 + 1ull);
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -144,6 +144,8 @@ __global__ void __launch_bounds__(TXT *TYT, MINB)
         bcoef = st->b;
         aprev = st->a;
         xupd = st->pending != 0;
+        // ghost planes of r come from the neighbour GPUs: wait for their hand-shake (no-op on one GPU / NCCL transport)
+        halo_wait_cta(cm, st->seq, k0 == 0, k1 == g.nzl);
     }
 
     // storage offset (bytes) of plane kk = k0-1+t: (kk+1)*plane, except the single-GPU periodic wrap

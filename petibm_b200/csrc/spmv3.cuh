@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(TXT *TYT, MINB)
                 bcoef = st->b;
                 aprev = st->a;
                 xupd = st->pending != 0;
+                halo_wait_cta(cm, st->seq, true, true);  // ghost planes of r from the neighbour GPUs (any segment may touch them)
             }
             state_read = true;
         }

@@ -123,9 +123,14 @@ __global__ void __launch_bounds__(32 * (TY + 1), MINB)
     {
         if (tx == 0)
         {
+            const unsigned long long seq = st->seq;
             unsigned int stage = 0, par = 1;  // parity to wait for on `empty`: the previous use of the stage
             for (int t = 0; t < nplanes; ++t)
             {
+                // a ghost plane of r filled by a neighbour GPU: its hand-shake first (only this thread reads it, through TMA)
+                if (t == 0 && k0 == 0) halo_wait_thread(cm, seq, true, false);
+                if (t == nplanes - 1 && k1 == g.nzl) halo_wait_thread(cm, seq, false, true);
+                if (cm.mode == 1 && (t == 0 || t == nplanes - 1)) proxy_async_fence();
                 if (t >= S) mbar_wait(bar_empty + 8u * stage, par);
                 const bool own = (t >= 1) && (t < nplanes - 1);
                 const bool wantx = own && xupd;

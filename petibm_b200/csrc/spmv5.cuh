@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(32 * TY, MINB)
     trace_kernel_start(ws);
     const double shift = st->shift, bcoef = st->b, aprev = st->a;
     const bool xupd = st->pending != 0;
+    halo_wait_cta(cm, st->seq, k0 == 0, k1 == g.nzl);  // ghost planes of r from the neighbour GPUs
 
     auto pval = [&](double r, double d, double pp) -> double {
         double z = r;

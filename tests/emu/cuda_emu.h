@@ -322,6 +322,7 @@ inline void mbar_init(unsigned int a, unsigned int count)
     memcpy(smem_ptr(a), &m, 8);
 }
 inline void mbar_init_fence() {}
+inline void proxy_async_fence() {}
 inline void mbar_arrive(unsigned int a)
 {
     emu::maybe_yield();
