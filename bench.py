@@ -414,6 +414,21 @@ def run_b200(args):
         k2_ms, k2_n = solver.profile(1)
         solver.setProfile(False)
         prof_ms_per_step = comm.allreduce_max(pm) / args.steps
+    # in-kernel duration of the same launches in the PRODUCTION path (CUDA-graph batches + programmatic dependent launch):
+    # %globaltimer stamps written by the kernels themselves (first CTA start -> scalars done), one extra solve, median.
+    # The event pairs above add launch latency and serialise the prologues; this is what the ncu launch list sees.
+    in_kernel_us = None
+    if profile:
+        try:
+            solver.setTrace(4 * args.iters + 16)
+            one_solve(x_dev, b_dev)
+            tr = solver.getTrace(4 * args.iters + 16).astype(np.int64)
+            solver.setTrace(0)
+            k0 = tr[tr[:, 4] == 0]
+            k1 = tr[tr[:, 4] == 1]
+            in_kernel_us = {"k_spmv": float(np.median(k0[:, 3] - k0[:, 0]) / 1e3), "k_update": float(np.median(k1[:, 3] - k1[:, 0]) / 1e3)}
+        except Exception as e:  # the trace is diagnostic only
+            in_kernel_us = {"error": str(e)[:100]}
     clocks = sampler.stop() if sampler else None
 
     # ---- timed region 2: end to end through the plugin call with host buffers ---------------
@@ -446,6 +461,7 @@ def run_b200(args):
                              "avg_launch_us": (k2_ms / max(k2_n, 1)) * 1e3,
                              "achieved": K2_BYTES_PER_ROW * nloc / max(k2_ms / max(k2_n, 1) * 1e-3, 1e-12) / 1e9},
                 "iteration_achieved": ITER_BYTES_PER_ROW * nloc * args.iters / (ms_per_step * 1e-3) / 1e9,
+                "in_kernel_us_graph_path": in_kernel_us,
                 "measured_in": "K extra steps of the same workload with a CUDA-event pair around every launch "
                                "(%.2f ms/step there vs %.2f ms/step in the value region)" % (prof_ms_per_step, ms_per_step)}
 

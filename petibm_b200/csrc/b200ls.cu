@@ -135,14 +135,14 @@ struct b200ls_solver
     int mg_built_levels = 0;
     int64_t graph_launches = 0;   // launches inside the graph replayed by graph_batch (csr_solver.inc)
     int csr_graph = 0;            // tuning "csr_graph": CG / BiCGStab batches of the assembled-operator paths as CUDA graphs
-    int mg_fuse = 0;         // tuning "mg_fuse": r -= a w and the six sums ride on the first / last fine-level step of the cycle
-    int mg_tail = 0;         // tuning "mg_tail": the coarse levels of the cycle as one launch (k_mg_tail; off until timed)
+    int mg_fuse = 1;         // tuning "mg_fuse": r -= a w and the six sums ride on the first / last fine-level step of the cycle (on: 15.1 -> 14.2 ms at 256^3, profiles/r02_tts_multigrid.log)
+    int mg_tail = 1;         // tuning "mg_tail": the coarse levels of the cycle as one launch (k_mg_tail; on: 597 -> 267 launches, 15.7 -> 15.1 ms at 256^3)
     MgOp *mg_tail_ops = nullptr;
     MgLevel *mg_tail_levels = nullptr;
     int mg_tail_nops = 0;
     int mg_tail_degrees[2] = {0, 0};
     double *mg_tail_result = nullptr;
-    int mg_graph = 0;        // tuning "mg_graph": replay pairs of preconditioned iterations as one CUDA graph (off until timed)
+    int mg_graph = 1;        // tuning "mg_graph": replay pairs of preconditioned iterations as one CUDA graph (on: 14.2 -> 13.8 ms at 256^3; 2-D 448^2: 4.05 -> 2.26 ms)
 
     // ---- direct solve of a small assembled system (preonly + lu; dense_kernels.cuh)
     double *d_dense = nullptr;   // n x n factors

@@ -160,3 +160,52 @@ def test_block_multigrid_on_a_stretched_ibpm_system(pb, dim):
     assert s.getReason() == 2 and 3 * its_mg <= s.getIters(), (its_mg, s.getIters())
     np.testing.assert_allclose(x, xs, rtol=0, atol=1e-6 * np.abs(xs).max())
     s.destroy()
+
+
+@pytest.mark.parametrize("shape,per", [((48, 40, 32), (0, 0, 0)), ((70, 45), (0, 0))])
+def test_the_launch_switches_do_not_change_the_numbers(pb, shape, per):
+    """mg_tail (coarse levels as one launch), mg_fuse (residual update and sums inside the cycle) and mg_graph (CUDA-graph
+    replay) are on by default since round 2 (profiles/r02_tts_multigrid.log); every combination gives the same history."""
+    widths = H.make_widths(shape)
+    A = H.oracle_matrix(widths, per)
+    b, _ = H.consistent_rhs(A)
+    ref = None
+    for tail, fuse, graph in ((1, 1, 1), (0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)):
+        s = pb.LinSolverB200("poisson", "None")
+        s.setOptions(pc_type="mg", rtol=1e-10, atol=1e-50, max_it=100)
+        s.setTuning("mg_tail", tail); s.setTuning("mg_fuse", fuse); s.setTuning("mg_graph", graph)
+        s.setStencil(H.grid_of(widths, per))
+        s.setNullSpace(True)
+        x = np.empty_like(b)
+        s.solve(x, b)
+        h = s.getHistory()
+        if ref is None:
+            ref = (h, x.copy())
+        else:
+            assert h.size == ref[0].size
+            np.testing.assert_allclose(h, ref[0], rtol=1e-9)
+            np.testing.assert_allclose(x, ref[1], rtol=0, atol=1e-10 * np.abs(ref[1]).max())
+        s.destroy()
+
+
+def test_graph_replay_of_the_assembled_operator_loops_does_not_change_the_numbers(pb):
+    """csr_graph: CG / BiCGStab batches of the CSR and line-coefficient paths as CUDA graphs -- same history on and off."""
+    widths = H.make_widths((14, 12, 10))
+    A, _ = H.velocity_system(widths, (0, 0, 0), dt=0.01, nu=0.01, c=0.5)
+    b = np.random.default_rng(4).standard_normal(A.shape[0])
+    out = {}
+    for stag in (True, False):
+        for graph in (0, 1):
+            s = pb.LinSolverB200("velocity", "None")
+            s.setOptions(ksp_type="bcgs", pc_type="jacobi", rtol=0.0, atol=1e-10, max_it=200)
+            s.setTuning("csr_graph", graph)
+            s.setGrid(H.grid_of(widths, (0, 0, 0)))
+            s.setStaggered(stag)
+            s.setMatrix(pb.Mat.from_scipy(A))
+            x = np.empty(A.shape[0])
+            s.solve(x, b)
+            out[(stag, graph)] = (s.getHistory(), x.copy(), s.operator)
+            s.destroy()
+    assert out[(True, 0)][2] == "staggered" and out[(False, 0)][2] == "csr"
+    for stag in (True, False):
+        assert np.array_equal(out[(stag, 0)][0], out[(stag, 1)][0]) and np.array_equal(out[(stag, 0)][1], out[(stag, 1)][1])
