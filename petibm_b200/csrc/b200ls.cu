@@ -147,6 +147,8 @@ struct b200ls_solver
     // ---- direct solve of a small assembled system (preonly + lu; dense_kernels.cuh)
     double *d_dense = nullptr;   // n x n factors
     int *d_dense_info = nullptr;
+    double *d_dense_work = nullptr;          // substitution: work vector | block flags | ticket
+    unsigned long long dense_epoch = 0;
     bool dense_ready = false;
 
     // ---- vectors (solver layout)
@@ -277,6 +279,7 @@ void free_vectors(b200ls_solver *h)
     h->tma_maps.clear();
     fr(h->d_dense);
     fr(h->d_dense_info);
+    fr(h->d_dense_work);
     h->dense_ready = false;
     fr(h->d_sep_coef);
     fr(h->d_sep_diag);
@@ -450,14 +453,23 @@ inline K1Cfg k1_config(const b200ls_solver *h)
         tiles[0] = h->tile;
         ntiles = 1;
     }
-    else if (h->tile < 0 && !(h->per[0] || h->per[1] || h->per[2]) &&
-             40.0 * (double)(nzl + 2) * (double)h->g.plane <= 110.0e6)
+    else if (h->tile < 0 && !(h->per[0] || h->per[1] || h->per[2]) && h->opt.pc_type != B200LS_PC_JACOBI)
     {
-        // the five solver vectors fit the 126 MB L2 (8-GPU slabs of 256^3, 128^3 on one GPU): the TMA kernel with 64 x 4
-        // tiles wins there (18.4 us against 24.1 us per launch on a 256 x 256 x 32 slab, profiles/r02_trace_2gpu_slab.log);
-        // out of HBM the two kernels are level and the cp.async kernel keeps its tuned launch shape
+        // (Jacobi keeps the cp.async kernel: with the extra 1/diag halo box and z rebuilt at six neighbours the TMA kernel
+        // is 17 % slower there, 3 155 against 3 785 iterations/s at 256^3, gpurun call r02o.)
+        // Non-periodic grids: the TMA kernel (k_spmv4, 64 x 4 tiles, 4 CTAs per SM).  When the five solver vectors fit the
+        // 126 MB L2 (8-GPU slabs of 256^3, 128^3 on one GPU) it wins clearly (18.4 us against 24.1 us per launch on a
+        // 256 x 256 x 32 slab, profiles/r02_trace_2gpu_slab.log) and the wave model below picks its z chunks.  Out of HBM it
+        // is level with the cp.async kernel kernel-by-kernel but faster inside the solve with chunks of about 43 planes
+        // (4 674 against 4 530 iterations/s at 256^3 on the same box, gpurun call r02n; 26 - 64 planes are within 2 %,
+        // 128 planes lose 10 %): nch = round(nzl / 43).
         tiles[0] = 41;
         ntiles = 1;
+        if (40.0 * (double)(nzl + 2) * (double)h->g.plane > 110.0e6 && h->kz_chunk <= 0)
+        {
+            const int nch = std::max(1, (nzl + 21) / 43);
+            return {41, (nzl + nch - 1) / nch};
+        }
     }
     K1Cfg best{tiles[0], std::max(1, std::min(nzl, 512))};
     double best_score = -1.0;

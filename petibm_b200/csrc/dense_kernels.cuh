@@ -283,4 +283,82 @@ __global__ void __launch_bounds__(1024) k_dense_solve(int n, int lda, const doub
     for (int i = tid; i < n; i += nt) x[i] = xs[i];
 }
 
+// Multi-CTA substitution: one CTA of four warps per block of 32 unknowns, wavefront over the blocks.  A CTA first streams
+// the off-diagonal blocks of its block row against the parts of the vector that are already final (each part is
+// published with a release flag by the CTA that solved it), and solves its 32 x 32 triangle as soon as the last one has
+// arrived: the dependent chain is one flag hop + one triangle per block (about 3 us) instead of one CTA streaming all
+// factors.  UPPER = false: y = L^-1 P b (unit diagonal); UPPER = true: x = U^-1 y, in place in `work`, copied to `out`.
+// The logical block index comes from a ticket, so a CTA only ever waits for CTAs that started before it.
+template <bool UPPER>
+__global__ void __launch_bounds__(128) k_dense_sweep(int n, int lda, const double *a, const int *perm, const double *b, double *work,
+                                                     double *out, unsigned long long *flags, unsigned int *ticket, unsigned long long epoch)
+{
+    __shared__ double s_part[4][LU_NB];
+    __shared__ double s_diag[LU_NB][LU_NB + 1];
+    __shared__ unsigned int s_blk;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nblk = (n + LU_NB - 1) / LU_NB;
+    if (tid == 0) s_blk = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int I = UPPER ? nblk - 1 - (int)s_blk : (int)s_blk;
+    const int r0 = I * LU_NB, nr = min(LU_NB, n - r0);
+    for (int e = tid; e < nr * nr; e += 128) s_diag[e / nr][e % nr] = a[(size_t)(r0 + e / nr) * lda + r0 + e % nr];
+    const bool row_ok = lane < nr;
+    const double *arow = a + (size_t)(r0 + (row_ok ? lane : 0)) * lda;
+    double acc = 0.0;
+    const int count = UPPER ? nblk - 1 - I : I;  // blocks this row depends on
+    for (int q = warp; q < count; q += 4)
+    {
+        const int J = UPPER ? nblk - 1 - q : q;  // in the order in which they become final
+        const int c0 = J * LU_NB, nc = min(LU_NB, n - c0);
+        double lrow[LU_NB];
+#pragma unroll
+        for (int c = 0; c < LU_NB; ++c) lrow[c] = (row_ok && c < nc) ? arow[c0 + c] : 0.0;  // static data: loaded before the wait
+        if (lane == 0)
+        {
+            unsigned int spins = 0;
+            const unsigned long long t0 = global_timer_ns();
+            while (ld_acquire_sys(flags + J) < epoch)
+                if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > 4000000000ull) break;  // never hang the GPU
+        }
+        __syncwarp();
+        const double yv = lane < nc ? __ldcg(work + c0 + lane) : 0.0;
+#pragma unroll
+        for (int c = 0; c < LU_NB; ++c) acc = fma(-lrow[c], __shfl_sync(0xffffffffu, yv, c), acc);
+    }
+    s_part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0)
+    {
+        double xr = 0.0;
+        if (row_ok) xr = UPPER ? __ldcg(work + r0 + lane) : b[perm[r0 + lane]];
+        xr += (s_part[0][lane] + s_part[1][lane]) + (s_part[2][lane] + s_part[3][lane]);
+        if (!UPPER)
+        {
+            for (int c = 0; c < nr; ++c)
+            {
+                const double xc = __shfl_sync(0xffffffffu, xr, c);
+                if (lane > c && lane < nr) xr = fma(-s_diag[lane][c], xc, xr);
+            }
+        }
+        else
+        {
+            for (int c = nr - 1; c >= 0; --c)
+            {
+                if (lane == c) xr = xr / s_diag[c][c];
+                const double xc = __shfl_sync(0xffffffffu, xr, c);
+                if (lane < c) xr = fma(-s_diag[lane][c], xc, xr);
+            }
+        }
+        if (row_ok)
+        {
+            work[r0 + lane] = xr;
+            if (UPPER) out[r0 + lane] = xr;
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_sys(flags + I, epoch);
+    }
+}
+
 }  // namespace b200

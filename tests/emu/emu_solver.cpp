@@ -1015,8 +1015,28 @@ extern "C" EMU_API int emu_dense_solve(int64_t n, const int64_t *rowptr, const i
     if (info != 0) return info;
     emu::launch(dim3(1), dim3(32), 0, [&] { k_lu_perm((int)n, piv.data(), perm.data()); });
     const size_t smem = sizeof(double) * ((size_t)lda + (size_t)LU_NB * (LU_NB + 1));
+    const int nblk = (int)((n + LU_NB - 1) / LU_NB);
+    std::vector<double> work((size_t)n, 0.0);
+    std::vector<unsigned long long> flags((size_t)nblk + 1, 0ull);
+    unsigned long long epoch = 0;
     for (int q = 0; q < nrhs; ++q)
-        emu::launch(dim3(1), dim3(threads), smem, [&] { k_dense_solve((int)n, lda, a.data(), perm.data(), b + (size_t)q * n, x + (size_t)q * n); });
+    {
+        const double *bq = b + (size_t)q * n;
+        double *xq = x + (size_t)q * n;
+        if (threads == 128 && nblk > 2)
+        {
+            // the multi-CTA wavefront substitution (CTAs run one after the other here, in ticket order: every wait is satisfied)
+            unsigned int *ticket = reinterpret_cast<unsigned int *>(&flags[(size_t)nblk]);
+            *ticket = 0;
+            ++epoch;
+            emu::launch(dim3(nblk), dim3(128), 0, [&] { k_dense_sweep<false>((int)n, lda, a.data(), perm.data(), bq, work.data(), xq, flags.data(), ticket, epoch); });
+            *ticket = 0;
+            ++epoch;
+            emu::launch(dim3(nblk), dim3(128), 0, [&] { k_dense_sweep<true>((int)n, lda, a.data(), perm.data(), bq, work.data(), xq, flags.data(), ticket, epoch); });
+        }
+        else
+            emu::launch(dim3(1), dim3(threads), smem, [&] { k_dense_solve((int)n, lda, a.data(), perm.data(), bq, xq); });
+    }
     return 0;
 }
 

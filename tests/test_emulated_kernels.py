@@ -634,7 +634,7 @@ def test_emulated_direct_solve_of_the_forces_system(emu):
     assert rc == 2                                  # zero pivot in column 1 (1-based: 2): KSP_DIVERGED_PC_FAILED on the device path
 
 
-@pytest.mark.parametrize("n", [3, 31, 32, 33, 75, 130])
+@pytest.mark.parametrize("n", [3, 31, 32, 33, 75, 130, 257])
 def test_emulated_direct_solve_pivots(emu, n):
     """Partial pivoting (what PETSc's LU / superlu_dist do): a matrix with a zero diagonal and rows of very different
     scale, sizes around the panel width of 32; unpivoted elimination fails or loses all digits on these."""
@@ -646,7 +646,9 @@ def test_emulated_direct_solve_pivots(emu, n):
     A[rng.integers(0, n, 2)] *= 1e6
     assert np.linalg.cond(A) < 1e12
     B = rng.standard_normal((2, n))
-    rc, X = _dense_solve(emu, sp.csr_matrix(A), B, 64)
+    # 128 threads and more than two blocks of 32 unknowns: the multi-CTA wavefront substitution (k_dense_sweep);
+    # otherwise the one-CTA kernel
+    rc, X = _dense_solve(emu, sp.csr_matrix(A), B, 128 if n > 64 else 64)
     assert rc == 0
     ref = np.linalg.solve(A, B.T).T
     np.testing.assert_allclose(X, ref, rtol=0, atol=1e-13 * np.linalg.cond(A) * np.abs(ref).max())
