@@ -406,7 +406,7 @@ inline TileCfg tile_dims(int tile)
         case 30: case 32: return {32, 12};  // k_spmv3 (balanced split; 32: + split barrier), 64 x 10 tile -- round-2 candidates
         case 31: case 33: return {32, 8};   // k_spmv3 (balanced split; 33: + split barrier), 64 x 6 tile  -- round-2 candidates
         case 40: return {32, 9};   // k_spmv4 (TMA): 64 x 8 tile + producer warp, S = 4, 2 CTAs/SM
-        case 41: return {32, 5};   // k_spmv4: 64 x 4 tile, S = 4, 4 CTAs/SM
+        case 41: case 44: case 45: return {32, 5};   // k_spmv4: 64 x 4 tile, S = 4 (44: S = 6, 45: S = 3), 4 CTAs/SM
         case 42: return {32, 9};   // k_spmv4: 64 x 8 tile, S = 3, 3 CTAs/SM
         case 43: return {32, 17};  // k_spmv4: 64 x 16 tile, S = 3, 1 CTA/SM
         case 50: case 51: case 53: case 54: case 55: case 56: return {32, 8};  // k_spmv5 (no staging, cache-resident slabs): 64 x 8 rows, 4 / 8 / 16 planes per thread
@@ -427,7 +427,7 @@ inline int tile_ctas_per_sm(int tile)
 {
     switch (tile)
     {
-        case 13: case 41: return 4;
+        case 13: case 41: case 44: case 45: return 4;
         case 18: case 30: case 32: case 40: return 2;
         case 0: return 2;
         case 43: return 1;
@@ -467,8 +467,28 @@ inline K1Cfg k1_config(const b200ls_solver *h)
         ntiles = 1;
         if (40.0 * (double)(nzl + 2) * (double)h->g.plane > 110.0e6 && h->kz_chunk <= 0)
         {
-            const int nch = std::max(1, (nzl + 21) / 43);
-            return {41, (nzl + nch - 1) / nch};
+            // z chunks of 40 .. 72 planes (shorter: more redundant halo planes and prologues; 128 planes in ONE partial wave
+            // lose 10 %), chosen for the fullest last wave of (SMs x 4) resident CTAs: at 256^3
+            // 43 or 64 planes (fill 0.87) give 4 660 - 4 680 iterations/s, 37 / 52 / 86 planes (fill 0.76 / 0.72 / 0.65)
+            // 4 470 / 4 390 / 4 290 (gpurun call r02p, profiles/r02_bench_kernel_choice.log)
+            const int64_t xy = (int64_t)((h->g.nx + 63) / 64) * ((h->g.ny + 3) / 4);
+            const int64_t slots = (int64_t)h->num_sms * 4;
+            int best_kz = nzl;
+            double best_score = -1.0;
+            for (int nch = 1; nch <= std::max(1, nzl / 40); ++nch)
+            {
+                const int kz = (nzl + nch - 1) / nch;
+                if (kz > 72 && nch < std::max(1, nzl / 40)) continue;
+                const int64_t blocks = xy * ((nzl + kz - 1) / kz);
+                const int64_t waves = (blocks + slots - 1) / slots;
+                const double score = (double)blocks / (double)(waves * slots) * ((double)kz / (double)(kz + 3));
+                if (score >= best_score * (1.0 - 1e-12))   // ties: fewer, longer chunks
+                {
+                    if (score > best_score * (1.0 + 1e-12) || kz > best_kz) best_kz = kz;
+                    best_score = std::max(score, best_score);
+                }
+            }
+            return {41, std::min(best_kz, 512)};
         }
     }
     K1Cfg best{tiles[0], std::max(1, std::min(nzl, 512))};
@@ -695,6 +715,8 @@ int launch_spmv_t(b200ls_solver *h, const VecSet &v, int ghost_store)
         case 33: return launch_spmv3_cfg<8, 4, 3, JAC, true>(h, v, ghost_store);
         case 40: return launch_spmv4_cfg<8, 4, 2, JAC>(h, v, ghost_store, grid, kz);
         case 41: return launch_spmv4_cfg<4, 4, 4, JAC>(h, v, ghost_store, grid, kz);
+        case 44: return launch_spmv4_cfg<4, 6, 4, JAC>(h, v, ghost_store, grid, kz);
+        case 45: return launch_spmv4_cfg<4, 3, 4, JAC>(h, v, ghost_store, grid, kz);
         case 42: return launch_spmv4_cfg<8, 3, 3, JAC>(h, v, ghost_store, grid, kz);
         case 43: return launch_spmv4_cfg<16, 3, 1, JAC>(h, v, ghost_store, grid, kz);
         case 50: return launch_spmv5_cfg<8, 4, 2, JAC>(h, v, ghost_store, grid);
@@ -740,7 +762,17 @@ void launch_update_t(b200ls_solver *h, int fin_kind, bool push)
         cm.r_ghost_up = nullptr;
     }
     const SolveConsts kc = make_consts(h);
-    const int blocks = upd_grid_blocks(h);
+    int blocks = upd_grid_blocks(h);
+    cm.npush = 0;
+    if (push && h->upd_variant == 0 && h->upd_blocks <= 0 && h->g.nzl > 2)
+    {
+        // the boundary planes get their own CTAs ON TOP of the interior's grid, so the interior streams with as many
+        // CTAs as on one GPU (pushers taken out of the grid: 46.5 us for a 256 x 256 x 128 slab, 33 us of HBM time)
+        const int64_t nb2 = (int64_t)h->g.plane;  // two planes of plane/2 double2 items
+        const int items = cm.push_items > 0 ? cm.push_items : 2;
+        cm.npush = (int)std::max<int64_t>(1, std::min<int64_t>((nb2 + 256 * items - 1) / (256 * items), blocks / 2));
+        blocks += cm.npush;
+    }
     if (h->upd_variant == 1)
         k_update<JAC, INIT, 4><<<blocks, 256, 0, h->stream>>>(h->g, v, fin_kind, h->ws, cm, h->d_state, kc, h->d_hist);
     else if (JAC && h->upd_variant == 2)

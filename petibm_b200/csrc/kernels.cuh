@@ -89,6 +89,7 @@ struct CommDev
     unsigned long long *halo_flag_up_peer;  // neighbour above: its flag [0]
     unsigned int *push_counter;             // pusher CTAs that have fenced (local)
     int push_items;              // items per pusher thread of k_update2 (0 = 2); experiment knob B200LS_PUSH_ITEMS
+    int npush;                   // pusher CTAs the host ADDED to the update grid (0: the kernel takes them out of its grid)
     int dbg_flags;               // bit 0: skip the system-scope fence of the pushers (TIMING EXPERIMENTS ONLY: unsafe)
 };
 
@@ -1022,7 +1023,7 @@ __global__ void __launch_bounds__(256) k_update2(GridDev g, UpdVecs v, int fin_k
     if (PUSH)
     {
         const unsigned int nb2 = g.nzl >= 2 ? 2u * plane2 : plane2;  // items of the boundary planes
-        npush = update_pushers(nb2, gridDim.x, cm.push_items);
+        npush = cm.npush > 0 ? (unsigned int)cm.npush : update_pushers(nb2, gridDim.x, cm.push_items);
         pusher = blockIdx.x < npush;
     }
     const bool no_interior_ctas = PUSH && npush >= gridDim.x;
