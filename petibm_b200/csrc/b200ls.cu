@@ -465,21 +465,24 @@ inline K1Cfg k1_config(const b200ls_solver *h)
         // 128 planes lose 10 %): nch = round(nzl / 43).
         tiles[0] = 41;
         ntiles = 1;
-        if (40.0 * (double)(nzl + 2) * (double)h->g.plane > 110.0e6 && h->kz_chunk <= 0)
+        if (40.0 * (double)(nzl + 2) * (double)h->g.plane > 110.0e6)
         {
-            // z chunks of 40 .. 72 planes (shorter: more redundant halo planes and prologues; 128 planes in ONE partial wave
-            // lose 10 %), chosen for the fullest last wave of (SMs x 4) resident CTAs: at 256^3
-            // 43 or 64 planes (fill 0.87) give 4 660 - 4 680 iterations/s, 37 / 52 / 86 planes (fill 0.76 / 0.72 / 0.65)
-            // 4 470 / 4 390 / 4 290 (gpurun call r02p, profiles/r02_bench_kernel_choice.log)
+            // Out of HBM the kernel runs at (resident CTAs) x (one plane per ~1.2 us each): it needs z chunks of 40 .. 72
+            // planes (shorter: redundant halo planes and prologues) AND at least 1.5 waves of (SMs x 4) CTAs -- 256^3 with
+            // 43 or 64 planes per CTA: 4 660 - 4 680 iterations/s; 37 / 52 / 86 planes (last wave 3 % / 16 % / 30 % full):
+            // 4 470 / 4 390 / 4 290; 128 planes = ONE wave of 512 CTAs: -10 %; a 256 x 256 x 64 slab (4 GPUs) as one wave of
+            // 256 CTAs: 11.2 k instead of 13.9 k iterations/s (gpurun calls r02p, r02s).  Grids too small for that keep the
+            // cp.async kernel and its tuned launch shape.
             const int64_t xy = (int64_t)((h->g.nx + 63) / 64) * ((h->g.ny + 3) / 4);
             const int64_t slots = (int64_t)h->num_sms * 4;
-            int best_kz = nzl;
+            int best_kz = 0;
             double best_score = -1.0;
-            for (int nch = 1; nch <= std::max(1, nzl / 40); ++nch)
+            for (int nch = 1; nch <= std::max(1, nzl / 40) && h->kz_chunk <= 0; ++nch)
             {
                 const int kz = (nzl + nch - 1) / nch;
-                if (kz > 72 && nch < std::max(1, nzl / 40)) continue;
+                if (kz > 72) continue;
                 const int64_t blocks = xy * ((nzl + kz - 1) / kz);
+                if (2 * blocks < 3 * slots) continue;
                 const int64_t waves = (blocks + slots - 1) / slots;
                 const double score = (double)blocks / (double)(waves * slots) * ((double)kz / (double)(kz + 3));
                 if (score >= best_score * (1.0 - 1e-12))   // ties: fewer, longer chunks
@@ -488,7 +491,13 @@ inline K1Cfg k1_config(const b200ls_solver *h)
                     best_score = std::max(score, best_score);
                 }
             }
-            return {41, std::min(best_kz, 512)};
+            if (best_kz > 0) return {41, best_kz};
+            if (h->kz_chunk <= 0)
+            {
+                tiles[0] = 10;   // back to the cp.async candidates
+                tiles[1] = 18;
+                ntiles = 2;
+            }
         }
     }
     K1Cfg best{tiles[0], std::max(1, std::min(nzl, 512))};
@@ -764,7 +773,8 @@ void launch_update_t(b200ls_solver *h, int fin_kind, bool push)
     const SolveConsts kc = make_consts(h);
     int blocks = upd_grid_blocks(h);
     cm.npush = 0;
-    if (push && h->upd_variant == 0 && h->upd_blocks <= 0 && h->g.nzl > 2)
+    static const bool push_extra = !(getenv("B200LS_PUSH_EXTRA") && atoi(getenv("B200LS_PUSH_EXTRA")) == 0);
+    if (push && push_extra && h->upd_variant == 0 && h->upd_blocks <= 0 && h->g.nzl > 2)
     {
         // the boundary planes get their own CTAs ON TOP of the interior's grid, so the interior streams with as many
         // CTAs as on one GPU (pushers taken out of the grid: 46.5 us for a 256 x 256 x 128 slab, 33 us of HBM time)
