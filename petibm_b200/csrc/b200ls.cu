@@ -406,7 +406,7 @@ inline TileCfg tile_dims(int tile)
         case 30: case 32: return {32, 12};  // k_spmv3 (balanced split; 32: + split barrier), 64 x 10 tile -- round-2 candidates
         case 31: case 33: return {32, 8};   // k_spmv3 (balanced split; 33: + split barrier), 64 x 6 tile  -- round-2 candidates
         case 40: return {32, 9};   // k_spmv4 (TMA): 64 x 8 tile + producer warp, S = 4, 2 CTAs/SM
-        case 41: case 44: case 45: return {32, 5};   // k_spmv4: 64 x 4 tile, S = 4 (44: S = 6, 45: S = 3), 4 CTAs/SM
+        case 41: case 44: case 45: case 46: case 47: return {32, 5};   // k_spmv4: 64 x 4 tile, S = 4 (44: S = 6, 45: S = 3), 4 CTAs/SM; 46 / 47: balanced split (S = 4 / 6)
         case 42: return {32, 9};   // k_spmv4: 64 x 8 tile, S = 3, 3 CTAs/SM
         case 43: return {32, 17};  // k_spmv4: 64 x 16 tile, S = 3, 1 CTA/SM
         case 50: case 51: case 53: case 54: case 55: case 56: return {32, 8};  // k_spmv5 (no staging, cache-resident slabs): 64 x 8 rows, 4 / 8 / 16 planes per thread
@@ -427,7 +427,7 @@ inline int tile_ctas_per_sm(int tile)
 {
     switch (tile)
     {
-        case 13: case 41: case 44: case 45: return 4;
+        case 13: case 41: case 44: case 45: case 46: case 47: return 4;
         case 18: case 30: case 32: case 40: return 2;
         case 0: return 2;
         case 43: return 1;
@@ -614,6 +614,18 @@ int launch_spmv3_cfg(b200ls_solver *h, const VecSet &v, int ghost_store)
     return B200LS_OK;
 }
 
+// k_spmv4<BAL>: CTAs and planes per CTA of the balanced split
+struct K4bCfg { int nctas, planes_per_cta; };
+inline K4bCfg k4b_config(const b200ls_solver *h, int ty, int ctas_per_sm)
+{
+    const int64_t ntiles = (int64_t)((h->g.nx + 63) / 64) * ((h->g.ny + ty - 1) / ty);
+    const int64_t total = ntiles * h->g.nzl;
+    int64_t nctas = std::min<int64_t>((int64_t)h->num_sms * ctas_per_sm, std::max<int64_t>(1, total / 8));
+    const int64_t ppc = (total + nctas - 1) / nctas;
+    nctas = (total + ppc - 1) / ppc;
+    return {(int)nctas, (int)ppc};
+}
+
 // ---- k_spmv4: tensor maps (one per vector and box shape, cached in the handle) and launch
 using TmaEncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -659,7 +671,7 @@ int tma_map_for(b200ls_solver *h, const double *vec, int bw, int bh, const TmaMa
     return B200LS_OK;
 }
 
-template <int TY, int S, int MINB, bool JAC>
+template <int TY, int S, int MINB, bool JAC, bool BAL = false>
 int launch_spmv4_cfg(b200ls_solver *h, const VecSet &v, int ghost_store, dim3 grid, int kz)
 {
     using L = Spmv4Smem<TY, S, JAC>;
@@ -675,14 +687,24 @@ int launch_spmv4_cfg(b200ls_solver *h, const VecSet &v, int ghost_store, dim3 gr
     maps.x = *m;
     if (JAC) TRY(tma_map_for(h, v.dinv, L::BW, L::BH, &m));
     maps.d = *m;  // without Jacobi: any valid map (never read)
-    auto kern = k_spmv4<TY, S, MINB, JAC>;
+    auto kern = k_spmv4<TY, S, MINB, JAC, BAL>;
     static bool attr_done = false;
     if (!attr_done)
     {
-        CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total(512)));
+        CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total(2048)));
         attr_done = true;
     }
-    CU(h, launch_k(h, h->in_loop && pdl_on(h), kern, grid, block, L::total(kz), maps, h->g, v, kz, h->ws, h->cm, h->d_state, kc,
+    int table = kz;
+    if (BAL)
+    {
+        // balanced split: one resident wave of CTAs, equal ranges of the linearised (tile, plane) space
+        if (h->g.nzl > 2048) return fail(h, B200LS_ERR_UNSUPPORTED, "balanced split: more than 2048 local planes");
+        const K4bCfg c = k4b_config(h, TY, MINB);
+        grid = dim3((unsigned)c.nctas);
+        kz = c.planes_per_cta;
+        table = h->g.nzl;
+    }
+    CU(h, launch_k(h, h->in_loop && pdl_on(h), kern, grid, block, L::total(table), maps, h->g, v, kz, h->ws, h->cm, h->d_state, kc,
                    h->d_hist, ghost_store));
     return B200LS_OK;
 }
@@ -726,6 +748,8 @@ int launch_spmv_t(b200ls_solver *h, const VecSet &v, int ghost_store)
         case 41: return launch_spmv4_cfg<4, 4, 4, JAC>(h, v, ghost_store, grid, kz);
         case 44: return launch_spmv4_cfg<4, 6, 4, JAC>(h, v, ghost_store, grid, kz);
         case 45: return launch_spmv4_cfg<4, 3, 4, JAC>(h, v, ghost_store, grid, kz);
+        case 46: return launch_spmv4_cfg<4, 4, 4, JAC, true>(h, v, ghost_store, grid, kz);
+        case 47: return launch_spmv4_cfg<4, 6, 4, JAC, true>(h, v, ghost_store, grid, kz);
         case 42: return launch_spmv4_cfg<8, 3, 3, JAC>(h, v, ghost_store, grid, kz);
         case 43: return launch_spmv4_cfg<16, 3, 1, JAC>(h, v, ghost_store, grid, kz);
         case 50: return launch_spmv5_cfg<8, 4, 2, JAC>(h, v, ghost_store, grid);

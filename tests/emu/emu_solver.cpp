@@ -150,18 +150,30 @@ inline TmaMap emu_tma_map(const GridDev &g, const double *vec, int bw, int bh)
     m.box[0] = bw; m.box[1] = bh; m.box[2] = 1;
     return m;
 }
-template <int TY, int S, int MINB, bool JAC>
+template <int TY, int S, int MINB, bool JAC, bool BAL = false>
 void launch_spmv4(const Problem &P, const VecSet &v, int kz, Ws &W, DevState *st, const SolveConsts &kc, double *hist, int ghost_store = 0)
 {
     using L = Spmv4Smem<TY, S, JAC>;
     const GridDev &g = P.g;
     dim3 grid((unsigned)((g.nx + 63) / 64), (unsigned)((g.ny + TY - 1) / TY), (unsigned)((g.nzl + kz - 1) / kz));
+    int table = kz;
+    if (BAL)
+    {
+        // `kz` is reused as the number of CTAs so that tests can force ranges that start mid-column and span columns;
+        // one CTA more than needed on purpose (a CTA without work still takes part in the grid reduction)
+        const long long total = (long long)grid.x * grid.y * g.nzl;
+        const int nctas = kz > 0 && kz < g.nzl ? kz : 3;
+        const int ppc = (int)((total + nctas - 1) / nctas);
+        grid = dim3((unsigned)((total + ppc - 1) / ppc) + 1);
+        kz = ppc;
+        table = g.nzl;
+    }
     Spmv4Maps maps;
     maps.r = emu_tma_map(g, v.r, L::BW, L::BH);
     maps.p = emu_tma_map(g, v.p_in, L::BW, L::BH);
     maps.x = emu_tma_map(g, v.x, L::BX, TY);
     maps.d = emu_tma_map(g, JAC ? v.dinv : v.r, L::BW, L::BH);
-    emu::launch(grid, dim3(32, TY + 1), L::total(kz), [&] { k_spmv4<TY, S, MINB, JAC>(maps, g, v, kz, W.ws, W.cm, st, kc, hist, ghost_store); });
+    emu::launch(grid, dim3(32, TY + 1), L::total(table), [&] { k_spmv4<TY, S, MINB, JAC, BAL>(maps, g, v, kz, W.ws, W.cm, st, kc, hist, ghost_store); });
 }
 
 template <bool JAC, bool APPLY>
@@ -188,6 +200,8 @@ void spmv(const Problem &P, int tile, const VecSet &v, int kz, Ws &W, DevState *
             if (tile == 40) return launch_spmv4<8, 4, 2, JAC>(P, v, kz, W, st, kc, hist);
             if (tile == 41) return launch_spmv4<4, 4, 4, JAC>(P, v, kz, W, st, kc, hist);
             if (tile == 42) return launch_spmv4<8, 3, 3, JAC>(P, v, kz, W, st, kc, hist);
+            if (tile == 46) return launch_spmv4<4, 4, 4, JAC, true>(P, v, kz, W, st, kc, hist);
+            if (tile == 47) return launch_spmv4<8, 3, 2, JAC, true>(P, v, kz, W, st, kc, hist);
             return launch_spmv4<16, 3, 1, JAC>(P, v, kz, W, st, kc, hist);
         }
         if (tile == 30) return launch_spmv3<12, 3, 2, JAC, false>(P, v, kz, W, st, kc, hist);

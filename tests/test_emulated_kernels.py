@@ -114,7 +114,7 @@ def test_emulated_cg_matches_oracle(emu, tile, pc):
         np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-9 * np.abs(ref.x).max())
 
 
-@pytest.mark.parametrize("tile", [40, 41, 42, 43, 50, 51, 52, 53])
+@pytest.mark.parametrize("tile", [40, 41, 42, 43, 46, 47, 50, 51, 52, 53])
 @pytest.mark.parametrize("pc", ["none", "jacobi"])
 def test_emulated_tma_kernel_matches_oracle(emu, tile, pc):
     """k_spmv4 (TMA boxes with zero fill outside the grid, mbarrier full/empty pipeline, neighbours' p rebuilt from the
@@ -140,7 +140,7 @@ def test_emulated_tma_kernel_does_not_depend_on_the_thread_schedule(emu):
     widths = H.make_widths(shape)
     A = H.oracle_matrix(widths, per)
     b, _ = H.consistent_rhs(A)
-    for tile in (40, 41):
+    for tile in (40, 41, 46):
         x0, h0, _, _, _ = _cg(emu, widths, per, b, pc="jacobi", max_it=6, tile=tile, kz=3)
         try:
             for seed in (1, 2, 3):
