@@ -409,6 +409,7 @@ inline TileCfg tile_dims(int tile)
         case 41: case 44: case 45: case 46: case 47: return {32, 5};   // k_spmv4: 64 x 4 tile, S = 4 (44: S = 6, 45: S = 3), 4 CTAs/SM; 46 / 47: balanced split (S = 4 / 6)
         case 42: return {32, 9};   // k_spmv4: 64 x 8 tile, S = 3, 3 CTAs/SM
         case 43: return {32, 17};  // k_spmv4: 64 x 16 tile, S = 3, 1 CTA/SM
+        case 48: case 49: return {32, 3};   // k_spmv4: 64 x 2 tile, S = 4 / 6, 6 CTAs/SM
         case 50: case 51: case 53: case 54: case 55: case 56: return {32, 8};  // k_spmv5 (no staging, cache-resident slabs): 64 x 8 rows, 4 / 8 / 16 planes per thread
         case 52: return {32, 4};                    // k_spmv5: 64 x 4 rows, 2 planes per thread
         default: return {32, 8};   // 10: 64 x 6 tile, S = 4, 3 CTAs/SM
@@ -431,6 +432,7 @@ inline int tile_ctas_per_sm(int tile)
         case 18: case 30: case 32: case 40: return 2;
         case 0: return 2;
         case 43: return 1;
+        case 48: case 49: return 6;
         default: return 3;
     }
 }
@@ -749,6 +751,8 @@ int launch_spmv_t(b200ls_solver *h, const VecSet &v, int ghost_store)
         case 44: return launch_spmv4_cfg<4, 6, 4, JAC>(h, v, ghost_store, grid, kz);
         case 45: return launch_spmv4_cfg<4, 3, 4, JAC>(h, v, ghost_store, grid, kz);
         case 46: return launch_spmv4_cfg<4, 4, 4, JAC, true>(h, v, ghost_store, grid, kz);
+        case 48: return launch_spmv4_cfg<2, 4, 6, JAC>(h, v, ghost_store, grid, kz);
+        case 49: return launch_spmv4_cfg<2, 6, 6, JAC>(h, v, ghost_store, grid, kz);
         case 47: return launch_spmv4_cfg<4, 6, 4, JAC, true>(h, v, ghost_store, grid, kz);
         case 42: return launch_spmv4_cfg<8, 3, 3, JAC>(h, v, ghost_store, grid, kz);
         case 43: return launch_spmv4_cfg<16, 3, 1, JAC>(h, v, ghost_store, grid, kz);
