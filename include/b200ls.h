@@ -146,12 +146,14 @@ int b200ls_destroy(b200ls_solver *h);
 const char *b200ls_last_error(const b200ls_solver *h);
 int b200ls_set_options(b200ls_solver *h, const b200ls_options *opts);
 int b200ls_get_options(const b200ls_solver *h, b200ls_options *opts);
-/* Launch-configuration knobs for experiments: "kz_chunk" (z planes per CTA of the SpMV kernel,
- * 0 = auto), "upd_blocks" (grid of the update kernel, 0 = auto), "tile" (SpMV tile variant),
- * "use_graph" (CUDA-graph the iteration batches, default 1), "mg_graph" / "csr_graph" (the same for pc_type mg / the
- * assembled-operator paths, default 0),
- * "mg_tail" (coarse levels of the multigrid cycle as one launch, default 0), "mg_fuse" (the residual update and the
- * reduction of the preconditioned CG loop folded into the first / last fine-level step of the cycle, default 0). */
+/* Launch-configuration knobs for experiments: "kz_chunk" (z planes per CTA of the fused SpMV
+ * kernel, 0 = auto), "upd_blocks" (grid of the update kernel, 0 = auto), "tile" (fused SpMV variant: -1 = auto -- the TMA
+ * kernel on non-periodic grids without Jacobi, the cp.async kernel otherwise; 10..18 cp.async tiles, 40..49 TMA variants,
+ * 50..56 staging-free variants), "upd_variant", "upd_reverse", "use_graph" / "use_pdl" (CUDA-graph batches and programmatic
+ * dependent launch of the CG loop, default 1), "csr_graph" (the same for the assembled-operator paths, default 0),
+ * "mg_graph", "mg_tail" (coarse levels of the multigrid cycle as one launch), "mg_fuse" (residual update and reduction of
+ * the preconditioned CG loop folded into the first / last fine-level step of the cycle): default 1 since round 2.
+ * On several GPUs the keys must be set to the same values on every rank. */
 int b200ls_set_tuning(b200ls_solver *h, const char *key, int value);
 
 /* ---- multi-GPU communicator (one process per GPU; z-slab partition of the DMDA grid) ----
