@@ -103,6 +103,31 @@ def test_c2_128cubed_and_headline_256cubed_against_the_oracle(pb, pc, n, nit):
     s.destroy()
 
 
+def test_large_ragged_stretched_grid_on_the_default_kernel(pb):
+    """Out-of-L2 grid whose extents are not multiples of the tile (300 x 290 x 130, stretched): the launch-shape model
+    picks the TMA kernel with several z chunks (ragged last tiles in x and y, ragged last chunk) -- bit-exact SpMV and the
+    first 25 residual norms against the oracle."""
+    n = (300, 290, 130)
+    widths = H.make_widths(n)
+    A = orc.assemble_dbng(widths, (0, 0, 0), 0.01, literal=False)
+    b, xs = H.consistent_rhs(A)
+    nit = 25
+    orc.set_fast(True, 0)
+    ref = orc.ksp_solve(A, b, rtol=0.0, atol=0.0, max_it=nit, const_nullspace=True)
+    orc.set_fast(False, 0)
+    s = pb.LinSolverB200("poisson", "None")
+    s.setOptions(rtol=0.0, atol=0.0, max_it=nit)
+    s.setStencil(H.grid_of(widths, (0, 0, 0)))
+    s.setNullSpace(True)
+    assert np.array_equal(s.apply(xs), b)
+    x = np.empty_like(b)
+    with pytest.raises(pb.B200Error):
+        s.solve(x, b)
+    np.testing.assert_allclose(s.getHistory(), ref.history, rtol=1e-10)
+    np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-9 * np.abs(ref.x).max())
+    s.destroy()
+
+
 def test_c3_ibpm_sized_modified_poisson(pb):
     """450 x 450 stretched grid + 158 Lagrangian points x 2 force components."""
     sub = [{"end": -0.75, "cells": 125, "stretchRatio": 1.0 / 1.02}, {"end": 0.75, "cells": 200, "stretchRatio": 1.0},
