@@ -663,9 +663,12 @@ int tma_map_for(b200ls_solver *h, const double *vec, int bw, int bh, const TmaMa
         const cuuint64_t strides[2] = {(cuuint64_t)h->g.px * 8, (cuuint64_t)h->g.plane * 8};
         const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
         const cuuint32_t estr[3] = {1, 1, 1};
+        // L2 promotion of the box rows (experiment knob B200LS_TMA_L2 = 0 none / 1 64 B / 2 128 B / 3 256 B; default 256 B)
+        static const int l2p = getenv("B200LS_TMA_L2") ? atoi(getenv("B200LS_TMA_L2")) : 3;
+        const CUtensorMapL2promotion prom = l2p == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : l2p == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                            : l2p == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
         const CUresult rc = enc(&m.m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)vec, dims, strides, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, prom, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (rc != CUDA_SUCCESS) return fail(h, B200LS_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d (box %d x %d)", (int)rc, bw, bh);
         it = h->tma_maps.emplace(key, m).first;
     }
