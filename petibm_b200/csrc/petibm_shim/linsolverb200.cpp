@@ -180,6 +180,7 @@ PetscErrorCode LinSolverB200::setMatrix(const Mat &A)
         // the previous matrix was solved as replicas on a single-rank handle: back to a distributed one
         ierr = newHandle(true); CHKERRQ(ierr);
         replicated = false;
+        mgReplica = false;
     }
     if (haveGrid && nranks == 1)
     {
@@ -209,15 +210,28 @@ PetscErrorCode LinSolverB200::setMatrix(const Mat &A)
         B200CHK(handle, b200ls_repart_candidates((int)gdim, gn, nranks, sizes.data(), cands.data(), 64, &found));
         if (found > 64) found = 64;
         const int64_t nslow = (gdim == 3) ? gn[2] : gn[1];
+        mgReplica = false;
         if (found > 0 && nslow >= nranks)
         {
-            // a second setMatrix replaces the exchange arena: drop the peer mappings everywhere first
-            B200CHK(handle, b200ls_comm_disconnect(handle));
-            ierr = MPI_Barrier(PETSC_COMM_WORLD); CHKERRQ(ierr);
             const int64_t base = nslow / nranks, rem = nslow % nranks;
             const int64_t lo = rank * base + (rank < rem ? rank : rem), hi = lo + base + (rank < rem ? 1 : 0);
-            B200CHK(handle, b200ls_set_poisson_stencil(handle, (int)gdim, gn, gper, gdL[0].data(), gdL[1].data(),
-                                                       gdim == 3 ? gdL[2].data() : nullptr, gdt, lo, hi));
+            if (savedOpts.pc_type == B200LS_PC_MG)
+            {
+                // the multigrid preconditioner runs on one GPU: a single-rank handle with the whole grid on every rank
+                ierr = newHandle(false); CHKERRQ(ierr);
+                replicated = true;   // (the handle is single-rank: a later setMatrix re-creates the distributed one)
+                mgReplica = true;
+                B200CHK(handle, b200ls_set_poisson_stencil(handle, (int)gdim, gn, gper, gdL[0].data(), gdL[1].data(),
+                                                           gdim == 3 ? gdL[2].data() : nullptr, gdt, 0, gdim == 3 ? gn[2] : 1));
+            }
+            else
+            {
+                // a second setMatrix replaces the exchange arena: drop the peer mappings everywhere first
+                B200CHK(handle, b200ls_comm_disconnect(handle));
+                ierr = MPI_Barrier(PETSC_COMM_WORLD); CHKERRQ(ierr);
+                B200CHK(handle, b200ls_set_poisson_stencil(handle, (int)gdim, gn, gper, gdL[0].data(), gdL[1].data(),
+                                                           gdim == 3 ? gdL[2].data() : nullptr, gdt, lo, hi));
+            }
             std::vector<int64_t> natRows((size_t)nloc);
             std::vector<int32_t> natCols(col.size());
             for (int c = 0; c < found && !recognised; ++c)
@@ -249,11 +263,14 @@ PetscErrorCode LinSolverB200::setMatrix(const Mat &A)
         opKind = "stencil";
         if (nranks > 1)
         {
-            // exchange the CUDA IPC handles of the exchange arenas: MPI is the host transport only
-            std::vector<char> mine(64), all((size_t)64 * nranks);
-            B200CHK(handle, b200ls_comm_export(handle, mine.data()));
-            ierr = MPI_Allgather(mine.data(), 64, MPI_BYTE, all.data(), 64, MPI_BYTE, PETSC_COMM_WORLD); CHKERRQ(ierr);
-            B200CHK(handle, b200ls_comm_connect(handle, all.data(), nranks));
+            if (!mgReplica)
+            {
+                // exchange the CUDA IPC handles of the exchange arenas: MPI is the host transport only
+                std::vector<char> mine(64), all((size_t)64 * nranks);
+                B200CHK(handle, b200ls_comm_export(handle, mine.data()));
+                ierr = MPI_Allgather(mine.data(), 64, MPI_BYTE, all.data(), 64, MPI_BYTE, PETSC_COMM_WORLD); CHKERRQ(ierr);
+                B200CHK(handle, b200ls_comm_connect(handle, all.data(), nranks));
+            }
             // box <-> slab exchange of solve(): counts/displacements for MPI_Alltoallv and the slab-side buffers
             int identity = 1;
             int64_t nslab = 0;
@@ -272,11 +289,32 @@ PetscErrorCode LinSolverB200::setMatrix(const Mat &A)
                     xcounts[q][(size_t)r] = (PetscMPIInt)c64[q][(size_t)r];
                 }
             }
-            if (!planIdentity)
+            if (!planIdentity || mgReplica)
             {
                 xbuf.assign((size_t)nslab, 0.0);
                 bslab.assign((size_t)nslab, 0.0);
                 xslab.assign((size_t)nslab, 0.0);
+            }
+            if (mgReplica)
+            {
+                // slab sizes of all ranks (rank order = natural ordering) for the all-gather of b in solve()
+                const long long mineSlab = (long long)nslab;
+                std::vector<long long> allSlab((size_t)nranks);
+                ierr = MPI_Allgather(&mineSlab, (int)sizeof(long long), MPI_BYTE, allSlab.data(), (int)sizeof(long long), MPI_BYTE,
+                                     PETSC_COMM_WORLD); CHKERRQ(ierr);
+                repCounts.assign((size_t)nranks, 0);
+                repDispls.assign((size_t)nranks, 0);
+                long long tot = 0;
+                for (int r = 0; r < nranks; ++r)
+                {
+                    if (allSlab[(size_t)r] > 2147483647LL || tot > 2147483647LL)
+                        SETERRQ(PETSC_COMM_WORLD, PETSC_ERR_SUP, "B200 linear solver: replicated grid exceeds the MPI count range.");
+                    repCounts[(size_t)r] = (PetscMPIInt)allSlab[(size_t)r];
+                    repDispls[(size_t)r] = (PetscMPIInt)tot;
+                    tot += allSlab[(size_t)r];
+                }
+                repB.assign((size_t)tot, 0.0);
+                repX.assign((size_t)tot, 0.0);
             }
         }
     }
@@ -324,6 +362,7 @@ PetscErrorCode LinSolverB200::setMatrix(const Mat &A)
             nlocRows = rowsTotal;
             ierr = newHandle(false); CHKERRQ(ierr);
             replicated = true;
+            mgReplica = false;
             repB.assign((size_t)rowsTotal, 0.0);
             repX.assign((size_t)rowsTotal, 0.0);
         }
@@ -418,7 +457,34 @@ PetscErrorCode LinSolverB200::solve(Vec &x, Vec &b)
     ierr = VecGetArrayRead(b, &barr); CHKERRQ(ierr);
     ierr = VecGetArray(x, &xarr); CHKERRQ(ierr);
     int rc;
-    if (replicated)
+    if (mgReplica)
+    {
+        // DMDA boxes -> slabs (if needed), all-gather the slabs, solve the whole grid on this GPU, own slab -> boxes
+        const double *bs = barr;
+        if (plan && !planIdentity)
+        {
+            ierr = MPI_Alltoallv(barr, xcounts[0].data(), xcounts[1].data(), MPI_DOUBLE, xbuf.data(), xcounts[2].data(),
+                                 xcounts[3].data(), MPI_DOUBLE, PETSC_COMM_WORLD); CHKERRQ(ierr);
+            B200CHK(handle, b200ls_repart_unpack_slab(plan, xbuf.data(), bslab.data()));
+            bs = bslab.data();
+        }
+        ierr = MPI_Allgatherv(bs, repCounts[(size_t)rank], MPI_DOUBLE, repB.data(), repCounts.data(), repDispls.data(),
+                              MPI_DOUBLE, PETSC_COMM_WORLD); CHKERRQ(ierr);
+        rc = b200ls_solve(handle, repB.data(), repX.data());
+        if (rc == B200LS_OK || rc == B200LS_ERR_DIVERGED)
+        {
+            const double *xs = repX.data() + repDispls[(size_t)rank];
+            if (plan && !planIdentity)
+            {
+                B200CHK(handle, b200ls_repart_pack_slab(plan, xs, xbuf.data()));
+                ierr = MPI_Alltoallv(xbuf.data(), xcounts[2].data(), xcounts[3].data(), MPI_DOUBLE, xarr, xcounts[0].data(),
+                                     xcounts[1].data(), MPI_DOUBLE, PETSC_COMM_WORLD); CHKERRQ(ierr);
+            }
+            else
+                std::memcpy(xarr, xs, sizeof(double) * (size_t)repCounts[(size_t)rank]);
+        }
+    }
+    else if (replicated)
     {
         // every rank solves the whole system on its GPU: all-gather b, keep the own rows of x
         ierr = MPI_Allgatherv(barr, repCounts[(size_t)rank], MPI_DOUBLE, repB.data(), repCounts.data(), repDispls.data(),

@@ -78,6 +78,10 @@ protected:
     bool replicated = false;
     std::vector<PetscMPIInt> repCounts, repDispls;  // rows per rank / first row of every rank (MPI_Allgatherv)
     std::vector<double> repB, repX;
+    // several ranks and -pc_type mg: the multigrid preconditioner runs on one GPU, so every rank sets up the WHOLE grid and
+    // solves a replica; solve() moves b boxes -> slabs (plan), all-gathers the slabs (rank order = natural ordering) and
+    // keeps its own slab of x
+    bool mgReplica = false;
     b200ls_options savedOpts;                        // to re-create the handle (replica <-> distributed)
     PetscErrorCode newHandle(bool withComm);
 };  // LinSolverB200

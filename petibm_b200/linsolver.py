@@ -109,6 +109,8 @@ class LinSolverB200(LinSolverBase):
         self._repart = None    # box <-> slab exchange plan when the vectors arrive as DMDA boxes
         self._staggered = True # setMatrix may use the line-coefficient form for velocity / IBPM matrices
         self._replicated = None  # (row_lo, row_hi, nrows_global) when several ranks solve replicas of a general system
+        self._mg_rep = None      # (lo, hi, n) in natural ordering: several ranks, pc_type mg -> every rank solves the whole grid
+        self._handle_wired = comm is not None and comm.nranks > 1   # the C handle is wired to the communicator
         self.operator = None   # "stencil" | "hybrid" | "staggered" | "csr" after setMatrix
         if device is None:
             device = comm.device if comm is not None else 0
@@ -197,7 +199,27 @@ class LinSolverB200(LinSolverBase):
         w = [np.ascontiguousarray(a, dtype=np.float64) for a in grid.widths]
         dz = w[2].ctypes.data_as(_lib._dp) if grid.dim == 3 else None
         lo, hi = self._slab(grid)
-        if self._comm is not None and self._comm.nranks > 1:
+        multi = self._comm is not None and self._comm.nranks > 1
+        self._mg_rep = None
+        if multi and self.options().pc_type == _lib.PC_MG:
+            # The multigrid preconditioner runs on one GPU.  On several ranks every rank sets up the
+            # WHOLE grid on its own GPU and solves a bit-identical replica: solve() all-gathers b and keeps its own slab
+            # of x.  Functional, not scalable -- but one multigrid solve on one GPU (13.8 ms at 256^3) is shorter than the
+            # 500 plain CG iterations it replaces on eight.
+            if self._handle_wired:
+                self._new_handle(with_comm=False)
+            nslow = grid.n[2] if grid.dim == 3 else grid.n[1]
+            _lib.check(self._L.b200ls_set_poisson_stencil(
+                self._h, grid.dim, n, per, w[0].ctypes.data_as(_lib._dp), w[1].ctypes.data_as(_lib._dp), dz,
+                float(grid.dt), 0, nslow if grid.dim == 3 else 1), self._h)
+            plane = int(grid.n[0] * grid.n[1]) if grid.dim == 3 else int(grid.n[0])
+            self._mg_rep = (lo * plane, hi * plane, int(grid.size))
+            self.operator = "stencil"
+            self.nlocal = self._local_size(grid, lo, hi)
+            return
+        if multi and not self._handle_wired:
+            self._new_handle(with_comm=True)     # the previous operator was solved as replicas: distributed handle again
+        if multi:
             # replacing the operator frees the exchange arena: every rank first drops its mappings of the peers
             _lib.check(self._L.b200ls_comm_disconnect(self._h), self._h)
             self._comm.barrier()
@@ -341,6 +363,7 @@ class LinSolverB200(LinSolverBase):
         _lib.check(self._L.b200ls_set_options(self._h, C.byref(opts)), self._h)
         if with_comm:
             self._comm.init_solver(self)
+        self._handle_wired = bool(with_comm)
 
     def setMatrix(self, A: Mat):
         """LinSolverKSP::setMatrix (linsolverksp.cpp:72-82).  The matrix is copied/recognised here, the
@@ -352,7 +375,7 @@ class LinSolverB200(LinSolverBase):
         multi = self._comm is not None and self._comm.nranks > 1
         if multi and getattr(self, "_replicated", None) is not None:
             self._new_handle(with_comm=True)     # the previous matrix was solved as replicas: distributed handle again
-            self._replicated = None
+        self._replicated = None
         if self._grid is not None and multi:
             self._repart = self._verify_boxes(A)
             recognised = self._repart is not None
@@ -414,6 +437,26 @@ class LinSolverB200(LinSolverBase):
                 x[...] = xf[lo:hi].reshape(x.shape)
             _lib.check(rc, self._h)
             return x
+        mgr = getattr(self, "_mg_rep", None)
+        if mgr is not None:
+            # pc_type mg on several ranks: boxes -> slabs (if the vectors arrive as DMDA boxes), all-gather the slabs (rank
+            # order = natural ordering), solve the whole grid on this GPU, keep the own slab
+            lo, hi, ntot = mgr
+            rp = getattr(self, "_repart", None)
+            boxes = rp is not None and not rp.identity
+            if _is_torch_cuda(b) or _is_torch_cuda(x) or not isinstance(x, np.ndarray):
+                raise ValueError("vectors of a replicated solve are host numpy arrays")
+            bs = rp.box_to_slab(np.asarray(b, dtype=np.float64), self._comm.group) if boxes else np.ascontiguousarray(b, dtype=np.float64)
+            if bs.size != hi - lo:
+                raise ValueError("vector length does not match the operator")
+            bf = np.frombuffer(b"".join(self._comm.allgather_bytes(bs.tobytes())), dtype=np.float64).copy()
+            xf = np.empty(ntot, dtype=np.float64)
+            rc = self._L.b200ls_solve(self._h, C.c_void_p(bf.ctypes.data), C.c_void_p(xf.ctypes.data))
+            if rc in (_lib.OK, _lib.ERR_DIVERGED):
+                xs = np.ascontiguousarray(xf[lo:hi])
+                x[...] = (rp.slab_to_box(xs, self._comm.group) if boxes else xs).reshape(x.shape)
+            _lib.check(rc, self._h)
+            return x
         rp = getattr(self, "_repart", None)
         if rp is not None and not rp.identity:
             # the caller's vectors are DMDA boxes: one all-to-all into the solver's slabs and one back (what
@@ -457,6 +500,13 @@ class LinSolverB200(LinSolverBase):
     def apply(self, x):
         """y = A x through the device operator (tests)."""
         x = np.ascontiguousarray(x, dtype=np.float64)
+        mgr = getattr(self, "_mg_rep", None)
+        if mgr is not None:                      # replicated whole-grid operator: slab in, slab out
+            lo, hi, ntot = mgr
+            xf = np.frombuffer(b"".join(self._comm.allgather_bytes(x.tobytes())), dtype=np.float64).copy()
+            yf = np.empty(ntot, dtype=np.float64)
+            _lib.check(self._L.b200ls_apply(self._h, C.c_void_p(xf.ctypes.data), C.c_void_p(yf.ctypes.data)), self._h)
+            return np.ascontiguousarray(yf[lo:hi])
         y = np.empty_like(x)
         _lib.check(self._L.b200ls_apply(self._h, C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data)), self._h)
         return y

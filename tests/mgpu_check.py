@@ -201,6 +201,55 @@ def run_replicated_case(comm, kind):
     return allok
 
 
+def run_mg_case(comm, shape, per, procs=None):
+    """-poisson_pc_type mg on several ranks: every rank solves a replica of the whole grid on its GPU (all-gather of b, own
+    part of x back), for slab vectors and -- with `procs` -- for DMDA boxes through the box <-> slab exchange."""
+    dim = len(shape)
+    widths = H.make_widths(shape)
+    A = H.oracle_matrix(widths, per)
+    b, xs = H.consistent_rhs(A)
+    c = Comm(comm.rank, comm.nranks, comm.device, "p2p", "store")
+    s = pb.LinSolverB200("poisson", "None", comm=c, device=comm.device)
+    s.setOptions(pc_type="mg", rtol=1e-10, atol=1e-50, max_it=200)
+    msgs, ok = [], True
+    if procs is None:
+        s.setStencil(H.grid_of(widths, per))
+        s.setNullSpace(True)
+        bl = c.local_block(b, shape)
+        want = c.local_block(xs, shape)
+        yl = s.apply(c.local_block(xs, shape))
+        if not np.array_equal(yl, bl):
+            ok = False
+            msgs.append("replicated apply differs")
+    else:
+        Aloc, bl, plan = H.box_local_system(A, b, dim, shape, procs, comm.rank)
+        s.setGrid(H.grid_of(widths, per))
+        s.setMatrix(Aloc.setNullSpace(True))
+        want = xs[plan.box_rows()]
+        if s.operator != "stencil" or s._mg_rep is None:
+            ok = False
+            msgs.append(f"operator {s.operator}")
+    x = np.empty_like(bl)
+    s.solve(x, bl)
+    its = c.allgather_bytes((s.getIters(), s.getReason(), s.getHistory().tobytes()))
+    if any(t != its[0] for t in its) or s.getReason() != 2 or s.getIters() > 25:
+        ok = False
+        msgs.append(f"its/reason {[t[:2] for t in its]}")
+    # x is determined up to the constant: compare mean-free parts through the global mean of the gathered solution
+    xg = np.frombuffer(b"".join(c.allgather_bytes(np.ascontiguousarray(x).tobytes())), dtype=np.float64)
+    wg = np.frombuffer(b"".join(c.allgather_bytes(np.ascontiguousarray(want).tobytes())), dtype=np.float64)
+    err = np.abs((xg - xg.mean()) - (wg - wg.mean())).max()
+    if err > 1e-7 * np.abs(xs).max():
+        ok = False
+        msgs.append(f"x diff {err:.3e}")
+    s.destroy()
+    allok = all(c.allgather_bytes(ok))
+    if comm.rank == 0:
+        print(f"[{'PASS' if allok else 'FAIL'}] pc_type mg as replicas on {comm.nranks} ranks: shape {shape} per {per} "
+              f"{'slabs' if procs is None else 'process grid ' + str(procs)}, {its[0][0]} iterations {'; '.join(msgs)}", flush=True)
+    return allok
+
+
 def main():
     import torch
 
@@ -240,6 +289,11 @@ def main():
         if new_cases:
             allok &= run_replicated_case(comm, "velocity")
             allok &= run_replicated_case(comm, "ibpm")
+            allok &= run_mg_case(comm, (48, 40, 44), (0, 0, 0))
+            allok &= run_mg_case(comm, (40, 36), (0, 0))
+            boxes = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(comm.nranks)
+            if boxes:
+                allok &= run_mg_case(comm, (22, 18, 19), (0, 0, 0), boxes)
     comm.barrier()
     if comm.rank == 0:
         print("MGPU_CHECK", "PASS" if allok else "FAIL", flush=True)
