@@ -82,6 +82,48 @@ class Comm:
             return float(value)
         return max(float(v) for v in self.allgather_bytes(float(value)))
 
+    def allgather_f64(self, local: np.ndarray) -> np.ndarray:
+        """Concatenation (rank order) of every rank's float64 vector; the parts may differ in length.  Tensor all-gather of
+        torch.distributed (over NVLink with the nccl backend: the vector takes the GPU as a staging buffer; gloo on CPU)
+        instead of the pickling object path -- this is the per-solve transport of the replicated solves."""
+        local = np.ascontiguousarray(local, dtype=np.float64)
+        if self.nranks == 1:
+            return local.copy()
+        import torch
+        import torch.distributed as dist
+
+        sizes = [int(v) for v in self.allgather_bytes(int(local.size))]
+        m = max(sizes)
+        on_gpu = dist.get_backend(self.group) == "nccl"
+        dev = torch.device("cuda", self.device) if on_gpu else torch.device("cpu")
+        mine = torch.zeros(m, dtype=torch.float64, device=dev)
+        mine[: local.size] = torch.from_numpy(local).to(dev)
+        out = torch.empty(m * self.nranks, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, mine, group=self.group)
+        out = out.cpu().numpy().reshape(self.nranks, m)
+        return np.concatenate([out[r, : sizes[r]] for r in range(self.nranks)])
+
+    def allgather_f64_device(self, local: np.ndarray):
+        """allgather_f64 that leaves the concatenated vector ON THE GPU (a CUDA float64 tensor), for solvers that take device
+        pointers: one H2D copy of the local part, the all-gather over NVLink, no host round trip.  nccl backend only;
+        returns None otherwise."""
+        import torch
+        import torch.distributed as dist
+
+        if self.nranks == 1 or dist.get_backend(self.group) != "nccl":
+            return None
+        local = np.ascontiguousarray(local, dtype=np.float64)
+        sizes = [int(v) for v in self.allgather_bytes(int(local.size))]
+        m = max(sizes)
+        dev = torch.device("cuda", self.device)
+        mine = torch.zeros(m, dtype=torch.float64, device=dev)
+        mine[: local.size] = torch.from_numpy(local).to(dev)
+        out = torch.empty(m * self.nranks, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, mine, group=self.group)
+        if all(sz == m for sz in sizes):
+            return out
+        return torch.cat([out[r * m: r * m + sizes[r]] for r in range(self.nranks)])
+
     def gather_matrix(self, nrows, indptr, indices, data, has_const=False, null_vecs=None):
         """All-gathers a row-distributed CSR matrix (global column indices) and its explicit null-space vectors: every
         rank receives the whole system -- the replicated solve of general systems on several ranks (LinSolverB200).

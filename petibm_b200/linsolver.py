@@ -420,6 +420,24 @@ class LinSolverB200(LinSolverBase):
         _lib.check(self._L.b200ls_set_nullspace(self._h, int(bool(has_const)), nv,
                                                 arr.ctypes.data_as(_lib._dp) if nv else None), self._h)
 
+    def _solve_gathered(self, b_local: np.ndarray, lo: int, hi: int, ntot: int):
+        """Replicated solves: all-gather b, solve the whole system on this GPU, return (rc, own part of x).  With the nccl
+        backend the gathered vector and the solution stay on the device (H2D of the local part, all-gather over NVLink,
+        b200ls_solve_device, D2H of the own part only); otherwise through host buffers."""
+        bd = self._comm.allgather_f64_device(b_local)
+        if bd is not None:
+            import torch
+
+            xd = torch.empty(ntot, dtype=torch.float64, device=bd.device)
+            torch.cuda.current_stream(bd.device).synchronize()
+            rc = self._L.b200ls_solve_device(self._h, C.c_void_p(bd.data_ptr()), C.c_void_p(xd.data_ptr()))
+            self._sync_stream(bd.device)
+            return rc, xd[lo:hi].cpu().numpy()
+        bf = self._comm.allgather_f64(b_local)
+        xf = np.empty(ntot, dtype=np.float64)
+        rc = self._L.b200ls_solve(self._h, C.c_void_p(bf.ctypes.data), C.c_void_p(xf.ctypes.data))
+        return rc, np.ascontiguousarray(xf[lo:hi])
+
     # ---- LinSolverKSP::solve (linsolverksp.cpp:85-105): zero initial guess, error if reason < 0
     def solve(self, x, b):
         rep = getattr(self, "_replicated", None)
@@ -429,12 +447,9 @@ class LinSolverB200(LinSolverBase):
                 raise ValueError("vectors of a replicated solve are host numpy arrays")
             if np.size(b) != hi - lo or x.size != hi - lo:
                 raise ValueError("vector length does not match the operator")
-            bf = np.frombuffer(b"".join(self._comm.allgather_bytes(np.ascontiguousarray(b, dtype=np.float64).tobytes())),
-                               dtype=np.float64).copy()
-            xf = np.empty(ntot, dtype=np.float64)
-            rc = self._L.b200ls_solve(self._h, C.c_void_p(bf.ctypes.data), C.c_void_p(xf.ctypes.data))
+            rc, xs = self._solve_gathered(np.ascontiguousarray(b, dtype=np.float64), lo, hi, ntot)
             if rc in (_lib.OK, _lib.ERR_DIVERGED):
-                x[...] = xf[lo:hi].reshape(x.shape)
+                x[...] = xs.reshape(x.shape)
             _lib.check(rc, self._h)
             return x
         mgr = getattr(self, "_mg_rep", None)
@@ -449,11 +464,8 @@ class LinSolverB200(LinSolverBase):
             bs = rp.box_to_slab(np.asarray(b, dtype=np.float64), self._comm.group) if boxes else np.ascontiguousarray(b, dtype=np.float64)
             if bs.size != hi - lo:
                 raise ValueError("vector length does not match the operator")
-            bf = np.frombuffer(b"".join(self._comm.allgather_bytes(bs.tobytes())), dtype=np.float64).copy()
-            xf = np.empty(ntot, dtype=np.float64)
-            rc = self._L.b200ls_solve(self._h, C.c_void_p(bf.ctypes.data), C.c_void_p(xf.ctypes.data))
+            rc, xs = self._solve_gathered(bs, lo, hi, ntot)
             if rc in (_lib.OK, _lib.ERR_DIVERGED):
-                xs = np.ascontiguousarray(xf[lo:hi])
                 x[...] = (rp.slab_to_box(xs, self._comm.group) if boxes else xs).reshape(x.shape)
             _lib.check(rc, self._h)
             return x
@@ -503,7 +515,7 @@ class LinSolverB200(LinSolverBase):
         mgr = getattr(self, "_mg_rep", None)
         if mgr is not None:                      # replicated whole-grid operator: slab in, slab out
             lo, hi, ntot = mgr
-            xf = np.frombuffer(b"".join(self._comm.allgather_bytes(x.tobytes())), dtype=np.float64).copy()
+            xf = self._comm.allgather_f64(x)
             yf = np.empty(ntot, dtype=np.float64)
             _lib.check(self._L.b200ls_apply(self._h, C.c_void_p(xf.ctypes.data), C.c_void_p(yf.ctypes.data)), self._h)
             return np.ascontiguousarray(yf[lo:hi])

@@ -62,6 +62,8 @@ def main():
     assert np.array_equal(offs, cuts) and not hc
     assert np.array_equal(ip, M.indptr) and np.array_equal(ix, M.indices) and np.array_equal(dv, M.data)
     assert nv.shape == (1, ntot) and np.array_equal(nv[0], vec)
+    # the per-solve transport of the replicated solves: uneven float64 parts, rank order
+    assert np.array_equal(comm.allgather_f64(vec[cuts[comm.rank]: cuts[comm.rank + 1]]), vec)
     comm.barrier()
     import torch.distributed as dist
 
