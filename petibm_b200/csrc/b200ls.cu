@@ -410,12 +410,14 @@ inline TileCfg tile_dims(int tile)
         case 42: return {32, 9};   // k_spmv4: 64 x 8 tile, S = 3, 3 CTAs/SM
         case 43: return {32, 17};  // k_spmv4: 64 x 16 tile, S = 3, 1 CTA/SM
         case 48: case 49: return {32, 3};   // k_spmv4: 64 x 2 tile, S = 4 / 6, 6 CTAs/SM
+        case 60: case 61: return {32, 7};   // k_spmv4: 64 x 6 tile, S = 4 / 3, 3 CTAs/SM
+        case 62: return {32, 6};            // k_spmv4: 64 x 5 tile, S = 4, 3 CTAs/SM
         case 50: case 51: case 53: case 54: case 55: case 56: return {32, 8};  // k_spmv5 (no staging, cache-resident slabs): 64 x 8 rows, 4 / 8 / 16 planes per thread
         case 52: return {32, 4};                    // k_spmv5: 64 x 4 rows, 2 planes per thread
         default: return {32, 8};   // 10: 64 x 6 tile, S = 4, 3 CTAs/SM
     }
 }
-inline bool tile_is_tma(int tile) { return tile >= 40 && tile < 50; }
+inline bool tile_is_tma(int tile) { return (tile >= 40 && tile < 50) || (tile >= 60 && tile < 70); }
 inline bool tile_is_direct(int tile) { return tile >= 50 && tile < 60; }
 inline int tile_direct_planes(int tile) { return (tile == 50 || tile == 54 || tile == 56) ? 4 : (tile == 51 || tile == 55) ? 8 : tile == 52 ? 2 : 16; }
 // rows of a tile that produce results
@@ -433,6 +435,7 @@ inline int tile_ctas_per_sm(int tile)
         case 0: return 2;
         case 43: return 1;
         case 48: case 49: return 6;
+        case 60: case 61: case 62: return 3;
         default: return 3;
     }
 }
@@ -755,6 +758,9 @@ int launch_spmv_t(b200ls_solver *h, const VecSet &v, int ghost_store)
         case 45: return launch_spmv4_cfg<4, 3, 4, JAC>(h, v, ghost_store, grid, kz);
         case 46: return launch_spmv4_cfg<4, 4, 4, JAC, true>(h, v, ghost_store, grid, kz);
         case 48: return launch_spmv4_cfg<2, 4, 6, JAC>(h, v, ghost_store, grid, kz);
+        case 60: return launch_spmv4_cfg<6, 4, 3, JAC>(h, v, ghost_store, grid, kz);
+        case 61: return launch_spmv4_cfg<6, 3, 3, JAC>(h, v, ghost_store, grid, kz);
+        case 62: return launch_spmv4_cfg<5, 4, 3, JAC>(h, v, ghost_store, grid, kz);
         case 49: return launch_spmv4_cfg<2, 6, 6, JAC>(h, v, ghost_store, grid, kz);
         case 47: return launch_spmv4_cfg<4, 6, 4, JAC, true>(h, v, ghost_store, grid, kz);
         case 42: return launch_spmv4_cfg<8, 3, 3, JAC>(h, v, ghost_store, grid, kz);

@@ -195,8 +195,10 @@ void spmv(const Problem &P, int tile, const VecSet &v, int kz, Ws &W, DevState *
             if (tile == 52) return run(std::integral_constant<int, 4>{}, std::integral_constant<int, 2>{});
             return run(std::integral_constant<int, 8>{}, std::integral_constant<int, 16>{});
         }
-        if (tile >= 40 && tile < 50 && !periodic)
+        if (((tile >= 40 && tile < 50) || (tile >= 60 && tile < 70)) && !periodic)
         {
+            if (tile == 60) return launch_spmv4<6, 4, 3, JAC>(P, v, kz, W, st, kc, hist);
+            if (tile == 62) return launch_spmv4<5, 4, 3, JAC>(P, v, kz, W, st, kc, hist);
             if (tile == 40) return launch_spmv4<8, 4, 2, JAC>(P, v, kz, W, st, kc, hist);
             if (tile == 41) return launch_spmv4<4, 4, 4, JAC>(P, v, kz, W, st, kc, hist);
             if (tile == 42) return launch_spmv4<8, 3, 3, JAC>(P, v, kz, W, st, kc, hist);
@@ -297,7 +299,7 @@ EMU_API int emu_stencil_cg(int dim, const int64_t *n, const int *per, const doub
     DevState st{};
     emu::launch(dim3(1), dim3(32), 0, [&] { k_state_reset(&st); });
     emu::launch(dim3(4), dim3(256), 0, [&] { k_scatter(P.g, b, r.data(), x.data()); });
-    if (kz <= 0 && (tile < 30 || tile >= 40)) kz = P.g.nzl;
+    if (kz <= 0 && (tile < 30 || tile >= 40)) kz = P.g.nzl;  // (tile 46 / 47 reuse kz as the CTA count)
     if (upd_blocks <= 0) upd_blocks = 3;
     UpdVecs uv{r.data(), w.data(), jacobi ? dinv.data() : nullptr, upd_reverse};
     if (has_const)

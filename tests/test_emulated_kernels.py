@@ -114,7 +114,7 @@ def test_emulated_cg_matches_oracle(emu, tile, pc):
         np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-9 * np.abs(ref.x).max())
 
 
-@pytest.mark.parametrize("tile", [40, 41, 42, 43, 46, 47, 50, 51, 52, 53])
+@pytest.mark.parametrize("tile", [40, 41, 42, 43, 46, 47, 50, 51, 52, 53, 60, 62])
 @pytest.mark.parametrize("pc", ["none", "jacobi"])
 def test_emulated_tma_kernel_matches_oracle(emu, tile, pc):
     """k_spmv4 (TMA boxes with zero fill outside the grid, mbarrier full/empty pipeline, neighbours' p rebuilt from the
