@@ -45,7 +45,10 @@ struct Spmv4Maps
 // BAL = true ("balanced split"): a 1-D grid of resident CTAs; the (tile, plane) space is linearised tile-major and cut into
 // equal ranges of kz_chunk planes, so a CTA finishes the tail of one tile column and continues with the head of the next.
 // The producer keeps the ring full across the switch (no drain / fill bubble between work items, no partial last wave);
-// every segment costs its two halo planes again.
+// every segment costs its two halo planes again.  MEASURED: 40 % slower than the regular grid (206 against 147 us at 256^3) --
+// in the regular grid neighbouring tiles march through the same planes at the same time, so their shared halo rows (59 % of
+// the r / p' bytes of a 64 x 4 tile) are L2 hits; here every CTA is at a different plane and they come from DRAM again.
+// Kept as tile ids 46 / 47 for the record.
 template <int TY, int S, int MINB, bool JACOBI, bool BAL>
 __global__ void __launch_bounds__(32 * (TY + 1), MINB)
     k_spmv4(const __grid_constant__ Spmv4Maps maps, GridDev g, VecSet v, int kz_chunk, ReduceWs ws, CommDev cm, DevState *st,
