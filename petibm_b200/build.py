@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200ls.so")
 SOURCES = ["b200ls.cu", "repart.cpp", "staggered.cpp"]
-DEPS = ["b200ls.cu", "repart.cpp", "staggered.cpp", "sep_kernels.cuh", "sep_solver.inc", "mg_kernels.cuh", "mg_schedule.h", "mg_solver.inc", "ops_kernels.cuh", "ops_solver.inc", "dense_kernels.cuh", "dense_solver.inc", "kernels.cuh", "spmv2.cuh", "spmv3.cuh", "spmv4.cuh", "spmv5.cuh", "update_fly.cuh", "hw.cuh", "csr_kernels.cuh", "csr_solver.inc", os.path.join("..", "..", "include", "b200ls.h")]
+DEPS = ["b200ls.cu", "repart.cpp", "staggered.cpp", "sep_kernels.cuh", "sep_tile.cuh", "sep_solver.inc", "mg_kernels.cuh", "mg_schedule.h", "mg_solver.inc", "ops_kernels.cuh", "ops_solver.inc", "dense_kernels.cuh", "dense_solver.inc", "kernels.cuh", "spmv2.cuh", "spmv3.cuh", "spmv4.cuh", "spmv5.cuh", "update_fly.cuh", "hw.cuh", "csr_kernels.cuh", "csr_solver.inc", os.path.join("..", "..", "include", "b200ls.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

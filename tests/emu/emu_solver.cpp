@@ -14,6 +14,7 @@
 #include "update_fly.cuh"
 #include "csr_kernels.cuh"
 #include "sep_kernels.cuh"
+#include "sep_tile.cuh"
 #include "mg_kernels.cuh"
 #include "ops_kernels.cuh"
 #include "dense_kernels.cuh"
@@ -541,6 +542,16 @@ EMU_API int emu_csr_solve(int64_t n, const int64_t *rowptr, const int32_t *col, 
 }  // extern "C"
 
 namespace {
+// tiled kernels of sep_tile.cuh instead of the row-per-thread ones: 0 = off, 2 / 4 = tile of 64 / 128 cells in x
+int g_sep_xr = 0, g_sep_zchunk = 0, g_sep_target = 0;
+}  // namespace
+extern "C" EMU_API void emu_set_sep_tile(int xr, int zchunk, int target_blocks)
+{
+    g_sep_xr = xr;
+    g_sep_zchunk = zchunk;
+    g_sep_target = target_blocks;
+}
+namespace {
 SepDev make_sep(int nfields, const int64_t *dims, const int *periodic, const double *widths, int64_t n, const double *coef,
                 const double *diag, const int64_t *rem_rowptr, const int32_t *rem_col, const double *rem_val)
 {
@@ -600,9 +611,19 @@ EMU_API int emu_sep_solve(int nfields, const int64_t *dims, const int *periodic,
     Ws W;
     const SepDev A = make_sep(nfields, dims, periodic, widths, n, coef, diag, rem_rowptr, rem_col, rem_val);
     const int blocks = 3;
+    // the tiled kernels (sep_solver.inc: sep_tile_xr): grid and plan as on the device
+    const int xr = g_sep_xr;
+    const bool hyb = widths != nullptr;
+    const SepTilePlan T = sep_tile_plan(A, xr ? xr : 2, g_sep_zchunk, g_sep_target > 0 ? g_sep_target : 24);
+    const dim3 tgrid((unsigned)T.blocks());
+    const size_t tsmem = sep_tile_smem_bytes(xr ? xr : 2);
     if (mode == 0)
     {
-        emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_apply(A, b, x_out); });
+        if (xr == 2 && hyb) emu::launch(tgrid, dim3(256), tsmem, [&] { k_sep_tile_apply<2, true>(A, T, b, x_out); });
+        else if (xr == 2) emu::launch(tgrid, dim3(256), tsmem, [&] { k_sep_tile_apply<2, false>(A, T, b, x_out); });
+        else if (xr == 4 && hyb) emu::launch(tgrid, dim3(256), tsmem, [&] { k_sep_tile_apply<4, true>(A, T, b, x_out); });
+        else if (xr == 4) emu::launch(tgrid, dim3(256), tsmem, [&] { k_sep_tile_apply<4, false>(A, T, b, x_out); });
+        else emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_apply(A, b, x_out); });
         return 0;
     }
     SolveConsts kc{};
@@ -612,7 +633,27 @@ EMU_API int emu_sep_solve(int nfields, const int64_t *dims, const int *periodic,
     emu::launch(dim3(1), dim3(32), 0, [&] { k_state_reset(&st); });
     std::vector<double> r((size_t)n), p0((size_t)n, 0.0), p1((size_t)n, 0.0), w((size_t)n, 0.0), x((size_t)n, 0.0);
     const double *dv = jacobi ? dinv_in : nullptr;
-    if (mode == 2)
+    if (mode == 2 && xr && !hyb)
+    {
+        std::vector<double> rp((size_t)n), vv((size_t)n), s((size_t)n), t((size_t)n);
+        if (jacobi) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_init<true>(n, b, dv, r.data(), rp.data(), p0.data(), vv.data(), W.ws, &st, kc, hist); });
+        else emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_init<false>(n, b, dv, r.data(), rp.data(), p0.data(), vv.data(), W.ws, &st, kc, hist); });
+        for (int it = 0; it < max_it + 2 && !st.done; ++it)
+        {
+            emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_p(n, r.data(), vv.data(), p0.data(), &st); });
+#define EMU_T1(XR, JAC) emu::launch(tgrid, dim3(256), tsmem, [&] { k_sep_tile_bcgs_spmv1<XR, JAC>(A, T, p0.data(), dv, rp.data(), vv.data(), W.ws, &st, kc, hist); })
+#define EMU_T2(XR, JAC) emu::launch(tgrid, dim3(256), tsmem, [&] { k_sep_tile_bcgs_spmv2<XR, JAC>(A, T, r.data(), vv.data(), dv, s.data(), t.data(), W.ws, &st, kc, hist); })
+            if (xr == 2) { if (jacobi) EMU_T1(2, true); else EMU_T1(2, false); }
+            else { if (jacobi) EMU_T1(4, true); else EMU_T1(4, false); }
+            if (xr == 2) { if (jacobi) EMU_T2(2, true); else EMU_T2(2, false); }
+            else { if (jacobi) EMU_T2(4, true); else EMU_T2(4, false); }
+#undef EMU_T1
+#undef EMU_T2
+            emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_upd(n, p0.data(), s.data(), t.data(), rp.data(), x.data(), r.data(), W.ws, &st, kc, hist); });
+        }
+        emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_tail(n, p0.data(), x.data(), &st); });
+    }
+    else if (mode == 2)
     {
         std::vector<double> rp((size_t)n), vv((size_t)n), s((size_t)n), t((size_t)n);
         if (jacobi) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_init<true>(n, b, dv, r.data(), rp.data(), p0.data(), vv.data(), W.ws, &st, kc, hist); });
@@ -649,9 +690,17 @@ EMU_API int emu_sep_solve(int nfields, const int64_t *dims, const int *periodic,
         {
             CsrVecs v{r.data(), pp[it & 1], pp[(it & 1) ^ 1], w.data(), x.data(), dv, nullvec};
 #define EMU_CS(JAC, NM) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_cg_spmv<JAC, NM>(A, v, W.ws, &st, kc, hist); })
-            if (jacobi) { if (nm == 2) EMU_CS(true, 2); else if (nm == 1) EMU_CS(true, 1); else EMU_CS(true, 0); }
+#define EMU_CT(XR, HYB, JAC, NM) emu::launch(tgrid, dim3(256), tsmem, [&] { k_sep_tile_cg_spmv<XR, HYB, JAC, NM>(A, T, v, W.ws, &st, kc, hist); })
+#define EMU_CTN(XR, HYB, JAC) do { if (nm == 2) EMU_CT(XR, HYB, JAC, 2); else if (nm == 1) EMU_CT(XR, HYB, JAC, 1); else EMU_CT(XR, HYB, JAC, 0); } while (0)
+#define EMU_CTJ(XR, HYB) do { if (jacobi) EMU_CTN(XR, HYB, true); else EMU_CTN(XR, HYB, false); } while (0)
+            if (xr == 2) { if (hyb) EMU_CTJ(2, true); else EMU_CTJ(2, false); }
+            else if (xr == 4) { if (hyb) EMU_CTJ(4, true); else EMU_CTJ(4, false); }
+            else if (jacobi) { if (nm == 2) EMU_CS(true, 2); else if (nm == 1) EMU_CS(true, 1); else EMU_CS(true, 0); }
             else { if (nm == 2) EMU_CS(false, 2); else if (nm == 1) EMU_CS(false, 1); else EMU_CS(false, 0); }
 #undef EMU_CS
+#undef EMU_CT
+#undef EMU_CTN
+#undef EMU_CTJ
             upd(false, nm == 2 ? (int)FIN_CSR_UPDATE : (int)FIN_UPDATE);
         }
         GridDev g1{};
@@ -954,7 +1003,18 @@ EMU_API int emu_hybrid_mg_pcg(int dim, const int64_t *n3, const int *periodic, c
     for (int it = 0; it < max_it + 2 && !st.done; ++it)
     {
         CsrVecs v{z, pp[it & 1], pp[(it & 1) ^ 1], w.data(), x.data(), nullptr, nullvec};
-        if (nm == 2) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_cg_spmv<false, 2>(A, v, W.ws, &st, kc, hist); });
+        if (g_sep_xr == 2 || g_sep_xr == 4)
+        {
+            // the hybrid operator always carries its face-area weights (HYB = true)
+            const SepTilePlan T = sep_tile_plan(A, g_sep_xr, g_sep_zchunk, g_sep_target > 0 ? g_sep_target : 24);
+            const dim3 tgrid((unsigned)T.blocks());
+            const size_t tsmem = sep_tile_smem_bytes(g_sep_xr);
+#define EMU_HT(XR, NM) emu::launch(tgrid, dim3(256), tsmem, [&] { k_sep_tile_cg_spmv<XR, true, false, NM>(A, T, v, W.ws, &st, kc, hist); })
+            if (g_sep_xr == 2) { if (nm == 2) EMU_HT(2, 2); else if (nm == 1) EMU_HT(2, 1); else EMU_HT(2, 0); }
+            else { if (nm == 2) EMU_HT(4, 2); else if (nm == 1) EMU_HT(4, 1); else EMU_HT(4, 0); }
+#undef EMU_HT
+        }
+        else if (nm == 2) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_cg_spmv<false, 2>(A, v, W.ws, &st, kc, hist); });
         else if (nm == 1) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_cg_spmv<false, 1>(A, v, W.ws, &st, kc, hist); });
         else emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_cg_spmv<false, 0>(A, v, W.ws, &st, kc, hist); });
         emu::launch(dim3(blocks), dim3(256), 0, [&] { k_mg_rupdate(n, r.data(), w.data(), &st); });

@@ -47,6 +47,7 @@ def make_module(emu):
             self._M = None
             self._null = (False, None)
             self._res = None
+            self._tuning = {}
             if file and file != "None":
                 L = _lib.lib()
                 o = _lib.Options()
@@ -67,7 +68,16 @@ def make_module(emu):
                 setattr(self._o, k, _NAMES[v] if isinstance(v, str) else v)
 
         def setTuning(self, key, value):
-            pass
+            self._tuning[key] = int(value)
+
+        def _tiles(self):
+            """The kernel choice of sep_tile_xr (sep_solver.inc) for the line-coefficient operator."""
+            xr = self._tuning.get("sep_tile", -1)
+            if xr < 0:
+                xr = 2 if self.operator == "staggered" and any(d[2] >= 8 for d in self._dims) else 0
+                if self.operator == "hybrid":
+                    xr = 2 if (self._grid.dim == 3 and self._grid.n[2] >= 8) else 0
+            return K._sep_tiles(emu, xr if xr in (2, 4) else 0, self._tuning.get("sep_zchunk", 0))
 
         # ---- operator
         def setGrid(self, grid):
@@ -139,9 +149,10 @@ def make_module(emu):
             if self.operator == "csr":
                 return orc.Csr.from_arrays(self._M.shape[0], self._M.shape[1], self._M.indptr, self._M.indices, self._M.data).spmv(x)
             per = [int(bool(p)) for p in g.periodic][:3]
-            if self.operator == "hybrid":
-                return K._sep_solve(emu, None, per[: g.dim], self._M, x, mode="apply", hybrid_widths=g.widths, dt=g.dt)[0]
-            return K._sep_solve(emu, self._dims, per, self._M, x, mode="apply")[0]
+            with self._tiles():
+                if self.operator == "hybrid":
+                    return K._sep_solve(emu, None, per[: g.dim], self._M, x, mode="apply", hybrid_widths=g.widths, dt=g.dt)[0]
+                return K._sep_solve(emu, self._dims, per, self._M, x, mode="apply")[0]
 
         # ---- KSPSolve
         def solve(self, x, b):
@@ -181,12 +192,13 @@ def make_module(emu):
             else:
                 per = [int(bool(p)) for p in g.periodic][:3]
                 mode = "bcgs" if o.ksp_type == 1 else "cg"
-                if self.operator == "hybrid":
-                    xs, hist, its, reason = K._sep_solve(emu, None, per[: g.dim], self._M, b, mode=mode, pc=pc, has_const=has_const,
-                                                         nullvec=nv, hybrid_widths=g.widths, dt=g.dt, **kw)
-                else:
-                    xs, hist, its, reason = K._sep_solve(emu, self._dims, per, self._M, b, mode=mode, pc=pc, has_const=has_const,
-                                                         nullvec=nv, **kw)
+                with self._tiles():
+                    if self.operator == "hybrid":
+                        xs, hist, its, reason = K._sep_solve(emu, None, per[: g.dim], self._M, b, mode=mode, pc=pc, has_const=has_const,
+                                                             nullvec=nv, hybrid_widths=g.widths, dt=g.dt, **kw)
+                    else:
+                        xs, hist, its, reason = K._sep_solve(emu, self._dims, per, self._M, b, mode=mode, pc=pc, has_const=has_const,
+                                                             nullvec=nv, **kw)
             x[...] = xs
             self._res = (hist, its, reason)
             if reason < 0:

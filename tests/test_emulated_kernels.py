@@ -19,7 +19,7 @@ EMU = os.path.join(ROOT, "tests", "emu")
 LIB = os.path.join(EMU, "libb200emu.so")
 SRC = [os.path.join(EMU, f) for f in ("emu_solver.cpp", "cuda_emu.h")] + \
       [os.path.join(ROOT, "petibm_b200", "csrc", f) for f in ("kernels.cuh", "spmv2.cuh", "spmv3.cuh", "hw.cuh", "csr_kernels.cuh",
-                                                            "sep_kernels.cuh", "mg_kernels.cuh", "mg_schedule.h",
+                                                            "sep_kernels.cuh", "sep_tile.cuh", "mg_kernels.cuh", "mg_schedule.h",
                                                             "ops_kernels.cuh", "update_fly.cuh", "dense_kernels.cuh", "spmv4.cuh", "spmv5.cuh")]
 
 _dp = C.POINTER(C.c_double)
@@ -49,6 +49,7 @@ def emu():
     L.emu_sep_solve.argtypes = [C.c_int, C.POINTER(C.c_int64), _ip, _dp, C.c_int64, _dp, _dp, C.POINTER(C.c_int64),
                                 C.POINTER(C.c_int32), _dp, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_double, C.c_double, C.c_int,
                                 _dp, _dp, _dp, C.c_int, _ip, _ip, _ip]
+    L.emu_set_sep_tile.argtypes = [C.c_int, C.c_int, C.c_int]
     return L
 
 
@@ -454,6 +455,44 @@ def test_emulated_hybrid_operator_on_a_stretched_ibpm_system(emu, dim):
         np.testing.assert_allclose(x, ref.x, rtol=0, atol=1e-6 * np.abs(ref.x).max())
 
 
+def _random_stencil_blocks(rng):
+    import scipy.sparse as sp
+
+    nf = int(rng.integers(1, 4))
+    per = [bool(rng.integers(0, 2)) for _ in range(3)]
+    dims = [[int(rng.integers(3 if per[d] else 1, 7)) for d in range(3)] for _ in range(nf)]
+    nextra = int(rng.integers(0, 5))
+    rows, cols, vals = [], [], []
+    off = 0
+    for n in dims:
+        n0, n1, n2 = n
+        size = n0 * n1 * n2
+        stride = (1, n0, n0 * n1)
+        l = np.arange(size)
+        idx = (l % n0, (l // n0) % n1, l // (n0 * n1))
+        rows.append(off + l); cols.append(off + l); vals.append(rng.uniform(5.0, 9.0, size))
+        for d in range(3):
+            if n[d] == 1:
+                continue
+            cm, cp = rng.uniform(-1.0, -0.1, n[d]), rng.uniform(-1.0, -0.1, n[d])
+            for coef, step in ((cm, -1), (cp, +1)):
+                nb = idx[d] + step
+                ok = (nb >= 0) & (nb < n[d])
+                if per[d]:
+                    nb, ok = nb % n[d], np.ones_like(ok)
+                rows.append(off + l[ok]); cols.append(off + l[ok] + (nb[ok] - idx[d][ok]) * stride[d]); vals.append(coef[idx[d]][ok])
+        off += size
+    nrows = off + nextra
+    if nextra:
+        k = 3 * nextra
+        rr = np.concatenate([rng.integers(0, nrows, k), np.arange(off, nrows)])
+        cc = np.concatenate([rng.integers(off, nrows, k), np.arange(off, nrows)])
+        rows.append(rr); cols.append(cc); vals.append(rng.uniform(0.1, 1.0, rr.size))
+    M = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nrows, nrows))
+    M.sum_duplicates(); M.sort_indices()
+    return M, dims, per
+
+
 def test_emulated_line_coefficient_spmv_on_random_stencil_blocks(emu):
     """Random combinations the structured tests do not reach: one to three blocks, extents down to one cell, periodic
     axes with three cells (every neighbour wraps somewhere), a random remainder behind the blocks.  y = A x must equal the
@@ -462,42 +501,158 @@ def test_emulated_line_coefficient_spmv_on_random_stencil_blocks(emu):
 
     rng = np.random.default_rng(77)
     for case in range(14):
-        nf = int(rng.integers(1, 4))
-        per = [bool(rng.integers(0, 2)) for _ in range(3)]
-        dims = [[int(rng.integers(3 if per[d] else 1, 7)) for d in range(3)] for _ in range(nf)]
-        nextra = int(rng.integers(0, 5))
-        rows, cols, vals = [], [], []
-        off = 0
-        for n in dims:
-            n0, n1, n2 = n
-            size = n0 * n1 * n2
-            stride = (1, n0, n0 * n1)
-            l = np.arange(size)
-            idx = (l % n0, (l // n0) % n1, l // (n0 * n1))
-            rows.append(off + l); cols.append(off + l); vals.append(rng.uniform(5.0, 9.0, size))
-            for d in range(3):
-                if n[d] == 1:
-                    continue
-                cm, cp = rng.uniform(-1.0, -0.1, n[d]), rng.uniform(-1.0, -0.1, n[d])
-                for coef, step in ((cm, -1), (cp, +1)):
-                    nb = idx[d] + step
-                    ok = (nb >= 0) & (nb < n[d])
-                    if per[d]:
-                        nb, ok = nb % n[d], np.ones_like(ok)
-                    rows.append(off + l[ok]); cols.append(off + l[ok] + (nb[ok] - idx[d][ok]) * stride[d]); vals.append(coef[idx[d]][ok])
-            off += size
-        nrows = off + nextra
-        if nextra:
-            k = 3 * nextra
-            rr = np.concatenate([rng.integers(0, nrows, k), np.arange(off, nrows)])
-            cc = np.concatenate([rng.integers(off, nrows, k), np.arange(off, nrows)])
-            rows.append(rr); cols.append(cc); vals.append(rng.uniform(0.1, 1.0, rr.size))
-        M = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nrows, nrows))
-        M.sum_duplicates(); M.sort_indices()
+        M, dims, per = _random_stencil_blocks(rng)
+        nrows = M.shape[0]
         Mo = orc.Csr.from_arrays(nrows, nrows, M.indptr, M.indices, M.data)
         x = rng.standard_normal(nrows)
         y, _, _, _ = _sep_solve(emu, dims, per, M, x, mode="apply")
-        assert np.array_equal(y, Mo.spmv(x)), (case, dims, per, nextra)
+        assert np.array_equal(y, Mo.spmv(x)), (case, dims, per)
+
+
+class _sep_tiles:
+    """Run the line-coefficient operator through the tiled kernels of sep_tile.cuh (xr = 2 / 4: tiles of 64 / 128 cells
+    in x; zchunk planes per chunk, 0 = the launch rule; target = the CTA count that rule aims for)."""
+
+    def __init__(self, L, xr, zchunk=0, target=24):
+        self.L, self.args = L, (xr, zchunk, target)
+
+    def __enter__(self):
+        self.L.emu_set_sep_tile(*self.args)
+
+    def __exit__(self, *exc):
+        self.L.emu_set_sep_tile(0, 0, 0)
+
+
+TILE_VARIANTS = [(2, 0), (2, 1), (2, 3), (4, 0), (4, 2)]
+
+
+@pytest.mark.parametrize("xr,zchunk", TILE_VARIANTS)
+@pytest.mark.parametrize("shape,per", [((9, 8), (0, 0)), ((8, 7, 6), (0, 0, 0)), ((7, 6, 5), (1, 0, 1)), ((5, 6, 7), (1, 1, 1)),
+                                       ((40, 3, 3), (0, 1, 0)), ((70, 19, 5), (0, 0, 0)), ((131, 10, 4), (1, 0, 0)),
+                                       ((66, 17), (0, 1)), ((3, 3, 9), (0, 0, 1))])
+def test_emulated_tiled_line_coefficient_spmv_is_bit_identical(emu, shape, per, xr, zchunk):
+    """sep_tile.cuh: the plane-marching tile kernels give y = A x bit for bit like MatMult_SeqAIJ on the assembled velocity
+    matrix -- several tiles in x and y, ragged edges, one or many z chunks, periodic axes (wrapped cells take sep_row)."""
+    A, _ = H.velocity_system(H.make_widths(shape), per, dt=0.01, nu=0.02)
+    Ao = orc.Csr.from_arrays(A.shape[0], A.shape[1], A.indptr, A.indices, A.data)
+    dims, p = _velocity_dims(shape, per)
+    x = np.random.default_rng(3).standard_normal(A.shape[0])
+    with _sep_tiles(emu, xr, zchunk):
+        y, _, _, _ = _sep_solve(emu, dims, p, A, x, mode="apply")
+    assert np.array_equal(y, Ao.spmv(x))
+
+
+@pytest.mark.parametrize("xr,zchunk", [(2, 2), (4, 0)])
+def test_emulated_tiled_kernels_do_not_depend_on_the_thread_schedule(emu, xr, zchunk):
+    """One barrier per plane guards the double-buffered shared plane: with shuffled fiber order and random preemption at
+    every shared-memory access the product stays bit-identical (a missing barrier would show as a schedule-dependent y)."""
+    shape, per = (70, 19, 5), (0, 0, 0)
+    A, _ = H.velocity_system(H.make_widths(shape), per, dt=0.01, nu=0.02)
+    Ao = orc.Csr.from_arrays(A.shape[0], A.shape[1], A.indptr, A.indices, A.data)
+    dims, p = _velocity_dims(shape, per)
+    x = np.random.default_rng(9).standard_normal(A.shape[0])
+    y0 = Ao.spmv(x)
+    try:
+        for seed in (1, 2, 3):
+            emu.emu_set_schedule(seed)
+            with _sep_tiles(emu, xr, zchunk):
+                y, _, _, _ = _sep_solve(emu, dims, p, A, x, mode="apply")
+            assert np.array_equal(y, y0)
+    finally:
+        emu.emu_set_schedule(0)
+
+
+@pytest.mark.parametrize("xr,zchunk", [(2, 0), (4, 3)])
+def test_emulated_tiled_line_coefficient_spmv_on_random_stencil_blocks(emu, xr, zchunk):
+    """The random blocks of the test above (extents down to one cell, three-cell periodic axes, random remainder)
+    through the tiled kernels."""
+    rng = np.random.default_rng(78)
+    for case in range(10):
+        M, dims, per = _random_stencil_blocks(rng)
+        Mo = orc.Csr.from_arrays(M.shape[0], M.shape[0], M.indptr, M.indices, M.data)
+        x = rng.standard_normal(M.shape[0])
+        with _sep_tiles(emu, xr, zchunk):
+            y, _, _, _ = _sep_solve(emu, dims, per, M, x, mode="apply")
+        assert np.array_equal(y, Mo.spmv(x)), (case, dims, per)
+
+
+@pytest.mark.parametrize("xr,zchunk", [(2, 0), (2, 2), (4, 0)])
+@pytest.mark.parametrize("pc", ["none", "jacobi"])
+def test_emulated_tiled_line_coefficient_krylov_paths(emu, pc, xr, zchunk):
+    """BiCGStab (+ Jacobi) on the velocity system, CG on a periodic one and CG with the explicit null-space vector on an
+    IBPM-style system with a remainder, through the tiled kernels: same iteration counts and reasons as the row-per-thread
+    kernels, histories equal up to the summation order of the dot products (1e-12), oracle agreement as before."""
+    import scipy.sparse as sp
+
+    shape, per = (8, 7, 6), (0, 0, 0)
+    A, _ = H.velocity_system(H.make_widths(shape), per, dt=0.5, nu=1.0)
+    Ao = orc.Csr.from_arrays(A.shape[0], A.shape[1], A.indptr, A.indices, A.data)
+    dims, p = _velocity_dims(shape, per)
+    b = np.random.default_rng(2).standard_normal(A.shape[0])
+    ref = orc.ksp_solve(Ao, b, ksp_type="bcgs", pc_type=pc, rtol=0.0, atol=1e-8, max_it=300)
+    x0, h0, i0, r0 = _sep_solve(emu, dims, p, A, b, mode="bcgs", pc=pc, atol=1e-8, max_it=300)
+    with _sep_tiles(emu, xr, zchunk):
+        x, hist, its, reason = _sep_solve(emu, dims, p, A, b, mode="bcgs", pc=pc, atol=1e-8, max_it=300)
+    assert abs(its - i0) <= 1 and reason == r0 == ref.reason == 3
+    # BiCGStab amplifies the rounding of its dot products from iteration to iteration: tight over the first entries,
+    # loose over the 35-iteration window (the oracle comparison of the row-per-thread kernels has the same shape)
+    np.testing.assert_allclose(hist[:10], h0[:10], rtol=1e-9)
+    m = min(hist.size, h0.size)
+    np.testing.assert_allclose(hist[:m], h0[:m], rtol=5e-2)
+    np.testing.assert_allclose(hist[:8], ref.history[:8], rtol=1e-9)
+    np.testing.assert_allclose(x, x0, rtol=0, atol=1e-6 * np.abs(x0).max())
+    shape, per = (7, 6, 5), (1, 0, 1)
+    A, _ = H.velocity_system(np.array([np.full(n, 1.0 / n) for n in shape], dtype=object).tolist(), per, dt=0.5, nu=1.0)
+    dims, p = _velocity_dims(shape, per)
+    b = np.random.default_rng(6).standard_normal(A.shape[0])
+    x0, h0, i0, r0 = _sep_solve(emu, dims, p, A, b, mode="cg", pc=pc, max_it=12)
+    with _sep_tiles(emu, xr, zchunk):
+        x, hist, its, reason = _sep_solve(emu, dims, p, A, b, mode="cg", pc=pc, max_it=12)
+    assert (its, reason) == (i0, r0)
+    np.testing.assert_allclose(hist, h0, rtol=1e-12)
+    np.testing.assert_allclose(x, x0, rtol=0, atol=1e-12 * np.abs(x0).max())
+    gshape = (10, 9)
+    G = orc.assemble_gradient(H.make_widths(gshape), [0, 0, 0]).to_scipy()
+    R = sp.random(G.shape[0], 7, density=0.05, random_state=4, format="csr")
+    K = sp.hstack([G, -R]).tocsr()
+    M = (-(K.T @ K) * 0.01).tocsr(); M.sort_indices()
+    nv = np.zeros(M.shape[0]); nv[: G.shape[1]] = 1.0 / np.sqrt(G.shape[1])
+    Mo = orc.Csr.from_arrays(M.shape[0], M.shape[1], M.indptr, M.indices, M.data)
+    xs = np.random.default_rng(5).standard_normal(M.shape[0]); xs -= (xs @ nv) * nv
+    bm = M @ xs
+    refm = orc.ksp_solve(Mo, bm, pc_type=pc, rtol=0, atol=0, max_it=15, nullvecs=nv)
+    with _sep_tiles(emu, xr, zchunk):
+        y, _, _, _ = _sep_solve(emu, [[10, 9, 1]], (0, 0, 0), M, xs, mode="apply")
+        x, hist, its, reason = _sep_solve(emu, [[10, 9, 1]], (0, 0, 0), M, bm, mode="cg", pc=pc, nullvec=nv, max_it=15)
+    assert np.array_equal(y, Mo.spmv(xs))
+    np.testing.assert_allclose(hist, refm.history, rtol=1e-10)
+    np.testing.assert_allclose(x, refm.x, rtol=0, atol=1e-9 * np.abs(refm.x).max())
+
+
+@pytest.mark.parametrize("xr,zchunk", [(2, 0), (4, 2)])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_emulated_tiled_hybrid_operator_on_a_stretched_ibpm_system(emu, dim, xr, zchunk):
+    """The hybrid form (pressure block with face areas + remainder, b200ls_set_poisson_hybrid) through the tiled kernels:
+    SpMV bit-identical to the assembled MatMult, CG with the explicit null-space vector as the row-per-thread kernels."""
+    sub = [{"end": 0.6, "cells": 5 if dim == 3 else 8, "stretchRatio": 1.0 / 1.25}, {"end": 1.4, "cells": 8 if dim == 3 else 14, "stretchRatio": 1.0},
+           {"end": 2.0, "cells": 5 if dim == 3 else 8, "stretchRatio": 1.25}]
+    w = orc.axis_from_subdomains(0.0, sub)
+    widths = [w.copy() for _ in range(dim)]
+    M, pN, nv = H.ibpm_system(widths, dt=0.01, nb=10)
+    Mo = orc.Csr.from_arrays(M.shape[0], M.shape[1], M.indptr, M.indices, M.data)
+    rng = np.random.default_rng(12)
+    xs = rng.standard_normal(M.shape[0]); xs -= (xs @ nv) * nv
+    bm = Mo.spmv(xs)
+    with _sep_tiles(emu, xr, zchunk):
+        y, _, _, _ = _sep_solve(emu, None, (0,) * dim, M, xs, mode="apply", hybrid_widths=widths)
+    assert np.array_equal(y, bm)
+    for pc in ("none", "jacobi"):
+        x0, h0, i0, r0 = _sep_solve(emu, None, (0,) * dim, M, bm, mode="cg", pc=pc, nullvec=nv, max_it=15, hybrid_widths=widths)
+        with _sep_tiles(emu, xr, zchunk):
+            x, hist, its, reason = _sep_solve(emu, None, (0,) * dim, M, bm, mode="cg", pc=pc, nullvec=nv, max_it=15, hybrid_widths=widths)
+        assert (its, reason) == (i0, r0)
+        np.testing.assert_allclose(hist[:8], h0[:8], rtol=1e-10)
+        np.testing.assert_allclose(hist, h0, rtol=1e-6)
 
 
 @pytest.mark.parametrize("shape,per", [((9, 7), (0, 0)), ((8, 6), (1, 0)), ((7, 6, 5), (0, 0, 0)), ((6, 5, 7), (1, 0, 1)),

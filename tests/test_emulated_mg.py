@@ -200,6 +200,17 @@ def test_emulated_block_preconditioner_on_the_ibpm_system(emu, dim):
     assert (its, reason) == (nit, -3)
     np.testing.assert_allclose(hist, hr, rtol=1e-8)
     np.testing.assert_allclose(x, xr, rtol=0, atol=1e-9 * np.abs(xr).max())
+    # the same solve with the operator product on the tiled kernels of sep_tile.cuh (tuning "sep_tile")
+    emu.emu_set_sep_tile.argtypes = [C.c_int, C.c_int, C.c_int]
+    for xr_tile in (2, 4):
+        emu.emu_set_sep_tile(xr_tile, 0, 24)
+        try:
+            xt, ht, it_t, reason_t = _hybrid_mg(emu, widths, M, b, nullvec=nv, max_it=nit)
+        finally:
+            emu.emu_set_sep_tile(0, 0, 0)
+        assert (it_t, reason_t) == (nit, -3)
+        np.testing.assert_allclose(ht, hist, rtol=1e-10)
+        np.testing.assert_allclose(xt, x, rtol=0, atol=1e-11 * np.abs(x).max())
     x, hist, its, reason = _hybrid_mg(emu, widths, M, b, nullvec=nv, rtol=1e-9, max_it=200)
     jac = orc.ksp_solve(Mo, b, pc_type="jacobi", rtol=1e-9, atol=1e-50, max_it=5000, nullvecs=nv)
     assert reason == 2 and jac.reason == 2 and 3 * its <= jac.its, (its, jac.its)

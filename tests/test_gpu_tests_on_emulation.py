@@ -27,6 +27,24 @@ def test_staggered_ibpm_like_body(pbe, pc):
     T2.test_ibpm_modified_poisson_stencil_block_plus_remainder(pbe, pc)
 
 
+@pytest.mark.parametrize("shape,per,tile,zchunk", [((70, 19, 12), (0, 0, 0), 2, 5), ((9, 8, 7), (1, 0, 1), 4, 0), ((66, 17), (0, 1), 2, 0)])
+def test_tiled_velocity_body(pbe, shape, per, tile, zchunk):
+    T2.test_tiled_kernels_velocity_system(pbe, shape, per, tile, zchunk)
+
+
+@pytest.mark.parametrize("pc,tile", [("none", 2), ("jacobi", 4)])
+def test_tiled_ibpm_like_body(pbe, pc, tile):
+    T2.test_tiled_kernels_ibpm_like_system_with_remainder(pbe, pc, tile)
+
+
+def test_tiled_hybrid_body(pbe):
+    T2.test_tiled_kernels_hybrid_operator_on_a_stretched_ibpm_system(pbe, 2)
+
+
+def test_default_kernel_choice_body(pbe):
+    T2.test_default_kernel_choice_of_the_line_coefficient_operator(pbe)
+
+
 def test_staggered_fallback_body(pbe):
     T2.test_a_matrix_without_the_structure_keeps_the_csr_operator(pbe)
 
