@@ -18,6 +18,8 @@
 #include <cstring>
 #include <deque>
 #include <map>
+#include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -135,7 +137,8 @@ struct b200ls_solver
     bool mg_ready = false;
     int mg_built_levels = 0;
     int64_t graph_launches = 0;   // launches inside the graph replayed by graph_batch (csr_solver.inc)
-    int sep_tile = -1;            // tuning "sep_tile": tiled plane-marching kernels of sep_tile.cuh for the line-coefficient operator (2 / 4: tiles of 64 / 128 cells in x, 0: row-per-thread kernels, -1: the rule of sep_tile_xr)
+    int sep_tile = -1;            // tuning "sep_tile": tiled plane-marching kernels of sep_tile.cuh for the line-coefficient operator (2: on, tiles of 64 cells in x; 0: row-per-thread kernels; -1: the rule of sep_tile_xr)
+    int sep_stages = 3;           // tuning "sep_stages": planes in the per-thread cp.async queue of those kernels (3 or 4)
     int sep_zchunk = 0;           // tuning "sep_zchunk": planes per z chunk of those kernels (0: enough chunks for 8 CTAs per SM)
     int csr_graph = 0;            // tuning "csr_graph": CG / BiCGStab batches of the assembled-operator paths as CUDA graphs
     int mg_fuse = 1;         // tuning "mg_fuse": r -= a w and the six sums ride on the first / last fine-level step of the cycle (on: 15.1 -> 14.2 ms at 256^3, profiles/r02_tts_multigrid.log)
@@ -1461,6 +1464,7 @@ int b200ls_create(b200ls_solver **out, int device)
     if (const char *e = getenv("B200LS_CSR_GRAPH")) h->csr_graph = atoi(e);
     if (const char *e = getenv("B200LS_SEP_TILE")) h->sep_tile = atoi(e);
     if (const char *e = getenv("B200LS_SEP_ZCHUNK")) h->sep_zchunk = atoi(e);
+    if (const char *e = getenv("B200LS_SEP_STAGES")) h->sep_stages = atoi(e);
     if (const char *e = getenv("B200LS_MG_TAIL")) h->mg_tail = atoi(e);
     if (const char *e = getenv("B200LS_MG_FUSE")) h->mg_fuse = atoi(e);
     build_commdev(h);
@@ -1536,6 +1540,7 @@ int b200ls_set_tuning(b200ls_solver *h, const char *key, int value)
     else if (k == "csr_graph") h->csr_graph = value;
     else if (k == "sep_tile") h->sep_tile = value;
     else if (k == "sep_zchunk") h->sep_zchunk = value;
+    else if (k == "sep_stages") h->sep_stages = value;
     else if (k == "mg_tail") h->mg_tail = value;
     else if (k == "mg_fuse") h->mg_fuse = value;
     else return fail(h, B200LS_ERR_ARG, "unknown tuning key %s", key);

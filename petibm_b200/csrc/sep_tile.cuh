@@ -7,6 +7,13 @@
 // k + 1; a double-buffered shared plane with a one-cell rim hands it to the x/y neighbours), the x/y coefficients live
 // in registers for the whole march, and nothing is divided per row.  One __syncthreads per plane.
 //
+// Everything a thread reads from HBM goes through a PRIVATE cp.async queue in shared memory (R stages, one plane each): the
+// operand arrays of its own cells and of the rim cells it is responsible for, the diagonal, and whatever the result needs
+// (1/diag, r', x).  A slot is written and read by the same thread only, so the queue needs no barrier -- just
+// cp.async.wait_group -- and R - 2 planes are in flight behind the one being consumed without costing a register.  (The first
+// version loaded plane k + 1 into registers at the top of step k: 18-20 warp-stalls on the long scoreboard per issued
+// instruction, 2 640 iterations/s against 2 733 for the row-per-thread kernels, profiles/r02_velocity_bench.log.)
+//
 // Bit-identity with MatMult_SeqAIJ on the assembled matrix is kept exactly as in sep_row: terms in ascending column order
 // (z-, y-, x-, diagonal, x+, y+, z+, remainder), no FMA contraction, a zero coefficient = "no entry" = nothing added.  A cell
 // with a WRAPPED periodic neighbour has a different column order; those cells (a surface) and the rows behind the stencil
@@ -86,15 +93,27 @@ inline SepTilePlan sep_tile_plan(const SepDev &A, int xr, int zchunk_req, int ta
     return T;
 }
 
-constexpr size_t sep_tile_smem_bytes(int xr) { return sizeof(double) * 2 * (SEP_TY + 2) * (32 * xr + 2); }
+// bytes of dynamic shared memory: two operand planes with their rim + R stages of the per-thread queue
+template <int XR, int R, int NRIM, int NOWN>
+struct SepTileSmem
+{
+    static constexpr int TX = 32 * XR, LD = TX + 2;
+    static constexpr unsigned int PLANE = 8u * (SEP_TY + 2) * LD;
+    static constexpr unsigned int OWN = 8u * NOWN * XR * 256, RIM = 8u * NRIM * XR * 96;  // rim slots: warps 0-2 only
+    static constexpr unsigned int STAGE = OWN + RIM;
+    static constexpr size_t bytes = 2u * PLANE + (size_t)R * STAGE;
+};
 
-// Op: double val(I j) -- the operand vector at row j, built from global memory (I: long long or unsigned int);
-//     void emit(I i, double own, double t) -- consumes row i's product t (own = val(i))
-template <int XR, bool HYB, class Op>
+// Op (one of the policies below):
+//   NRIM operand arrays src[0 .. NRIM) -- operand(s) builds the vector entry the product multiplies from their values;
+//   NEX extra arrays ex[0 .. NEX) read at the row itself; emit(i, own, t, raw, e) consumes row i's product t
+//   (own = operand of the row, raw = its operand-array values, e = its extra-array values).
+template <int XR, bool HYB, int R, class Op>
 __device__ __forceinline__ void sep_tile_rows(const SepDev &A, const SepTilePlan &T, Op &op)
 {
-    constexpr int TX = 32 * XR, TY = SEP_TY, LD = TX + 2;
-    B200_DYNAMIC_SMEM(smem_raw);  // two planes of (TY + 2) x LD doubles: sep_tile_smem_bytes(XR)
+    constexpr int TX = 32 * XR, TY = SEP_TY, LD = TX + 2, NRIM = Op::NRIM, NEX = Op::NEX, NOWN = NRIM + 1 + NEX;
+    using SM = SepTileSmem<XR, R, NRIM, NOWN>;
+    B200_DYNAMIC_SMEM(smem_raw);
     const unsigned int s_base = smem_u32(smem_raw);
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     int b = blockIdx.x;
@@ -107,10 +126,7 @@ __device__ __forceinline__ void sep_tile_rows(const SepDev &A, const SepTilePlan
         {
             for (long long i = A.nsep + (long long)(b - T.surf_blocks) * blockDim.x + tid; i < A.nrows;
                  i += (long long)T.tail_blocks * blockDim.x)
-            {
-                const double own = op.val(i);
-                op.emit(i, own, sep_row(A, i, fetch));
-            }
+                op.emit_global(i, sep_row(A, i, fetch));
             return;
         }
         for (int q = b * (int)blockDim.x + tid; q < T.surf_cells; q += T.surf_blocks * (int)blockDim.x)
@@ -148,8 +164,7 @@ __device__ __forceinline__ void sep_tile_rows(const SepDev &A, const SepTilePlan
                 if ((f.per0 && (i0 == 0 || i0 == n0 - 1)) || (f.per1 && (i1 == 0 || i1 == n1 - 1))) continue;
             }
             const long long i = f.off + ((long long)i2 * n1 + i1) * n0 + i0;
-            const double own = op.val(i);
-            op.emit(i, own, sep_row(A, i, fetch));
+            op.emit_global(i, sep_row(A, i, fetch));
         }
         return;
     }
@@ -208,57 +223,119 @@ __device__ __forceinline__ void sep_tile_rows(const SepDev &A, const SepTilePlan
         xin = (jy < n1 && jx >= 0 && jx < n0) ? 1u : 0u;
         h0 = (int)(f.off + (long long)jy * n0 + jx);
     }
+    const unsigned int hload = hlive & xin;  // rim cells inside the field
 
-    double vm[XR], vc[XR], vp[XR], hv[XR];
-    // io / ho: row index of own cell 0 / rim cell 0 in the plane being loaded.  Row indices are 32-bit here (the host
-    // refuses systems of 2^31 rows or more), so an address is one IMAD.WIDE; an index that is never dereferenced may wrap.
-    auto load_plane = [&](unsigned int io, unsigned int ho, double (&v)[XR], double (&h)[XR]) {
+    // ---- the per-thread queue: stage kk % R holds plane kk.  Row indices are 32-bit here (the host refuses systems of
+    // 2^31 rows or more), so an address is one IMAD.WIDE.
+    const unsigned int s2 = (unsigned int)n0 * (unsigned int)n1;
+    const unsigned int q_base = s_base + 2u * SM::PLANE + 8u * (unsigned)tid;
+    auto own_slot = [&](int kk, int a, int r) { return q_base + (unsigned)(kk % R) * SM::STAGE + 8u * 256u * (unsigned)(a * XR + r); };
+    auto rim_slot = [&](int kk, int a, int r) { return q_base + (unsigned)(kk % R) * SM::STAGE + SM::OWN + 8u * 96u * (unsigned)(a * XR + r); };
+    // planes kb - 1 and ke are only needed as z neighbours: operand arrays of the own cells, nothing else
+    auto issue = [&](int kk) {
+        if (kk >= 0 && kk < n2 && kk <= ke)
+        {
+            const unsigned int io = (unsigned int)own0 + (unsigned int)kk * s2, ho = (unsigned int)h0 + (unsigned int)kk * s2;
+            const bool full = kk >= kb && kk < ke;
 #pragma unroll
-        for (int r = 0; r < XR; ++r) v[r] = (live >> r & 1u) ? op.val(io + 32u * r) : 0.0;
+            for (int r = 0; r < XR; ++r)
+                if (live >> r & 1u)
+                {
 #pragma unroll
-        for (int r = 0; r < XR; ++r) h[r] = ((hlive & xin) >> r & 1u) ? op.val(ho + 32u * r) : 0.0;
+                    for (int a = 0; a < NRIM; ++a) cp_async8(own_slot(kk, a, r), op.src[a] + (io + 32u * r));
+                    if (full)
+                    {
+                        cp_async8(own_slot(kk, NRIM, r), A.diag + (io + 32u * r));
+#pragma unroll
+                        for (int a = 0; a < NEX; ++a) cp_async8(own_slot(kk, NRIM + 1 + a, r), op.ex[a] + (io + 32u * r));
+                    }
+                }
+            if (full)
+            {
+#pragma unroll
+                for (int r = 0; r < XR; ++r)
+                    if (hload >> r & 1u)
+                    {
+#pragma unroll
+                        for (int a = 0; a < NRIM; ++a) cp_async8(rim_slot(kk, a, r), op.src[a] + (ho + 32u * r));
+                    }
+            }
+        }
+        cp_async_commit();
     };
-    constexpr unsigned int PLANE = 8u * (TY + 2) * LD;
+    auto own_operands = [&](int kk, double (&v)[XR]) {
+#pragma unroll
+        for (int r = 0; r < XR; ++r)
+        {
+            v[r] = 0.0;
+            if (live >> r & 1u)
+            {
+                double sv[NRIM];
+#pragma unroll
+                for (int a = 0; a < NRIM; ++a) sv[a] = lds64(own_slot(kk, a, r));
+                v[r] = op.operand(sv);
+            }
+        }
+    };
+    auto rim_operands = [&](int kk, double (&h)[XR]) {
+#pragma unroll
+        for (int r = 0; r < XR; ++r)
+        {
+            h[r] = 0.0;
+            if (hload >> r & 1u)
+            {
+                double sv[NRIM];
+#pragma unroll
+                for (int a = 0; a < NRIM; ++a) sv[a] = lds64(rim_slot(kk, a, r));
+                h[r] = op.operand(sv);
+            }
+        }
+    };
     const unsigned int s_own = s_base + 8u * (unsigned)((ty + 1) * LD + 1 + tx), s_rim = s_base + 8u * (unsigned)(hs0 < 0 ? 0 : hs0);
     auto store_plane = [&](int buf, const double (&v)[XR], const double (&h)[XR]) {
 #pragma unroll
-        for (int r = 0; r < XR; ++r) sts64(s_own + buf * PLANE + 256u * r, v[r]);
+        for (int r = 0; r < XR; ++r) sts64(s_own + buf * SM::PLANE + 256u * r, v[r]);
 #pragma unroll
         for (int r = 0; r < XR; ++r)
-            if (hlive >> r & 1u) sts64(s_rim + buf * PLANE + 256u * r, h[r]);
+            if (hlive >> r & 1u) sts64(s_rim + buf * SM::PLANE + 256u * r, h[r]);
     };
 
-    const unsigned int s2 = (unsigned int)n0 * (unsigned int)n1;
-    unsigned int io = (unsigned int)own0 + (unsigned int)kb * s2, ho = (unsigned int)h0 + (unsigned int)kb * s2;
+    double vm[XR], vc[XR], vp[XR], hv[XR];
 #pragma unroll
-    for (int r = 0; r < XR; ++r) vm[r] = (kb > 0 && (live >> r & 1u)) ? op.val(io - s2 + 32u * r) : 0.0;
-    load_plane(io, ho, vc, hv);
+    for (int q = -1; q < R - 1; ++q) issue(kb + q);
+    cp_async_wait<R - 2>();  // planes kb - 1 and kb have landed
+#pragma unroll
+    for (int r = 0; r < XR; ++r) vm[r] = 0.0;
+    if (kb > 0) own_operands(kb - 1, vm);
+    own_operands(kb, vc);
+    rim_operands(kb, hv);
     store_plane(kb & 1, vc, hv);
     __syncthreads();
+    issue(kb + R - 1);  // into the stage of plane kb - 1
 
     for (int k = kb; k < ke; ++k)
     {
         const int buf = k & 1;
-        if (k + 1 < n2) load_plane(io + s2, ho + s2, vp, hv);
-        else
-        {
+        cp_async_wait<R - 2>();  // plane k + 1 has landed; k + 2 .. k + R - 1 are in flight
 #pragma unroll
-            for (int r = 0; r < XR; ++r) vp[r] = hv[r] = 0.0;
-        }
+        for (int r = 0; r < XR; ++r) vp[r] = hv[r] = 0.0;
+        if (k + 1 < n2) own_operands(k + 1, vp);
+        if (k + 1 < ke) rim_operands(k + 1, hv);
         const bool wz = f.per2 && (k == 0 || k == n2 - 1);
         const double czm = f.cm[2][k], czp = f.cp[2][k];
         const double dzk = HYB ? f.w[2][k] : 0.0;
         const unsigned int todo = wz ? 0u : (live & ~wrap);
+        const unsigned int io = (unsigned int)own0 + (unsigned int)k * s2;
 #pragma unroll
         for (int r = 0; r < XR; ++r)
         {
             if (!(todo >> r & 1u)) continue;
             const unsigned int i = io + 32u * r;
-            const unsigned int c = s_own + buf * PLANE + 256u * r;
+            const unsigned int c = s_own + buf * SM::PLANE + 256u * r;
             // the four in-plane neighbours (the rim holds zeros outside the field; a term with a zero coefficient is
             // dropped below whatever its operand)
             const double vym = lds64(c - 8u * LD), vxm = lds64(c - 8u), vxp = lds64(c + 8u), vyp = lds64(c + 8u * LD);
-            const double dg = A.diag[i];
+            const double dg = lds64(own_slot(k, NRIM, r));
             double axm = cxm[r], axp = cxp[r], aym = cym, ayp = cyp, azm = czm, azp = czp;
             if (HYB)
             {
@@ -288,12 +365,16 @@ __device__ __forceinline__ void sep_tile_rows(const SepDev &A, const SepTilePlan
                 for (int64_t q = A.rem_rowptr[i]; q < A.rem_rowptr[i + 1u]; ++q)
                     t = __dadd_rn(t, __dmul_rn(A.rem_val[q], op.val((unsigned int)A.rem_col[q])));
             }
-            op.emit(i, vc[r], t);
+            double raw[NRIM], e[NEX + 1];
+#pragma unroll
+            for (int a = 0; a < NRIM; ++a) raw[a] = Op::NEEDS_RAW ? lds64(own_slot(k, a, r)) : 0.0;
+#pragma unroll
+            for (int a = 0; a < NEX; ++a) e[a] = lds64(own_slot(k, NRIM + 1 + a, r));
+            op.emit(i, vc[r], t, raw, e);
         }
         if (k + 1 < ke) store_plane(buf ^ 1, vp, hv);
         __syncthreads();
-        io += s2;
-        ho += s2;
+        issue(k + R);  // into the stage of plane k: this thread has read everything it queued there
 #pragma unroll
         for (int r = 0; r < XR; ++r)
         {
@@ -301,76 +382,117 @@ __device__ __forceinline__ void sep_tile_rows(const SepDev &A, const SepTilePlan
             vc[r] = vp[r];
         }
     }
+    cp_async_wait<0>();
 }
 
 // ---- the operand / result policies of the four products -------------------------------------------------------------
 
-struct SepOpApply
+// the generic-path halves shared by the policies: the operand and the result of a row straight from global memory
+template <class Op>
+struct SepOpBase
 {
-    const double *x;
-    double *y;
-    template <class I>
-    __device__ __forceinline__ double val(I j) const { return x[j]; }
-    template <class I>
-    __device__ __forceinline__ void emit(I i, double, double t) { y[i] = t; }
-};
-
-// CG class 0:  x += a' p' ; p = z + b p' ; w = A p ; p.w   (k_sep_cg_spmv)
-template <bool JACOBI, int NULLMODE>
-struct SepOpCg
-{
-    CsrVecs v;
-    double shift, bcoef, aprev;
-    bool xupd;
-    double acc[1];
     template <class I>
     __device__ __forceinline__ double val(I j) const
     {
-        return __dadd_rn(csr_z<JACOBI, NULLMODE>(v, j, shift), __dmul_rn(bcoef, v.p_in[j]));
+        const Op &o = *static_cast<const Op *>(this);
+        double sv[Op::NRIM];
+#pragma unroll
+        for (int a = 0; a < Op::NRIM; ++a) sv[a] = o.src[a][j];
+        return o.operand(sv);
     }
     template <class I>
-    __device__ __forceinline__ void emit(I i, double own, double t)
+    __device__ __forceinline__ void emit_global(I i, double t)
     {
-        if (xupd) v.x[i] = __dadd_rn(v.x[i], __dmul_rn(aprev, v.p_in[i]));
-        v.p_out[i] = own;
-        v.w[i] = t;
+        Op &o = *static_cast<Op *>(this);
+        double raw[Op::NRIM], e[Op::NEX + 1];
+#pragma unroll
+        for (int a = 0; a < Op::NRIM; ++a) raw[a] = o.src[a][i];
+#pragma unroll
+        for (int a = 0; a < Op::NEX; ++a) e[a] = o.ex[a][i];
+        o.emit(i, o.operand(raw), t, raw, e);
+    }
+};
+
+struct SepOpApply : SepOpBase<SepOpApply>
+{
+    static constexpr int NRIM = 1, NEX = 0;
+    static constexpr bool NEEDS_RAW = false;
+    const double *src[1];
+    const double *ex[1];
+    double *y;
+    __device__ __forceinline__ double operand(const double (&s)[1]) const { return s[0]; }
+    template <class I>
+    __device__ __forceinline__ void emit(I i, double, double t, const double (&)[1], const double (&)[1]) { y[i] = t; }
+};
+
+// CG class 0:  x += a' p' ; p = z + b p' ; w = A p ; p.w   (k_sep_cg_spmv).  Operand arrays: r, p', [1/diag], [null vector];
+// extra: x.
+template <bool JACOBI, int NULLMODE>
+struct SepOpCg : SepOpBase<SepOpCg<JACOBI, NULLMODE>>
+{
+    static constexpr int NRIM = 2 + (JACOBI ? 1 : 0) + (NULLMODE == 2 ? 1 : 0), NEX = 1;
+    static constexpr bool NEEDS_RAW = true;
+    const double *src[NRIM];
+    const double *ex[1];
+    double *x, *p_out, *w;
+    double shift, bcoef, aprev;
+    bool xupd;
+    double acc[1];
+    __device__ __forceinline__ double operand(const double (&s)[NRIM]) const
+    {
+        double z = s[0];  // csr_z: B r with the null space removed
+        if (JACOBI) z = __dmul_rn(z, s[2]);
+        if (NULLMODE == 1) z = __dadd_rn(z, shift);
+        if (NULLMODE == 2) z = __dadd_rn(z, __dmul_rn(shift, s[2 + (JACOBI ? 1 : 0)]));
+        return __dadd_rn(z, __dmul_rn(bcoef, s[1]));
+    }
+    template <class I>
+    __device__ __forceinline__ void emit(I i, double own, double t, const double (&raw)[NRIM], const double (&e)[2])
+    {
+        if (xupd) x[i] = __dadd_rn(e[0], __dmul_rn(aprev, raw[1]));
+        p_out[i] = own;
+        w[i] = t;
         acc[0] = fma(own, t, acc[0]);
     }
 };
 
-// BiCGStab: v = B A p ; v.rp   (k_sep_bcgs_spmv1)
+// BiCGStab: v = B A p ; v.rp   (k_sep_bcgs_spmv1).  Operand array: p; extras: r', [1/diag].
 template <bool JACOBI>
-struct SepOpBcgs1
+struct SepOpBcgs1 : SepOpBase<SepOpBcgs1<JACOBI>>
 {
-    const double *p, *dinv, *rp;
+    static constexpr int NRIM = 1, NEX = JACOBI ? 2 : 1;
+    static constexpr bool NEEDS_RAW = false;
+    const double *src[1];
+    const double *ex[NEX];
     double *vv;
     double acc[1];
+    __device__ __forceinline__ double operand(const double (&s)[1]) const { return s[0]; }
     template <class I>
-    __device__ __forceinline__ double val(I j) const { return p[j]; }
-    template <class I>
-    __device__ __forceinline__ void emit(I i, double, double t)
+    __device__ __forceinline__ void emit(I i, double, double t, const double (&)[1], const double (&e)[NEX + 1])
     {
-        if (JACOBI) t = __dmul_rn(t, dinv[i]);
+        if (JACOBI) t = __dmul_rn(t, e[1]);
         vv[i] = t;
-        acc[0] = fma(t, rp[i], acc[0]);
+        acc[0] = fma(t, e[0], acc[0]);
     }
 };
 
-// BiCGStab: s = r - alpha v ; t = B A s ; {s.t, t.t, s.s}   (k_sep_bcgs_spmv2)
+// BiCGStab: s = r - alpha v ; t = B A s ; {s.t, t.t, s.s}   (k_sep_bcgs_spmv2).  Operand arrays: r, v; extra: [1/diag].
 template <bool JACOBI>
-struct SepOpBcgs2
+struct SepOpBcgs2 : SepOpBase<SepOpBcgs2<JACOBI>>
 {
-    const double *r, *vv, *dinv;
+    static constexpr int NRIM = 2, NEX = JACOBI ? 1 : 0;
+    static constexpr bool NEEDS_RAW = false;
+    const double *src[2];
+    const double *ex[1];
     double *s, *t_out;
     double malpha;
     double acc[3];
+    __device__ __forceinline__ double operand(const double (&q)[2]) const { return __dadd_rn(__dmul_rn(malpha, q[1]), q[0]); }  // VecWAXPY(S,-alpha,V,R)
     template <class I>
-    __device__ __forceinline__ double val(I j) const { return __dadd_rn(__dmul_rn(malpha, vv[j]), r[j]); }  // VecWAXPY(S,-alpha,V,R)
-    template <class I>
-    __device__ __forceinline__ void emit(I i, double own, double t)
+    __device__ __forceinline__ void emit(I i, double own, double t, const double (&)[2], const double (&e)[NEX + 1])
     {
         s[i] = own;
-        if (JACOBI) t = __dmul_rn(t, dinv[i]);
+        if (JACOBI) t = __dmul_rn(t, e[0]);
         t_out[i] = t;
         acc[0] = fma(own, t, acc[0]);
         acc[1] = fma(t, t, acc[1]);
@@ -378,42 +500,76 @@ struct SepOpBcgs2
     }
 };
 
-template <int XR, bool HYB>
-__global__ void __launch_bounds__(256) k_sep_tile_apply(SepDev A, SepTilePlan T, const double *x, double *y)
+template <int XR, int R, class Op>
+constexpr size_t sep_tile_smem_bytes()
 {
-    SepOpApply op{x, y};
-    sep_tile_rows<XR, HYB>(A, T, op);
+    return SepTileSmem<XR, R, Op::NRIM, Op::NRIM + 1 + Op::NEX>::bytes;
 }
 
-template <int XR, bool HYB, bool JACOBI, int NULLMODE>
+template <int XR, bool HYB, int R>
+__global__ void __launch_bounds__(256) k_sep_tile_apply(SepDev A, SepTilePlan T, const double *x, double *y)
+{
+    SepOpApply op;
+    op.src[0] = x;
+    op.ex[0] = nullptr;
+    op.y = y;
+    sep_tile_rows<XR, HYB, R>(A, T, op);
+}
+
+template <int XR, bool HYB, int R, bool JACOBI, int NULLMODE>
 __global__ void __launch_bounds__(256) k_sep_tile_cg_spmv(SepDev A, SepTilePlan T, CsrVecs v, ReduceWs ws, DevState *st, SolveConsts kc,
                                                           double *hist)
 {
     if (st->done) return;
-    SepOpCg<JACOBI, NULLMODE> op{v, st->shift, st->b, st->a, st->pending != 0, {0.0}};
-    sep_tile_rows<XR, HYB>(A, T, op);
+    SepOpCg<JACOBI, NULLMODE> op;
+    op.src[0] = v.r;
+    op.src[1] = v.p_in;
+    if (JACOBI) op.src[2] = v.dinv;
+    if (NULLMODE == 2) op.src[2 + (JACOBI ? 1 : 0)] = v.nv;
+    op.ex[0] = v.x;
+    op.x = v.x;
+    op.p_out = v.p_out;
+    op.w = v.w;
+    op.shift = st->shift;
+    op.bcoef = st->b;
+    op.aprev = st->a;
+    op.xupd = st->pending != 0;
+    op.acc[0] = 0.0;
+    sep_tile_rows<XR, HYB, R>(A, T, op);
     csr_reduce_finalize<1>(op.acc, FIN_SPMV, ws, st, kc, hist);
 }
 
-template <int XR, bool JACOBI>
+template <int XR, int R, bool JACOBI>
 __global__ void __launch_bounds__(256) k_sep_tile_bcgs_spmv1(SepDev A, SepTilePlan T, const double *p, const double *dinv,
                                                              const double *rp, double *vv, ReduceWs ws, DevState *st, SolveConsts kc,
                                                              double *hist)
 {
     if (st->done) return;
-    SepOpBcgs1<JACOBI> op{p, dinv, rp, vv, {0.0}};
-    sep_tile_rows<XR, false>(A, T, op);
+    SepOpBcgs1<JACOBI> op;
+    op.src[0] = p;
+    op.ex[0] = rp;
+    if (JACOBI) op.ex[JACOBI ? 1 : 0] = dinv;
+    op.vv = vv;
+    op.acc[0] = 0.0;
+    sep_tile_rows<XR, false, R>(A, T, op);
     csr_reduce_finalize<1>(op.acc, FIN_BCGS_D1, ws, st, kc, hist);
 }
 
-template <int XR, bool JACOBI>
+template <int XR, int R, bool JACOBI>
 __global__ void __launch_bounds__(256) k_sep_tile_bcgs_spmv2(SepDev A, SepTilePlan T, const double *r, const double *vv,
                                                              const double *dinv, double *s, double *t_out, ReduceWs ws, DevState *st,
                                                              SolveConsts kc, double *hist)
 {
     if (st->done) return;
-    SepOpBcgs2<JACOBI> op{r, vv, dinv, s, t_out, -st->alpha, {0.0, 0.0, 0.0}};
-    sep_tile_rows<XR, false>(A, T, op);
+    SepOpBcgs2<JACOBI> op;
+    op.src[0] = r;
+    op.src[1] = vv;
+    op.ex[0] = dinv;
+    op.s = s;
+    op.t_out = t_out;
+    op.malpha = -st->alpha;
+    op.acc[0] = op.acc[1] = op.acc[2] = 0.0;
+    sep_tile_rows<XR, false, R>(A, T, op);
     csr_reduce_finalize<3>(op.acc, FIN_BCGS_OMEGA, ws, st, kc, hist);
 }
 

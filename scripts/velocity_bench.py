@@ -20,6 +20,7 @@ ap.add_argument("--no-cpu", action="store_true")
 ap.add_argument("--graph", type=int, default=0)
 ap.add_argument("--tiles", type=int, nargs="+", default=[-1], help="tuning sep_tile values for the line-coefficient form (-1: the library's rule)")
 ap.add_argument("--zchunks", type=int, nargs="+", default=[0], help="tuning sep_zchunk values tried with every tile > 0")
+ap.add_argument("--stages", type=int, nargs="+", default=[3], help="tuning sep_stages values tried with every tile > 0")
 ap.add_argument("--no-csr", action="store_true")
 a = ap.parse_args()
 n = tuple(a.size)
@@ -32,13 +33,15 @@ rows = A.shape[0]
 rng = np.random.default_rng(3)
 b = rng.standard_normal(rows)
 M = pb.Mat.from_scipy(A)
-variants = [("staggered", t, z) for t in a.tiles for z in (a.zchunks if t > 0 else [0])] + ([] if a.no_csr else [("csr", 0, 0)])
-for form, tile, zchunk in variants:
+variants = [("staggered", t, z, g) for t in a.tiles for z in (a.zchunks if t > 0 else [0]) for g in (a.stages if t > 0 else [3])] + \
+           ([] if a.no_csr else [("csr", 0, 0, 3)])
+for form, tile, zchunk, stages in variants:
     s = pb.LinSolverB200("velocity", "None")
     s.setOptions(ksp_type="bcgs", pc_type="jacobi", rtol=0.0, atol=0.0, max_it=a.iters)
     s.setTuning("csr_graph", a.graph)
     s.setTuning("sep_tile", tile)
     s.setTuning("sep_zchunk", zchunk)
+    s.setTuning("sep_stages", stages)
     s.setGrid(pb.Grid([np.asarray(w) for w in widths], (False,) * 3, 0.01))
     s.setStaggered(form == "staggered")
     s.setMatrix(M)
@@ -55,7 +58,7 @@ for form, tile, zchunk in variants:
     per_it = best["loop_ms"] / its * 1e-3
     model = 176.0 if s.operator == "staggered" else 360.0
     print(json.dumps({"system": "velocity A = I/dt - c nu L, BiCGStab + Jacobi", "size": list(n), "rows": rows, "operator": s.operator,
-                      "sep_tile": tile, "sep_zchunk": zchunk,
+                      "sep_tile": tile, "sep_zchunk": zchunk, "sep_stages": stages,
                       "iterations": its, "loop_ms": round(best["loop_ms"], 3), "iterations_per_s": round(1.0 / per_it, 1),
                       "model_bytes_per_row": model, "model_GBs": round(model * rows / per_it / 1e9, 1),
                       "launches": best["launches"], "csr_graph": a.graph, "assembly_s": round(t_asm, 1),

@@ -543,7 +543,7 @@ EMU_API int emu_csr_solve(int64_t n, const int64_t *rowptr, const int32_t *col, 
 
 namespace {
 // tiled kernels of sep_tile.cuh instead of the row-per-thread ones: 0 = off, 2 / 4 = tile of 64 / 128 cells in x
-int g_sep_xr = 0, g_sep_zchunk = 0, g_sep_target = 0;
+int g_sep_xr = 0, g_sep_zchunk = 0, g_sep_target = 0, g_sep_stages = 3;
 }  // namespace
 extern "C" EMU_API void emu_set_sep_tile(int xr, int zchunk, int target_blocks)
 {
@@ -551,6 +551,7 @@ extern "C" EMU_API void emu_set_sep_tile(int xr, int zchunk, int target_blocks)
     g_sep_zchunk = zchunk;
     g_sep_target = target_blocks;
 }
+extern "C" EMU_API void emu_set_sep_stages(int stages) { g_sep_stages = stages == 4 ? 4 : 3; }
 namespace {
 SepDev make_sep(int nfields, const int64_t *dims, const int *periodic, const double *widths, int64_t n, const double *coef,
                 const double *diag, const int64_t *rem_rowptr, const int32_t *rem_col, const double *rem_val)
@@ -616,13 +617,16 @@ EMU_API int emu_sep_solve(int nfields, const int64_t *dims, const int *periodic,
     const bool hyb = widths != nullptr;
     const SepTilePlan T = sep_tile_plan(A, xr ? xr : 2, g_sep_zchunk, g_sep_target > 0 ? g_sep_target : 24);
     const dim3 tgrid((unsigned)T.blocks());
-    const size_t tsmem = sep_tile_smem_bytes(xr ? xr : 2);
     if (mode == 0)
     {
-        if (xr == 2 && hyb) emu::launch(tgrid, dim3(256), tsmem, [&] { k_sep_tile_apply<2, true>(A, T, b, x_out); });
-        else if (xr == 2) emu::launch(tgrid, dim3(256), tsmem, [&] { k_sep_tile_apply<2, false>(A, T, b, x_out); });
-        else if (xr == 4 && hyb) emu::launch(tgrid, dim3(256), tsmem, [&] { k_sep_tile_apply<4, true>(A, T, b, x_out); });
-        else if (xr == 4) emu::launch(tgrid, dim3(256), tsmem, [&] { k_sep_tile_apply<4, false>(A, T, b, x_out); });
+#define EMU_TA(XR, HYB, R) emu::launch(tgrid, dim3(256), sep_tile_smem_bytes<XR, R, SepOpApply>(), [&] { k_sep_tile_apply<XR, HYB, R>(A, T, b, x_out); })
+#define EMU_TAR(XR, HYB) do { if (g_sep_stages == 4) EMU_TA(XR, HYB, 4); else EMU_TA(XR, HYB, 3); } while (0)
+        if (xr == 2 && hyb) EMU_TAR(2, true);
+        else if (xr == 2) EMU_TAR(2, false);
+        else if (xr == 4 && hyb) EMU_TAR(4, true);
+        else if (xr == 4) EMU_TAR(4, false);
+#undef EMU_TA
+#undef EMU_TAR
         else emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_apply(A, b, x_out); });
         return 0;
     }
@@ -641,12 +645,16 @@ EMU_API int emu_sep_solve(int nfields, const int64_t *dims, const int *periodic,
         for (int it = 0; it < max_it + 2 && !st.done; ++it)
         {
             emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_p(n, r.data(), vv.data(), p0.data(), &st); });
-#define EMU_T1(XR, JAC) emu::launch(tgrid, dim3(256), tsmem, [&] { k_sep_tile_bcgs_spmv1<XR, JAC>(A, T, p0.data(), dv, rp.data(), vv.data(), W.ws, &st, kc, hist); })
-#define EMU_T2(XR, JAC) emu::launch(tgrid, dim3(256), tsmem, [&] { k_sep_tile_bcgs_spmv2<XR, JAC>(A, T, r.data(), vv.data(), dv, s.data(), t.data(), W.ws, &st, kc, hist); })
-            if (xr == 2) { if (jacobi) EMU_T1(2, true); else EMU_T1(2, false); }
-            else { if (jacobi) EMU_T1(4, true); else EMU_T1(4, false); }
-            if (xr == 2) { if (jacobi) EMU_T2(2, true); else EMU_T2(2, false); }
-            else { if (jacobi) EMU_T2(4, true); else EMU_T2(4, false); }
+#define EMU_T1(XR, R, JAC) emu::launch(tgrid, dim3(256), sep_tile_smem_bytes<XR, R, SepOpBcgs1<JAC>>(), [&] { k_sep_tile_bcgs_spmv1<XR, R, JAC>(A, T, p0.data(), dv, rp.data(), vv.data(), W.ws, &st, kc, hist); })
+#define EMU_T2(XR, R, JAC) emu::launch(tgrid, dim3(256), sep_tile_smem_bytes<XR, R, SepOpBcgs2<JAC>>(), [&] { k_sep_tile_bcgs_spmv2<XR, R, JAC>(A, T, r.data(), vv.data(), dv, s.data(), t.data(), W.ws, &st, kc, hist); })
+#define EMU_T1R(XR, JAC) do { if (g_sep_stages == 4) EMU_T1(XR, 4, JAC); else EMU_T1(XR, 3, JAC); } while (0)
+#define EMU_T2R(XR, JAC) do { if (g_sep_stages == 4) EMU_T2(XR, 4, JAC); else EMU_T2(XR, 3, JAC); } while (0)
+            if (xr == 2) { if (jacobi) EMU_T1R(2, true); else EMU_T1R(2, false); }
+            else { if (jacobi) EMU_T1R(4, true); else EMU_T1R(4, false); }
+            if (xr == 2) { if (jacobi) EMU_T2R(2, true); else EMU_T2R(2, false); }
+            else { if (jacobi) EMU_T2R(4, true); else EMU_T2R(4, false); }
+#undef EMU_T1R
+#undef EMU_T2R
 #undef EMU_T1
 #undef EMU_T2
             emu::launch(dim3(blocks), dim3(256), 0, [&] { k_bcgs_upd(n, p0.data(), s.data(), t.data(), rp.data(), x.data(), r.data(), W.ws, &st, kc, hist); });
@@ -690,7 +698,8 @@ EMU_API int emu_sep_solve(int nfields, const int64_t *dims, const int *periodic,
         {
             CsrVecs v{r.data(), pp[it & 1], pp[(it & 1) ^ 1], w.data(), x.data(), dv, nullvec};
 #define EMU_CS(JAC, NM) emu::launch(dim3(blocks), dim3(256), 0, [&] { k_sep_cg_spmv<JAC, NM>(A, v, W.ws, &st, kc, hist); })
-#define EMU_CT(XR, HYB, JAC, NM) emu::launch(tgrid, dim3(256), tsmem, [&] { k_sep_tile_cg_spmv<XR, HYB, JAC, NM>(A, T, v, W.ws, &st, kc, hist); })
+#define EMU_CTR(XR, HYB, R, JAC, NM) emu::launch(tgrid, dim3(256), sep_tile_smem_bytes<XR, R, SepOpCg<JAC, NM>>(), [&] { k_sep_tile_cg_spmv<XR, HYB, R, JAC, NM>(A, T, v, W.ws, &st, kc, hist); })
+#define EMU_CT(XR, HYB, JAC, NM) do { if (g_sep_stages == 4) EMU_CTR(XR, HYB, 4, JAC, NM); else EMU_CTR(XR, HYB, 3, JAC, NM); } while (0)
 #define EMU_CTN(XR, HYB, JAC) do { if (nm == 2) EMU_CT(XR, HYB, JAC, 2); else if (nm == 1) EMU_CT(XR, HYB, JAC, 1); else EMU_CT(XR, HYB, JAC, 0); } while (0)
 #define EMU_CTJ(XR, HYB) do { if (jacobi) EMU_CTN(XR, HYB, true); else EMU_CTN(XR, HYB, false); } while (0)
             if (xr == 2) { if (hyb) EMU_CTJ(2, true); else EMU_CTJ(2, false); }
@@ -699,6 +708,7 @@ EMU_API int emu_sep_solve(int nfields, const int64_t *dims, const int *periodic,
             else { if (nm == 2) EMU_CS(false, 2); else if (nm == 1) EMU_CS(false, 1); else EMU_CS(false, 0); }
 #undef EMU_CS
 #undef EMU_CT
+#undef EMU_CTR
 #undef EMU_CTN
 #undef EMU_CTJ
             upd(false, nm == 2 ? (int)FIN_CSR_UPDATE : (int)FIN_UPDATE);
@@ -1008,8 +1018,7 @@ EMU_API int emu_hybrid_mg_pcg(int dim, const int64_t *n3, const int *periodic, c
             // the hybrid operator always carries its face-area weights (HYB = true)
             const SepTilePlan T = sep_tile_plan(A, g_sep_xr, g_sep_zchunk, g_sep_target > 0 ? g_sep_target : 24);
             const dim3 tgrid((unsigned)T.blocks());
-            const size_t tsmem = sep_tile_smem_bytes(g_sep_xr);
-#define EMU_HT(XR, NM) emu::launch(tgrid, dim3(256), tsmem, [&] { k_sep_tile_cg_spmv<XR, true, false, NM>(A, T, v, W.ws, &st, kc, hist); })
+#define EMU_HT(XR, NM) emu::launch(tgrid, dim3(256), sep_tile_smem_bytes<XR, 3, SepOpCg<false, NM>>(), [&] { k_sep_tile_cg_spmv<XR, true, 3, false, NM>(A, T, v, W.ws, &st, kc, hist); })
             if (g_sep_xr == 2) { if (nm == 2) EMU_HT(2, 2); else if (nm == 1) EMU_HT(2, 1); else EMU_HT(2, 0); }
             else { if (nm == 2) EMU_HT(4, 2); else if (nm == 1) EMU_HT(4, 1); else EMU_HT(4, 0); }
 #undef EMU_HT

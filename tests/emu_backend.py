@@ -77,7 +77,7 @@ def make_module(emu):
                 xr = 2 if self.operator == "staggered" and any(d[2] >= 8 for d in self._dims) else 0
                 if self.operator == "hybrid":
                     xr = 2 if (self._grid.dim == 3 and self._grid.n[2] >= 8) else 0
-            return K._sep_tiles(emu, xr if xr in (2, 4) else 0, self._tuning.get("sep_zchunk", 0))
+            return K._sep_tiles(emu, 2 if xr == 2 else 0, self._tuning.get("sep_zchunk", 0), stages=self._tuning.get("sep_stages", 3))
 
         # ---- operator
         def setGrid(self, grid):

@@ -50,6 +50,7 @@ def emu():
                                 C.POINTER(C.c_int32), _dp, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_double, C.c_double, C.c_int,
                                 _dp, _dp, _dp, C.c_int, _ip, _ip, _ip]
     L.emu_set_sep_tile.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.emu_set_sep_stages.argtypes = [C.c_int]
     return L
 
 
@@ -511,16 +512,19 @@ def test_emulated_line_coefficient_spmv_on_random_stencil_blocks(emu):
 
 class _sep_tiles:
     """Run the line-coefficient operator through the tiled kernels of sep_tile.cuh (xr = 2 / 4: tiles of 64 / 128 cells
-    in x; zchunk planes per chunk, 0 = the launch rule; target = the CTA count that rule aims for)."""
+    in x; zchunk planes per chunk, 0 = the launch rule; target = the CTA count that rule aims for; stages = planes in the
+    per-thread cp.async queue, 3 or 4)."""
 
-    def __init__(self, L, xr, zchunk=0, target=24):
-        self.L, self.args = L, (xr, zchunk, target)
+    def __init__(self, L, xr, zchunk=0, target=24, stages=3):
+        self.L, self.args, self.stages = L, (xr, zchunk, target), stages
 
     def __enter__(self):
         self.L.emu_set_sep_tile(*self.args)
+        self.L.emu_set_sep_stages(self.stages)
 
     def __exit__(self, *exc):
         self.L.emu_set_sep_tile(0, 0, 0)
+        self.L.emu_set_sep_stages(3)
 
 
 TILE_VARIANTS = [(2, 0), (2, 1), (2, 3), (4, 0), (4, 2)]
@@ -537,9 +541,10 @@ def test_emulated_tiled_line_coefficient_spmv_is_bit_identical(emu, shape, per, 
     Ao = orc.Csr.from_arrays(A.shape[0], A.shape[1], A.indptr, A.indices, A.data)
     dims, p = _velocity_dims(shape, per)
     x = np.random.default_rng(3).standard_normal(A.shape[0])
-    with _sep_tiles(emu, xr, zchunk):
-        y, _, _, _ = _sep_solve(emu, dims, p, A, x, mode="apply")
-    assert np.array_equal(y, Ao.spmv(x))
+    for stages in (3, 4):
+        with _sep_tiles(emu, xr, zchunk, stages=stages):
+            y, _, _, _ = _sep_solve(emu, dims, p, A, x, mode="apply")
+        assert np.array_equal(y, Ao.spmv(x)), stages
 
 
 @pytest.mark.parametrize("xr,zchunk", [(2, 2), (4, 0)])
@@ -591,7 +596,8 @@ def test_emulated_tiled_line_coefficient_krylov_paths(emu, pc, xr, zchunk):
     b = np.random.default_rng(2).standard_normal(A.shape[0])
     ref = orc.ksp_solve(Ao, b, ksp_type="bcgs", pc_type=pc, rtol=0.0, atol=1e-8, max_it=300)
     x0, h0, i0, r0 = _sep_solve(emu, dims, p, A, b, mode="bcgs", pc=pc, atol=1e-8, max_it=300)
-    with _sep_tiles(emu, xr, zchunk):
+    stages = 4 if zchunk else 3
+    with _sep_tiles(emu, xr, zchunk, stages=stages):
         x, hist, its, reason = _sep_solve(emu, dims, p, A, b, mode="bcgs", pc=pc, atol=1e-8, max_it=300)
     assert abs(its - i0) <= 1 and reason == r0 == ref.reason == 3
     # BiCGStab amplifies the rounding of its dot products from iteration to iteration: tight over the first entries,
@@ -606,7 +612,7 @@ def test_emulated_tiled_line_coefficient_krylov_paths(emu, pc, xr, zchunk):
     dims, p = _velocity_dims(shape, per)
     b = np.random.default_rng(6).standard_normal(A.shape[0])
     x0, h0, i0, r0 = _sep_solve(emu, dims, p, A, b, mode="cg", pc=pc, max_it=12)
-    with _sep_tiles(emu, xr, zchunk):
+    with _sep_tiles(emu, xr, zchunk, stages=stages):
         x, hist, its, reason = _sep_solve(emu, dims, p, A, b, mode="cg", pc=pc, max_it=12)
     assert (its, reason) == (i0, r0)
     np.testing.assert_allclose(hist, h0, rtol=1e-12)
@@ -621,7 +627,7 @@ def test_emulated_tiled_line_coefficient_krylov_paths(emu, pc, xr, zchunk):
     xs = np.random.default_rng(5).standard_normal(M.shape[0]); xs -= (xs @ nv) * nv
     bm = M @ xs
     refm = orc.ksp_solve(Mo, bm, pc_type=pc, rtol=0, atol=0, max_it=15, nullvecs=nv)
-    with _sep_tiles(emu, xr, zchunk):
+    with _sep_tiles(emu, xr, zchunk, stages=stages):
         y, _, _, _ = _sep_solve(emu, [[10, 9, 1]], (0, 0, 0), M, xs, mode="apply")
         x, hist, its, reason = _sep_solve(emu, [[10, 9, 1]], (0, 0, 0), M, bm, mode="cg", pc=pc, nullvec=nv, max_it=15)
     assert np.array_equal(y, Mo.spmv(xs))

@@ -27,18 +27,18 @@ def test_staggered_ibpm_like_body(pbe, pc):
     T2.test_ibpm_modified_poisson_stencil_block_plus_remainder(pbe, pc)
 
 
-@pytest.mark.parametrize("shape,per,tile,zchunk", [((70, 19, 12), (0, 0, 0), 2, 5), ((9, 8, 7), (1, 0, 1), 4, 0), ((66, 17), (0, 1), 2, 0)])
-def test_tiled_velocity_body(pbe, shape, per, tile, zchunk):
-    T2.test_tiled_kernels_velocity_system(pbe, shape, per, tile, zchunk)
+@pytest.mark.parametrize("shape,per,zchunk,stages", [((70, 19, 12), (0, 0, 0), 5, 3), ((9, 8, 7), (1, 0, 1), 0, 4), ((66, 17), (0, 1), 0, 3)])
+def test_tiled_velocity_body(pbe, shape, per, zchunk, stages):
+    T2.test_tiled_kernels_velocity_system(pbe, shape, per, zchunk, stages)
 
 
-@pytest.mark.parametrize("pc,tile", [("none", 2), ("jacobi", 4)])
-def test_tiled_ibpm_like_body(pbe, pc, tile):
-    T2.test_tiled_kernels_ibpm_like_system_with_remainder(pbe, pc, tile)
+@pytest.mark.parametrize("pc,stages", [("none", 3), ("jacobi", 4)])
+def test_tiled_ibpm_like_body(pbe, pc, stages):
+    T2.test_tiled_kernels_ibpm_like_system_with_remainder(pbe, pc, stages)
 
 
 def test_tiled_hybrid_body(pbe):
-    T2.test_tiled_kernels_hybrid_operator_on_a_stretched_ibpm_system(pbe, 2)
+    T2.test_tiled_kernels_hybrid_operator_on_a_stretched_ibpm_system(pbe, 3)
 
 
 def test_default_kernel_choice_body(pbe):

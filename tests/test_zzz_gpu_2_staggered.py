@@ -22,7 +22,7 @@ def pb():
 
 def _pair(pb, name, grid, M, tile=0, **opts):
     """Two solvers on the same matrix: line-coefficient form and plain CSR.  tile = 0: the row-per-thread kernels of
-    sep_kernels.cuh, whose dot products are summed like those of the CSR kernels (bit-identical histories); 2 / 4: the
+    sep_kernels.cuh, whose dot products are summed like those of the CSR kernels (bit-identical histories); 2: the
     tiled plane-marching kernels of sep_tile.cuh (same row sums bit for bit, dot products in another order)."""
     out = []
     for staggered in (True, False):
@@ -144,21 +144,22 @@ def test_hybrid_operator_on_a_stretched_ibpm_system(pb, dim):
     s.destroy(); c.destroy()
 
 
-@pytest.mark.parametrize("tile,zchunk", [(2, 0), (2, 5), (4, 0)])
+@pytest.mark.parametrize("zchunk,stages", [(0, 3), (5, 3), (0, 4), (3, 4)])
 @pytest.mark.parametrize("shape,per", [((70, 19, 12), (0, 0, 0)), ((9, 8, 7), (1, 0, 1)), ((40, 20, 16), (0, 1, 0)), ((66, 17), (0, 1))])
-def test_tiled_kernels_velocity_system(pb, shape, per, tile, zchunk):
-    """sep_tile.cuh on the device: several tiles in x and y, ragged edges, one and many z chunks, periodic axes (wrapped
-    cells and nothing else go through sep_row).  y = A x is bit-identical to MatMult_SeqAIJ on the assembled matrix;
+def test_tiled_kernels_velocity_system(pb, shape, per, zchunk, stages):
+    """sep_tile.cuh on the device: several tiles in x and y, ragged edges, one and many z chunks, three and four stages in
+    the per-thread cp.async queue, periodic axes (wrapped cells and nothing else go through sep_row).  y = A x is bit-identical to MatMult_SeqAIJ on the assembled matrix;
     BiCGStab + Jacobi follows the row-per-thread kernels (dot products summed in another order: 1e-9 over the first
     entries) and the oracle."""
     widths = H.make_widths(shape)
     A, _ = H.velocity_system(widths, per, dt=0.01, nu=0.01, c=0.5)
     Ao = orc.Csr.from_arrays(A.shape[0], A.shape[1], A.indptr, A.indices, A.data)
     opts = dict(ksp_type="bcgs", pc_type="jacobi", rtol=0.0, atol=1e-9, max_it=500)
-    t, _c = _pair(pb, "velocity", H.grid_of(widths, per), A, tile=tile, **opts)
+    t, _c = _pair(pb, "velocity", H.grid_of(widths, per), A, tile=2, **opts)
     s, _c2 = _pair(pb, "velocity", H.grid_of(widths, per), A, tile=0, **opts)
     _c.destroy(); _c2.destroy()
     t.setTuning("sep_zchunk", zchunk)
+    t.setTuning("sep_stages", stages)
     t.setMatrix(pb.Mat.from_scipy(A))
     s.setMatrix(pb.Mat.from_scipy(A))
     assert t.operator == s.operator == "staggered"
@@ -180,9 +181,9 @@ def test_tiled_kernels_velocity_system(pb, shape, per, tile, zchunk):
     t.destroy(); s.destroy()
 
 
-@pytest.mark.parametrize("tile", [2, 4])
+@pytest.mark.parametrize("stages", [3, 4])
 @pytest.mark.parametrize("pc", ["none", "jacobi"])
-def test_tiled_kernels_ibpm_like_system_with_remainder(pb, pc, tile):
+def test_tiled_kernels_ibpm_like_system_with_remainder(pb, pc, stages):
     """Stencil block + remainder rows and columns, CG with the explicit null-space vector (ibpm.cpp:251-267) on the tiled
     kernels: the remainder entries of a stencil row follow its stencil terms, the rows behind the block take sep_row."""
     shape, nf = (70, 26), 14
@@ -200,8 +201,9 @@ def test_tiled_kernels_ibpm_like_system_with_remainder(pb, pc, tile):
     xs = rng.standard_normal(M.shape[0]); xs -= (xs @ nv) * nv
     b = M @ xs
     nit = 40
-    t, c = _pair(pb, "poisson", pb.Grid(widths, (False, False, False), 0.01), M, tile=tile, pc_type=pc, rtol=0.0, atol=0.0, max_it=nit)
+    t, c = _pair(pb, "poisson", pb.Grid(widths, (False, False, False), 0.01), M, tile=2, pc_type=pc, rtol=0.0, atol=0.0, max_it=nit)
     c.destroy()
+    t.setTuning("sep_stages", stages)
     t.setMatrix(pb.Mat.from_scipy(M).setNullSpace(False, nv))
     assert t.operator == "staggered"
     assert np.array_equal(t.apply(xs), Mo.spmv(xs))
@@ -215,8 +217,8 @@ def test_tiled_kernels_ibpm_like_system_with_remainder(pb, pc, tile):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("tile", [2, 4])
-def test_tiled_kernels_hybrid_operator_on_a_stretched_ibpm_system(pb, tile):
+@pytest.mark.parametrize("stages", [3, 4])
+def test_tiled_kernels_hybrid_operator_on_a_stretched_ibpm_system(pb, stages):
     """The hybrid form (pressure block of a stretched grid with its face areas + remainder) on the tiled kernels."""
     sub = [{"end": 0.6, "cells": 6, "stretchRatio": 1.0 / 1.2}, {"end": 1.4, "cells": 10, "stretchRatio": 1.0},
            {"end": 2.0, "cells": 6, "stretchRatio": 1.2}]
@@ -228,8 +230,9 @@ def test_tiled_kernels_hybrid_operator_on_a_stretched_ibpm_system(pb, tile):
     xs = rng.standard_normal(M.shape[0]); xs -= (xs @ nv) * nv
     b = Mo.spmv(xs)
     nit = 20
-    t, c = _pair(pb, "poisson", pb.Grid(widths, (False, False, False), 0.01), M, tile=tile, pc_type="jacobi", rtol=0.0, atol=0.0, max_it=nit)
+    t, c = _pair(pb, "poisson", pb.Grid(widths, (False, False, False), 0.01), M, tile=2, pc_type="jacobi", rtol=0.0, atol=0.0, max_it=nit)
     c.destroy()
+    t.setTuning("sep_stages", stages)
     t.setMatrix(pb.Mat.from_scipy(M).setNullSpace(False, nv))
     assert t.operator == "hybrid"
     assert np.array_equal(t.apply(xs), b)
