@@ -74,9 +74,9 @@ def make_module(emu):
             """The kernel choice of sep_tile_xr (sep_solver.inc) for the line-coefficient operator."""
             xr = self._tuning.get("sep_tile", -1)
             if xr < 0:
-                xr = 2 if self.operator == "staggered" and any(d[2] >= 8 for d in self._dims) else 0
+                xr = 2 if self.operator == "staggered" and any(d[2] >= 8 and d[0] >= 48 for d in self._dims) else 0
                 if self.operator == "hybrid":
-                    xr = 2 if (self._grid.dim == 3 and self._grid.n[2] >= 8) else 0
+                    xr = 2 if (self._grid.dim == 3 and self._grid.n[2] >= 8 and self._grid.n[0] >= 48) else 0
             return K._sep_tiles(emu, 2 if xr == 2 else 0, self._tuning.get("sep_zchunk", 0), stages=self._tuning.get("sep_stages", 3))
 
         # ---- operator

@@ -248,7 +248,7 @@ def test_tiled_kernels_hybrid_operator_on_a_stretched_ibpm_system(pb, stages):
 def test_default_kernel_choice_of_the_line_coefficient_operator(pb):
     """Without a tuning key the library picks the kernels itself (sep_tile_xr in sep_solver.inc); whatever it picks, the
     product is the assembled MatMult bit for bit and the solve converges like the oracle's."""
-    shape, per = (40, 20, 16), (0, 0, 0)
+    shape, per = (72, 20, 16), (0, 0, 0)
     widths = H.make_widths(shape)
     A, _ = H.velocity_system(widths, per, dt=0.01, nu=0.01, c=0.5)
     Ao = orc.Csr.from_arrays(A.shape[0], A.shape[1], A.indptr, A.indices, A.data)
