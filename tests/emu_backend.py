@@ -70,9 +70,11 @@ def make_module(emu):
         def setTuning(self, key, value):
             self._tuning[key] = int(value)
 
-        def _tiles(self):
+        def _tiles(self, bcgs=False):
             """The kernel choice of sep_tile_xr (sep_solver.inc) for the line-coefficient operator."""
             xr = self._tuning.get("sep_tile", -1)
+            if xr < 0 and not bcgs:
+                xr = 0
             if xr < 0:
                 xr = 2 if self.operator == "staggered" and any(d[2] >= 8 and d[0] >= 48 for d in self._dims) else 0
                 if self.operator == "hybrid":
@@ -192,7 +194,7 @@ def make_module(emu):
             else:
                 per = [int(bool(p)) for p in g.periodic][:3]
                 mode = "bcgs" if o.ksp_type == 1 else "cg"
-                with self._tiles():
+                with self._tiles(bcgs=(mode == "bcgs")):
                     if self.operator == "hybrid":
                         xs, hist, its, reason = K._sep_solve(emu, None, per[: g.dim], self._M, b, mode=mode, pc=pc, has_const=has_const,
                                                              nullvec=nv, hybrid_widths=g.widths, dt=g.dt, **kw)
