@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--no-profile", action="store_true", help="no per-kernel events (CUDA-graph batches instead)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-bench history comparison with the oracle")
+    ap.add_argument("--no-other-paths", action="store_true", help="skip the velocity / multigrid side measurements (1 GPU only, after the headline)")
     ap.add_argument("--cpu-iters", type=int, default=0, help="iterations of the CPU sample (0 = auto; reference arm: --iters)")
     ap.add_argument("--cpu-budget", type=float, default=900.0, help="reference arm: seconds after which steps become bounded samples")
     ap.add_argument("--tune", nargs="*", default=[], help="key=value launch knobs (kz_chunk, tile, upd_blocks)")
@@ -125,6 +126,42 @@ def parity_block(n, pc, hist, nit=30, tol=1e-10):
     rel = float(np.max(np.abs(h - ref.history[: nit + 1]) / ref.history[: nit + 1]))
     return {"max_rel": rel, "tol": tol, "ok": bool(rel <= tol), "entries": int(nit + 1),
             "against": "oracle KSPSolve_CG restatement (OpenMP summation), same right-hand side"}
+
+
+def other_paths_block(vel_size=(128, 128, 128), mg_size=(256, 256, 256), timeout_s=150):
+    """The other systems of SURVEY 8 timed by the same run, AFTER the headline measurement and outside every timed region
+    (one sub-process each, so nothing here can disturb or break the JSON line): the velocity system A = I/dt - c nu L with
+    BiCGStab + Jacobi (rows a10 / f1; scripts/velocity_bench.py: tiled kernels of sep_tile.cuh as the library picks them,
+    then the row-per-thread kernels) and the time to solution of the pressure solve with the multigrid preconditioner
+    (row f3; scripts/tts_bench.py).  Reported next to the headline, never part of it."""
+    root = os.path.dirname(os.path.abspath(__file__))
+    jobs = {
+        "velocity_bicgstab_jacobi": ["scripts/velocity_bench.py", "--size", *map(str, vel_size), "--no-cpu", "--no-csr", "--reps", "2",
+                                     "--tiles", "-1", "0"],
+        "poisson_cg_mg_time_to_solution": ["scripts/tts_bench.py", "--size", *map(str, mg_size), "--rtol", "1e-8", "--pcs", "mg", "--reps", "2",
+                                           "--mg-graph", "1", "--mg-tail", "1", "--mg-fuse", "1"],
+    }
+    out = {}
+    for name, cmd in jobs.items():
+        try:
+            r = subprocess.run([sys.executable, *cmd], cwd=root, capture_output=True, text=True, timeout=timeout_s)
+            rows = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if r.returncode != 0 or not rows:
+                out[name] = {"error": (r.stderr or r.stdout)[-300:]}
+            elif name.startswith("velocity"):
+                by = {row["sep_tile"]: row for row in rows}
+                t, o = by.get(-1), by.get(0)
+                out[name] = {"size": list(vel_size), "rows": t["rows"], "iterations": t["iterations"],
+                             "iterations_per_s": t["iterations_per_s"], "model_bytes_per_row": t["model_bytes_per_row"],
+                             "model_GBs": t["model_GBs"],
+                             "row_per_thread_kernels_iterations_per_s": o["iterations_per_s"] if o else None}
+            else:
+                m = rows[-1]
+                out[name] = {"size": list(mg_size), "rtol": m["rtol"], "iterations": m["iterations"], "solve_ms": m["solve_ms"],
+                             "launches": m["launches"], "max_rel_error": m["max_rel_error"]}
+        except Exception as e:  # noqa: BLE001  (a failure here must not cost the headline line)
+            out[name] = {"error": repr(e)[:300]}
+    return out
 
 
 def peaks():
@@ -499,8 +536,11 @@ def run_b200(args):
             "gpu_launches": int(launches), "clocks": clocks,
             "hbm_gbs_iteration": ITER_BYTES_PER_ROW * N * args.iters / (ms_per_step * 1e-3) / 1e9,
         }
-        print(json.dumps(line), flush=True)
     solver.destroy()
+    if comm.rank == 0:
+        if comm.nranks == 1 and not args.no_other_paths:
+            line["other_paths"] = other_paths_block()
+        print(json.dumps(line), flush=True)
     if comm.nranks > 1:
         import torch.distributed as dist
 
