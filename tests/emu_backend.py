@@ -76,9 +76,8 @@ def make_module(emu):
             if xr < 0 and not bcgs:
                 xr = 0
             if xr < 0:
-                xr = 2 if self.operator == "staggered" and any(d[2] >= 8 and d[0] >= 48 for d in self._dims) else 0
-                if self.operator == "hybrid":
-                    xr = 2 if (self._grid.dim == 3 and self._grid.n[2] >= 8 and self._grid.n[0] >= 48) else 0
+                big = sum(d[0] * d[1] * d[2] for d in self._dims) >= (1 << 20) if self.operator == "staggered" else False
+                xr = 2 if big and any(d[2] >= 8 and d[0] >= 48 for d in self._dims) else 0
             return K._sep_tiles(emu, 2 if xr == 2 else 0, self._tuning.get("sep_zchunk", 0), stages=self._tuning.get("sep_stages", 3))
 
         # ---- operator

@@ -50,7 +50,7 @@ def test_b200_arm_line():
 @pytest.mark.gpu
 def test_other_paths_block_reports_the_velocity_and_multigrid_solves():
     """The side measurements bench.py appends at N = 1 (velocity BiCGStab, multigrid time to solution): numbers, not
-    errors, on small systems (64 cells per line: the tiled kernels are the ones the library picks)."""
+    errors, on small systems."""
     sys.path.insert(0, ROOT)
     import bench
 
