@@ -128,7 +128,7 @@ def parity_block(n, pc, hist, nit=30, tol=1e-10):
             "against": "oracle KSPSolve_CG restatement (OpenMP summation), same right-hand side"}
 
 
-def other_paths_block(vel_size=(128, 128, 128), mg_size=(256, 256, 256), timeout_s=150):
+def other_paths_block(vel_size=(128, 128, 128), mg_size=(256, 256, 256), timeout_s=90):
     """The other systems of SURVEY 8 timed by the same run, AFTER the headline measurement and outside every timed region
     (one sub-process each, so nothing here can disturb or break the JSON line): the velocity system A = I/dt - c nu L with
     BiCGStab + Jacobi (rows a10 / f1; scripts/velocity_bench.py: tiled kernels of sep_tile.cuh as the library picks them,
