@@ -552,6 +552,32 @@ extern "C" EMU_API void emu_set_sep_tile(int xr, int zchunk, int target_blocks)
     g_sep_target = target_blocks;
 }
 extern "C" EMU_API void emu_set_sep_stages(int stages) { g_sep_stages = stages == 4 ? 4 : 3; }
+// launch geometry of the tiled kernels (sep_tile_plan, host code shared with sep_solver.inc) for the tests of its rules:
+// out = {stencil_blocks, surf_blocks, tail_blocks, surf_cells, then per field: tiles_x, tiles, nchunk, zchunk, block0, surf0}
+extern "C" EMU_API void emu_sep_tile_plan(int nfields, const int64_t *dims, const int *periodic, int64_t nrows, int xr, int zchunk,
+                                          int target_blocks, int *out)
+{
+    SepDev A{};
+    A.nf = nfields;
+    A.nrows = nrows;
+    long long off = 0;
+    for (int f = 0; f < nfields; ++f)
+    {
+        SepField &F = A.f[f];
+        F.n0 = (int)dims[3 * f]; F.n1 = (int)dims[3 * f + 1]; F.n2 = (int)dims[3 * f + 2];
+        F.per0 = periodic[0] && F.n0 >= 3; F.per1 = periodic[1] && F.n1 >= 3; F.per2 = periodic[2] && F.n2 >= 3;
+        F.off = off;
+        off += (long long)F.n0 * F.n1 * F.n2;
+    }
+    A.nsep = off;
+    const SepTilePlan T = sep_tile_plan(A, xr, zchunk, target_blocks);
+    out[0] = T.stencil_blocks; out[1] = T.surf_blocks; out[2] = T.tail_blocks; out[3] = T.surf_cells;
+    for (int f = 0; f < nfields; ++f)
+    {
+        int *o = out + 4 + 6 * f;
+        o[0] = T.f[f].tiles_x; o[1] = T.f[f].tiles; o[2] = T.f[f].nchunk; o[3] = T.f[f].zchunk; o[4] = T.f[f].block0; o[5] = T.f[f].surf0;
+    }
+}
 namespace {
 SepDev make_sep(int nfields, const int64_t *dims, const int *periodic, const double *widths, int64_t n, const double *coef,
                 const double *diag, const int64_t *rem_rowptr, const int32_t *rem_col, const double *rem_val)

@@ -547,6 +547,50 @@ def test_emulated_tiled_line_coefficient_spmv_is_bit_identical(emu, shape, per, 
         assert np.array_equal(y, Ao.spmv(x)), stages
 
 
+def test_tiled_kernel_launch_geometry(emu):
+    """sep_tile_plan (host code shared by sep_solver.inc and the emulation): the chunks of a field cover its planes exactly
+    once, the automatic rule never launches more CTAs than it was given slots for unless one chunk per tile already does,
+    keeps at least 4 planes per chunk, and sizes the surface / tail parts from the periodic faces and the remainder rows."""
+    emu.emu_sep_tile_plan.argtypes = [C.c_int, C.POINTER(C.c_int64), _ip, C.c_int64, C.c_int, C.c_int, C.c_int, _ip]
+
+    def plan(dims, per, extra, xr, zchunk, target):
+        d = np.ascontiguousarray(dims, dtype=np.int64).reshape(-1)
+        p = (C.c_int * 3)(*per)
+        out = (C.c_int * (4 + 6 * len(dims)))()
+        nsep = int(sum(a * b * c for a, b, c in dims))
+        emu.emu_sep_tile_plan(len(dims), d.ctypes.data_as(C.POINTER(C.c_int64)), p, nsep + extra, xr, zchunk, target, out)
+        o = list(out)
+        return o[:4], [o[4 + 6 * f: 10 + 6 * f] for f in range(len(dims))]
+
+    # the 128^3 velocity system on 148 SMs x 3 resident CTAs: 96 tiles per plane-set, 4 chunks of 32 planes = 384 CTAs
+    (sb, surf_b, tail_b, surf_c), fields = plan([[127, 128, 128], [128, 127, 128], [128, 128, 127]], (0, 0, 0), 0, 2, 0, 444)
+    assert (sb, surf_b, tail_b, surf_c) == (384, 0, 0, 0)
+    assert [f[:4] for f in fields] == [[2, 32, 4, 32]] * 3 and [f[4] for f in fields] == [0, 128, 256]
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        nf = int(rng.integers(1, 4))
+        per = [int(rng.integers(0, 2)) for _ in range(3)]
+        dims = [[int(rng.integers(3, 300)), int(rng.integers(3, 70)), int(rng.integers(1, 200))] for _ in range(nf)]
+        xr = int(rng.choice([2, 4])); zchunk = int(rng.choice([0, 0, 1, 5, 64])); target = int(rng.choice([24, 444, 1184]))
+        extra = int(rng.integers(0, 3)) * 100
+        (sb, surf_b, tail_b, surf_c), fields = plan(dims, per, extra, xr, zchunk, target)
+        b0 = 0; surf = 0; tiles_all = 0
+        for (n0, n1, n2), (tiles_x, tiles, nchunk, zc, block0, surf0) in zip(dims, fields):
+            assert tiles_x == -(-n0 // (32 * xr)) and tiles == tiles_x * -(-n1 // 8)
+            assert (nchunk - 1) * zc < n2 <= nchunk * zc                       # every plane in exactly one chunk, no empty chunk
+            assert block0 == b0 and surf0 == surf
+            if zchunk:
+                assert zc == min(zchunk, n2) or nchunk == -(-n2 // zchunk)
+            else:
+                assert zc >= min(4, n2)
+            b0 += tiles * nchunk; tiles_all += tiles
+            surf += (2 * n1 * n2 if per[0] else 0) + (2 * n0 * n2 if per[1] else 0) + (2 * n0 * n1 if (per[2] and n2 >= 3) else 0)
+        assert sb == b0 and surf_c == surf
+        if not zchunk:
+            assert sb <= max(target, tiles_all)
+        assert surf_b == min(-(-surf // 256), 128) and tail_b == min(-(-extra // 256), 64)
+
+
 @pytest.mark.parametrize("xr,zchunk", [(2, 2), (4, 0)])
 def test_emulated_tiled_kernels_do_not_depend_on_the_thread_schedule(emu, xr, zchunk):
     """One barrier per plane guards the double-buffered shared plane: with shuffled fiber order and random preemption at
