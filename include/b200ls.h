@@ -154,7 +154,7 @@ int b200ls_get_options(const b200ls_solver *h, b200ls_options *opts);
  * "mg_graph", "mg_tail" (coarse levels of the multigrid cycle as one launch), "mg_fuse" (residual update and reduction of
  * the preconditioned CG loop folded into the first / last fine-level step of the cycle): default 1 since round 2;
  * "sep_tile" (line-coefficient / hybrid operator: 2 = tiled plane-marching kernels, 0 = row-per-thread kernels, -1 = auto:
- * tiled for the BiCGStab solve of 3-D systems of >= 2^20 rows with lines of >= 48 cells, the timed case), "sep_zchunk"
+ * tiled for the BiCGStab solve of non-periodic 3-D systems of >= 2^20 rows, the timed case), "sep_zchunk"
  * (planes per z chunk of the tiled kernels, 0 = as many chunks as fit one resident wave), "sep_stages" (planes in their
  * per-thread cp.async queue: 3 or 4).
  * On several GPUs the keys must be set to the same values on every rank. */

@@ -77,7 +77,7 @@ def make_module(emu):
                 xr = 0
             if xr < 0:
                 big = sum(d[0] * d[1] * d[2] for d in self._dims) >= (1 << 20) if self.operator == "staggered" else False
-                xr = 2 if big and any(d[2] >= 8 and d[0] >= 48 for d in self._dims) else 0
+                xr = 2 if big and not any(self._grid.periodic) and any(d[2] >= 8 and d[0] >= 48 for d in self._dims) else 0
             return K._sep_tiles(emu, 2 if xr == 2 else 0, self._tuning.get("sep_zchunk", 0), stages=self._tuning.get("sep_stages", 3))
 
         # ---- operator
