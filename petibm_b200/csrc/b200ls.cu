@@ -18,8 +18,6 @@
 #include <cstring>
 #include <deque>
 #include <map>
-#include <mutex>
-#include <set>
 #include <string>
 #include <vector>
 
