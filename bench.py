@@ -133,7 +133,10 @@ def other_paths_block(vel_size=(128, 128, 128), mg_size=(256, 256, 256), timeout
     (one sub-process each, so nothing here can disturb or break the JSON line): the velocity system A = I/dt - c nu L with
     BiCGStab + Jacobi (rows a10 / f1; scripts/velocity_bench.py: tiled kernels of sep_tile.cuh as the library picks them,
     then the row-per-thread kernels) and the time to solution of the pressure solve with the multigrid preconditioner
-    (row f3; scripts/tts_bench.py).  Reported next to the headline, never part of it."""
+    (row f3; scripts/tts_bench.py).  Reported next to the headline, never part of it.  The velocity matrix is the INPUT
+    of that measurement: it is assembled on the host by tests/helpers.py (which plays PetIBM's role of handing a Mat to
+    setMatrix, with the oracle's mesh restatement for the cell widths); only the device solve is timed and nothing of the
+    oracle is on the solver's path."""
     root = os.path.dirname(os.path.abspath(__file__))
     jobs = {
         "velocity_bicgstab_jacobi": ["scripts/velocity_bench.py", "--size", *map(str, vel_size), "--no-cpu", "--no-csr", "--reps", "2",
